@@ -1,0 +1,995 @@
+// b200m_api.cu -- C-ABI of libb200master.so (include/b200_master.h): handle, host-side
+// filter design, plan upload, batch orchestration and the stage-level entry points.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <complex>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <tuple>
+#include <vector>
+
+#include "../../include/b200_master.h"
+#include "b200m_kernels.cuh"
+
+using namespace b200m;
+
+// ------------------------------------------------------------------------------------
+struct ProfRec { int name; cudaEvent_t a, b; };
+
+struct b200m_handle {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    // scratch arena
+    char *ws = nullptr;
+    size_t ws_cap = 0, ws_used = 0;
+    int64_t ws_limit = (int64_t)64 << 30;
+    // plan cache
+    std::vector<b200m_plan> plans_key;
+    std::vector<PlanDev> plans_host;
+    PlanDev *d_plans = nullptr;
+    size_t d_plans_cap = 0;
+    std::map<std::tuple<double, double, double, double>, CurveEntry *> curves;
+    // pinned staging for descriptors / small results
+    char *pin = nullptr;
+    size_t pin_cap = 0;
+    // profiling
+    bool profiling = false;
+    std::vector<std::string> prof_names;
+    std::vector<ProfRec> prof_recs;
+    std::vector<cudaEvent_t> ev_pool;
+    std::map<std::string, std::pair<double, int64_t>> prof_acc;
+    int64_t launches = 0;
+};
+
+static std::string g_create_err;
+
+static int fail(b200m_handle *h, int code, const char *fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (h) h->err = buf; else g_create_err = buf;
+    return code;
+}
+
+#define CK(call)                                                                          \
+    do {                                                                                  \
+        cudaError_t e_ = (call);                                                          \
+        if (e_ != cudaSuccess)                                                            \
+            return fail(h, B200M_ERR_CUDA, "%s failed: %s (%s:%d)", #call,                \
+                        cudaGetErrorString(e_), __FILE__, __LINE__);                      \
+    } while (0)
+
+// ---- profiling: CUDA events around every launch on the handle's stream ----------------
+static int prof_name_id(b200m_handle *h, const char *name)
+{
+    for (size_t i = 0; i < h->prof_names.size(); ++i)
+        if (h->prof_names[i] == name) return (int)i;
+    h->prof_names.push_back(name);
+    return (int)h->prof_names.size() - 1;
+}
+
+static cudaEvent_t prof_event(b200m_handle *h)
+{
+    if (!h->ev_pool.empty()) { cudaEvent_t e = h->ev_pool.back(); h->ev_pool.pop_back(); return e; }
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    return e;
+}
+
+struct LaunchScope {
+    b200m_handle *h; ProfRec r; bool on;
+    LaunchScope(b200m_handle *h_, const char *name) : h(h_), on(h_->profiling)
+    {
+        ++h->launches;
+        if (on) { r.name = prof_name_id(h, name); r.a = prof_event(h); r.b = prof_event(h); cudaEventRecord(r.a, h->stream); }
+    }
+    ~LaunchScope() { if (on) { cudaEventRecord(r.b, h->stream); h->prof_recs.push_back(r); } }
+};
+#define LAUNCH(name, ...) do { LaunchScope ls_(h, name); __VA_ARGS__; } while (0)
+
+static int prof_collect(b200m_handle *h)
+{
+    if (h->prof_recs.empty()) return B200M_OK;
+    CK(cudaStreamSynchronize(h->stream));
+    for (auto &r : h->prof_recs) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, r.a, r.b);
+        auto &acc = h->prof_acc[h->prof_names[r.name]];
+        acc.first += ms; acc.second += 1;
+        h->ev_pool.push_back(r.a); h->ev_pool.push_back(r.b);
+    }
+    h->prof_recs.clear();
+    return B200M_OK;
+}
+
+// ---- arena ---------------------------------------------------------------------------
+static int ws_reserve(b200m_handle *h, size_t bytes)
+{
+    if (bytes <= h->ws_cap) return B200M_OK;
+    CK(cudaStreamSynchronize(h->stream));
+    if (h->ws) { cudaFree(h->ws); h->ws = nullptr; h->ws_cap = 0; }
+    size_t want = bytes + (bytes >> 3);
+    if (cudaMalloc(&h->ws, want) != cudaSuccess) {
+        cudaGetLastError();
+        want = bytes;
+        if (cudaMalloc(&h->ws, want) != cudaSuccess) {
+            cudaGetLastError();
+            return fail(h, B200M_ERR_NOMEM, "cudaMalloc of %zu workspace bytes failed", bytes);
+        }
+    }
+    h->ws_cap = want;
+    return B200M_OK;
+}
+
+struct Arena {
+    char *base; size_t used = 0;
+    explicit Arena(char *b) : base(b) {}
+    template <typename T> T *take(size_t n)
+    {
+        used = (used + 255) & ~(size_t)255;
+        T *p = reinterpret_cast<T *>(base + used);
+        used += n * sizeof(T);
+        return p;
+    }
+};
+
+static int pin_reserve(b200m_handle *h, size_t bytes)
+{
+    if (bytes <= h->pin_cap) return B200M_OK;
+    CK(cudaStreamSynchronize(h->stream));
+    if (h->pin) cudaFreeHost(h->pin);
+    h->pin = nullptr; h->pin_cap = 0;
+    CK(cudaMallocHost(&h->pin, bytes + 4096));
+    h->pin_cap = bytes + 4096;
+    return B200M_OK;
+}
+
+// ------------------------------------------------------------------------------------
+// Host-side design
+// ------------------------------------------------------------------------------------
+static void build_sectab(const b200m_biquad &q, SecTab &T)
+{
+    typedef long double ld;
+    std::memset(&T, 0, sizeof T);
+    T.b0 = q.b0; T.b1 = q.b1; T.b2 = q.b2; T.a1 = q.a1; T.a2 = q.a2;
+    const ld A[4] = {-(ld)q.a1, 1.0L, -(ld)q.a2, 0.0L};
+    auto mm = [](const ld *X, const ld *Y, ld *Z) {
+        ld r[4] = {X[0] * Y[0] + X[1] * Y[2], X[0] * Y[1] + X[1] * Y[3],
+                   X[2] * Y[0] + X[3] * Y[2], X[2] * Y[1] + X[3] * Y[3]};
+        for (int i = 0; i < 4; ++i) Z[i] = r[i];
+    };
+    ld v[2] = {(ld)q.b1 - (ld)q.a1 * (ld)q.b0, (ld)q.b2 - (ld)q.a2 * (ld)q.b0};
+    for (int n = SEG - 1; n >= 0; --n) {
+        T.g[n][0] = (double)v[0]; T.g[n][1] = (double)v[1];
+        ld w[2] = {A[0] * v[0] + A[1] * v[1], A[2] * v[0] + A[3] * v[1]};
+        v[0] = w[0]; v[1] = w[1];
+    }
+    ld AL[4] = {1, 0, 0, 1};
+    for (int n = 0; n < SEG; ++n) mm(AL, A, AL);
+    ld Pk[4] = {AL[0], AL[1], AL[2], AL[3]};
+    for (int k = 0; k < 5; ++k) {
+        for (int i = 0; i < 4; ++i) T.P[k][i] = (double)Pk[i];
+        mm(Pk, Pk, Pk);
+    }
+    for (int i = 0; i < 4; ++i) T.PW[i] = (double)Pk[i];
+    ld Qj[4] = {1, 0, 0, 1};
+    for (int j = 0; j < 32; ++j) {
+        for (int i = 0; i < 4; ++i) T.Q[j][i] = (double)Qj[i];
+        mm(Qj, AL, Qj);
+    }
+}
+
+static const double kPi = 3.14159265358979323846;
+
+// ENG:170-182 (doubled angle w = 2*pi*f/nyquist; `gain` used as RBJ's A)
+static bool design_shelf(double rate, double f, double db, bool low, double qf, b200m_biquad *o)
+{
+    if (db == 0) return false;
+    const double wn = f / (0.5 * rate), g = std::pow(10.0, db / 20.0), w = wn * 2 * kPi;
+    const double alpha = std::sin(w) / (2.0 * qf), c = std::cos(w), rt = 2 * std::sqrt(g) * alpha;
+    double b0, b1, b2, a0, a1, a2;
+    if (low) {
+        b0 = g * ((g + 1) - (g - 1) * c + rt); b1 = 2 * g * ((g - 1) - (g + 1) * c); b2 = g * ((g + 1) - (g - 1) * c - rt);
+        a0 = (g + 1) + (g - 1) * c + rt; a1 = -2 * ((g - 1) + (g + 1) * c); a2 = (g + 1) + (g - 1) * c - rt;
+    } else {
+        b0 = g * ((g + 1) + (g - 1) * c + rt); b1 = -2 * g * ((g - 1) + (g + 1) * c); b2 = g * ((g + 1) + (g - 1) * c - rt);
+        a0 = (g + 1) - (g - 1) * c + rt; a1 = 2 * ((g - 1) - (g + 1) * c); a2 = (g + 1) - (g - 1) * c - rt;
+    }
+    *o = {b0 / a0, b1 / a0, b2 / a0, a1 / a0, a2 / a0};
+    return true;
+}
+
+// ENG:185-193
+static bool design_peak(double rate, double f, double db, double qf, b200m_biquad *o)
+{
+    if (db == 0) return false;
+    const double wn = f / (0.5 * rate), g = std::pow(10.0, db / 20.0), w = wn * 2 * kPi;
+    const double alpha = std::sin(w) / (2.0 * qf);
+    const double b0 = 1 + alpha * g, b1 = -2 * std::cos(w), b2 = 1 - alpha * g;
+    const double a0 = 1 + alpha / g, a1 = -2 * std::cos(w), a2 = 1 - alpha / g;
+    *o = {b0 / a0, b1 / a0, b2 / a0, a1 / a0, a2 / a0};
+    return true;
+}
+
+// scipy.signal.butter(4, fc, btype, fs=rate, output='sos'): buttap -> lp2lp/lp2hp ->
+// bilinear -> zpk2sos (pairing 'nearest': sections ordered with the poles closest to the
+// unit circle last, overall gain on the first section).
+static void design_butter4(double rate, double fc, bool highpass, b200m_biquad out[2])
+{
+    typedef std::complex<double> cd;
+    const double wn = 2.0 * fc / rate, fs = 2.0;
+    const double warped = 2 * fs * std::tan(kPi * wn / fs);
+    cd p[4];
+    double k = 1.0;
+    for (int i = 0; i < 4; ++i) {
+        const double m = -3 + 2 * i;
+        p[i] = -std::exp(cd(0, kPi * m / 8.0));
+    }
+    cd z[4];
+    if (!highpass) {
+        for (int i = 0; i < 4; ++i) p[i] *= warped;
+        k *= std::pow(warped, 4);
+    } else {
+        cd prod(1, 0);
+        for (int i = 0; i < 4; ++i) prod *= -p[i];
+        for (int i = 0; i < 4; ++i) { p[i] = warped / p[i]; z[i] = 0; }
+        k *= (cd(1, 0) / prod).real();
+    }
+    const double fs2 = 2.0 * fs;
+    cd num(1, 0), den(1, 0);
+    if (highpass) for (int i = 0; i < 4; ++i) num *= (fs2 - z[i]);
+    for (int i = 0; i < 4; ++i) den *= (fs2 - p[i]);
+    cd pz[4];
+    for (int i = 0; i < 4; ++i) pz[i] = (fs2 + p[i]) / (fs2 - p[i]);
+    k *= (num / den).real();
+    // conjugate pairs: (0,3) and (1,2) by construction of buttap
+    double a1[2], a2[2], rad[2];
+    const int pair[2][2] = {{0, 3}, {1, 2}};
+    for (int s = 0; s < 2; ++s) {
+        const cd q = pz[pair[s][0]];
+        a1[s] = -2.0 * q.real();
+        a2[s] = std::norm(q);
+        rad[s] = std::abs(q);
+    }
+    const int first = rad[0] <= rad[1] ? 0 : 1, second = 1 - first;
+    const double zb1 = highpass ? -2.0 : 2.0;
+    out[0] = {k, k * zb1, k, a1[first], a2[first]};
+    out[1] = {1.0, zb1, 1.0, a1[second], a2[second]};
+}
+
+// pyloudnorm IIRfilter coefficients of the K-weighting pre-filter
+static void design_kweight(double rate, b200m_biquad out[2])
+{
+    {
+        const double G = 4.0, Q = 1.0 / std::sqrt(2.0), fc = 1500.0;
+        const double A = std::pow(10.0, G / 40.0), w0 = 2.0 * kPi * (fc / rate);
+        const double alpha = std::sin(w0) / (2.0 * Q), c = std::cos(w0), rt = 2 * std::sqrt(A) * alpha;
+        const double b0 = A * ((A + 1) + (A - 1) * c + rt), b1 = -2 * A * ((A - 1) + (A + 1) * c), b2 = A * ((A + 1) + (A - 1) * c - rt);
+        const double a0 = (A + 1) - (A - 1) * c + rt, a1 = 2 * ((A - 1) - (A + 1) * c), a2 = (A + 1) - (A - 1) * c - rt;
+        out[0] = {b0 / a0, b1 / a0, b2 / a0, a1 / a0, a2 / a0};
+    }
+    {
+        const double Q = 0.5, fc = 38.0;
+        const double w0 = 2.0 * kPi * (fc / rate), alpha = std::sin(w0) / (2.0 * Q), c = std::cos(w0);
+        const double b0 = (1 + c) / 2, b1 = -(1 + c), b2 = (1 + c) / 2, a0 = 1 + alpha, a1 = -2 * c, a2 = 1 - alpha;
+        out[1] = {b0 / a0, b1 / a0, b2 / a0, a1 / a0, a2 / a0};
+    }
+}
+
+static void design_band(double rate, double thr_db, double ratio, double attack_ms, double release_ms, b200m_band *b)
+{
+    b->thresh_rms = 32768.0 * std::pow(10.0, thr_db / 20.0);
+    b->attack_frames = attack_ms * (rate / 1000.0);
+    b->release_frames = release_ms * (rate / 1000.0);
+    b->slope = 1 - (1.0 / ratio);
+    b->look_frames = (int32_t)b->attack_frames;
+    b->reserved = 0;
+}
+
+extern "C" int b200m_plan_from_settings(const b200m_settings *s, int sample_rate, int channels, b200m_plan *p)
+{
+    if (!s || !p || sample_rate <= 0 || (channels != 1 && channels != 2)) return B200M_ERR_INVALID;
+    std::memset(p, 0, sizeof *p);
+    p->sample_rate = sample_rate; p->channels = channels;
+    p->sat_on = s->saturation != 0;
+    const double mix = (s->saturation / 100.0) * (s->saturation / 100.0);
+    p->sat_clean = (float)(1 - mix); p->sat_mix = (float)mix; p->sat_drive = (float)(1 + mix * 4);
+    int n = 0;
+    b200m_biquad q;
+    if (design_shelf(sample_rate, 250, s->bass_boost, true, 0.707, &q)) p->eq[n++] = q;
+    if (design_peak(sample_rate, 1000, -s->mid_cut, 1.0, &q)) p->eq[n++] = q;
+    if (design_peak(sample_rate, 4000, s->presence_boost, 1.0, &q)) p->eq[n++] = q;
+    if (design_shelf(sample_rate, 8000, s->treble_boost, false, 0.707, &q)) p->eq[n++] = q;
+    p->n_eq = n;
+    p->width_on = (channels == 2) && (s->width != 1.0);
+    p->width = s->width;
+    p->multiband = s->multiband != 0;
+    if (p->multiband) {
+        if (s->low_ratio == 0 || s->mid_ratio == 0 || s->high_ratio == 0) return B200M_ERR_INVALID;
+        if (!(4000.0 < 0.5 * sample_rate)) return B200M_ERR_INVALID;   // scipy butter raises too
+        design_butter4(sample_rate, 250, false, p->lp);
+        design_butter4(sample_rate, 4000, true, p->hp);
+        design_band(sample_rate, s->low_thresh, s->low_ratio, 10.0, 200.0, &p->band[0]);
+        design_band(sample_rate, s->mid_thresh, s->mid_ratio, 5.0, 150.0, &p->band[1]);
+        design_band(sample_rate, s->high_thresh, s->high_ratio, 1.0, 50.0, &p->band[2]);
+    }
+    design_kweight(sample_rate, p->kw);
+    p->has_lufs = s->has_lufs != 0;
+    p->lufs = s->lufs;
+    return B200M_OK;
+}
+
+// ------------------------------------------------------------------------------------
+// Plan upload (device tables), cached across calls with identical plans
+// ------------------------------------------------------------------------------------
+static int get_curve(b200m_handle *h, const b200m_band &b, const CurveEntry **out)
+{
+    auto key = std::make_tuple(b.thresh_rms, b.attack_frames, b.release_frames, b.slope);
+    auto it = h->curves.find(key);
+    if (it != h->curves.end()) { *out = it->second; return B200M_OK; }
+    // pydub: db = 20 * math.log(rms / thresh_rms, 10) = 20 * (log(x) / log(10));
+    //        max_att = (1 - 1/ratio) * max(db, 0); inc = max_att / attack; dec = max_att / release
+    std::vector<CurveEntry> tab(CURVE_N);
+    const double l10 = std::log(10.0);
+    for (int r = 0; r < CURVE_N; ++r) {
+        double over = 0.0;
+        if (r != 0) {
+            const double db = 20 * (std::log((double)r / b.thresh_rms) / l10);
+            over = db > 0 ? db : 0.0;
+        }
+        const double M = b.slope * over;
+        tab[r] = {M, M / b.attack_frames, M / b.release_frames, 0.0};
+    }
+    CurveEntry *d = nullptr;
+    CK(cudaMalloc(&d, CURVE_N * sizeof(CurveEntry)));
+    CK(cudaMemcpy(d, tab.data(), CURVE_N * sizeof(CurveEntry), cudaMemcpyHostToDevice));
+    h->curves[key] = d;
+    *out = d;
+    return B200M_OK;
+}
+
+static int ensure_plans(b200m_handle *h, const b200m_plan *plans, int n)
+{
+    if ((int)h->plans_key.size() == n && n > 0 &&
+        std::memcmp(h->plans_key.data(), plans, n * sizeof(b200m_plan)) == 0)
+        return B200M_OK;
+    CK(cudaStreamSynchronize(h->stream));   // previous launches may still read d_plans
+    h->plans_host.assign(n, PlanDev());
+    for (int i = 0; i < n; ++i) {
+        const b200m_plan &p = plans[i];
+        PlanDev &d = h->plans_host[i];
+        std::memset(&d, 0, sizeof d);
+        if (p.channels != 1 && p.channels != 2) return fail(h, B200M_ERR_INVALID, "plan %d: channels must be 1 or 2", i);
+        if (p.n_eq < 0 || p.n_eq > 4) return fail(h, B200M_ERR_INVALID, "plan %d: n_eq out of range", i);
+        d.rate = p.sample_rate; d.channels = p.channels; d.sat_on = p.sat_on; d.n_eq = p.n_eq;
+        d.width_on = p.width_on && p.channels == 2; d.multiband = p.multiband; d.has_lufs = p.has_lufs;
+        d.sat_clean = p.sat_clean; d.sat_mix = p.sat_mix; d.sat_drive = p.sat_drive;
+        d.width = p.width; d.lufs = p.lufs;
+        for (int s = 0; s < p.n_eq; ++s) build_sectab(p.eq[s], d.eq[s]);
+        build_sectab(p.kw[0], d.kw[0]);
+        build_sectab(p.kw[1], d.kw[1]);
+        if (p.multiband) {
+            for (int s = 0; s < 2; ++s) { build_sectab(p.lp[s], d.lp[s]); build_sectab(p.hp[s], d.hp[s]); }
+            for (int b = 0; b < 3; ++b) {
+                const b200m_band &bb = p.band[b];
+                if (bb.look_frames < 0 || bb.look_frames > 8192)
+                    return fail(h, B200M_ERR_INVALID, "plan %d band %d: look_frames %d unsupported", i, b, bb.look_frames);
+                d.band[b] = {bb.thresh_rms, bb.attack_frames, bb.release_frames, bb.slope, bb.look_frames,
+                             (int32_t)std::floor(std::min(bb.thresh_rms, 1e9))};
+                int rc = get_curve(h, bb, &d.curve[b]);
+                if (rc) return rc;
+            }
+        }
+    }
+    if ((size_t)n > h->d_plans_cap) {
+        if (h->d_plans) cudaFree(h->d_plans);
+        h->d_plans = nullptr; h->d_plans_cap = 0;
+        CK(cudaMalloc(&h->d_plans, n * sizeof(PlanDev)));
+        h->d_plans_cap = n;
+    }
+    CK(cudaMemcpyAsync(h->d_plans, h->plans_host.data(), n * sizeof(PlanDev), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    h->plans_key.assign(plans, plans + n);
+    return B200M_OK;
+}
+
+// ------------------------------------------------------------------------------------
+// lifetime
+// ------------------------------------------------------------------------------------
+template <typename K> static cudaError_t allow_smem(K kernel, size_t bytes)
+{
+    return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+}
+
+static size_t detect_smem_bytes(int H)
+{
+    const int total = H + DT;
+    int K = (total + DNT) / DNT;
+    K |= 1;
+    return (size_t)(total + 1) * 8 + (size_t)DNT * K * 4;
+}
+
+extern "C" int b200m_abi_version(void) { return B200M_ABI_VERSION; }
+
+extern "C" int b200m_create(int device, b200m_handle **out)
+{
+    b200m_handle *h = nullptr;
+    if (!out) return B200M_ERR_INVALID;
+    *out = nullptr;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) {
+        cudaGetLastError();
+        return fail(nullptr, B200M_ERR_CUDA, "no CUDA device: libb200master has no CPU fallback");
+    }
+    if (device < 0 || device >= count) return fail(nullptr, B200M_ERR_INVALID, "device %d out of range (0..%d)", device, count - 1);
+    cudaError_t e = cudaSetDevice(device);
+    if (e != cudaSuccess) return fail(nullptr, B200M_ERR_CUDA, "cudaSetDevice(%d): %s", device, cudaGetErrorString(e));
+    h = new b200m_handle();
+    h->device = device;
+    e = allow_smem(k_chain<1>, chain_smem_bytes<1>());
+    if (e == cudaSuccess) e = allow_smem(k_chain<2>, chain_smem_bytes<2>());
+    if (e == cudaSuccess) e = allow_smem(k_detect<1>, detect_smem_bytes(8192));
+    if (e == cudaSuccess) e = allow_smem(k_detect<2>, detect_smem_bytes(8192));
+    if (e == cudaSuccess) e = allow_smem(k_kweight<1, int16_t>, kweight_smem_bytes());
+    if (e == cudaSuccess) e = allow_smem(k_kweight<2, int16_t>, kweight_smem_bytes());
+    if (e == cudaSuccess) e = allow_smem(k_kweight<1, float>, kweight_smem_bytes());
+    if (e == cudaSuccess) e = allow_smem(k_sosfilt<float>, sosfilt_smem_bytes());
+    if (e == cudaSuccess) e = allow_smem(k_sosfilt<double>, sosfilt_smem_bytes());
+    if (e != cudaSuccess) {
+        fail(nullptr, B200M_ERR_CUDA, "kernel attribute set-up failed (is this an sm_100a device?): %s", cudaGetErrorString(e));
+        delete h;
+        return B200M_ERR_CUDA;
+    }
+    *out = h;
+    return B200M_OK;
+}
+
+extern "C" void b200m_destroy(b200m_handle *h)
+{
+    if (!h) return;
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream);
+    if (h->ws) cudaFree(h->ws);
+    if (h->d_plans) cudaFree(h->d_plans);
+    if (h->pin) cudaFreeHost(h->pin);
+    for (auto &kv : h->curves) cudaFree(kv.second);
+    for (auto &r : h->prof_recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+    for (auto e : h->ev_pool) cudaEventDestroy(e);
+    delete h;
+}
+
+extern "C" const char *b200m_last_error(const b200m_handle *h) { return h ? h->err.c_str() : g_create_err.c_str(); }
+
+extern "C" int b200m_set_stream(b200m_handle *h, void *s)
+{
+    if (!h) return B200M_ERR_INVALID;
+    CK(cudaStreamSynchronize(h->stream));
+    h->stream = (cudaStream_t)s;
+    return B200M_OK;
+}
+
+extern "C" int b200m_synchronize(b200m_handle *h)
+{
+    if (!h) return B200M_ERR_INVALID;
+    CK(cudaSetDevice(h->device));
+    CK(cudaStreamSynchronize(h->stream));
+    return B200M_OK;
+}
+
+extern "C" int b200m_set_workspace_limit(b200m_handle *h, int64_t bytes)
+{
+    if (!h || bytes < (1 << 20)) return B200M_ERR_INVALID;
+    h->ws_limit = bytes;
+    return B200M_OK;
+}
+
+extern "C" int64_t b200m_launch_count(const b200m_handle *h) { return h ? h->launches : 0; }
+
+extern "C" int b200m_set_profiling(b200m_handle *h, int on)
+{
+    if (!h) return B200M_ERR_INVALID;
+    int rc = prof_collect(h);
+    h->profiling = on != 0;
+    return rc;
+}
+
+extern "C" int b200m_kernel_time_ms(b200m_handle *h, const char *kernel, double *total_ms, int64_t *launches)
+{
+    if (!h || !kernel) return B200M_ERR_INVALID;
+    int rc = prof_collect(h);
+    if (rc) return rc;
+    auto it = h->prof_acc.find(kernel);
+    if (total_ms) *total_ms = it == h->prof_acc.end() ? 0.0 : it->second.first;
+    if (launches) *launches = it == h->prof_acc.end() ? 0 : it->second.second;
+    return B200M_OK;
+}
+
+extern "C" int b200m_reset_profile(b200m_handle *h)
+{
+    if (!h) return B200M_ERR_INVALID;
+    int rc = prof_collect(h);
+    h->prof_acc.clear();
+    return rc;
+}
+
+// ------------------------------------------------------------------------------------
+// The chain on device buffers (shared by master_batch and the stage entry points)
+// ------------------------------------------------------------------------------------
+struct Group {
+    int ch = 2;
+    int n_streams = 0, n_tracks = 0;
+    int max_stream_frames = 0;
+    int64_t max_track_frames = 0;
+    int max_blocks = 0;
+    int max_look = 0;
+    bool any_multiband = false, any_lufs = false;
+    const StreamDesc *d_streams = nullptr;
+    const TrackDesc *d_tracks = nullptr;
+};
+
+static int launch_compressor(b200m_handle *h, const Group &g, const BandPtrs &bp, int nbands, int band_base, int16_t *d_proc)
+{
+    const dim3 gd((g.max_stream_frames + DT - 1) / DT, g.n_streams, nbands);
+    const size_t smem = detect_smem_bytes(g.max_look);
+    if (g.ch == 2) LAUNCH("k_detect", k_detect<2><<<gd, DNT, smem, h->stream>>>(g.d_streams, h->d_plans, bp, band_base));
+    else           LAUNCH("k_detect", k_detect<1><<<gd, DNT, smem, h->stream>>>(g.d_streams, h->d_plans, bp, band_base));
+    const int chains = g.n_streams * nbands;
+    LAUNCH("k_recur", k_recur<<<(chains + 31) / 32, 32, 0, h->stream>>>(g.d_streams, h->d_plans, g.n_streams, nbands, band_base, bp));
+    const dim3 ga((g.max_stream_frames + 255) / 256, g.n_streams);
+    if (g.ch == 2) LAUNCH("k_apply", k_apply<2><<<ga, 256, 0, h->stream>>>(g.d_streams, h->d_plans, bp, nbands, band_base, d_proc));
+    else           LAUNCH("k_apply", k_apply<1><<<ga, 256, 0, h->stream>>>(g.d_streams, h->d_plans, bp, nbands, band_base, d_proc));
+    CK(cudaGetLastError());
+    return B200M_OK;
+}
+
+static int launch_loudness(b200m_handle *h, const Group &g, const int16_t *d_proc, const float *d_mono,
+                           float *d_kw, double *d_z, double *d_zsel, double2 *d_loud)
+{
+    if (g.any_lufs) {
+        if (d_mono)         LAUNCH("k_kweight", k_kweight<1, float><<<g.n_tracks, KNT, kweight_smem_bytes(), h->stream>>>(d_mono, g.d_tracks, h->d_plans, d_kw));
+        else if (g.ch == 2) LAUNCH("k_kweight", k_kweight<2, int16_t><<<g.n_tracks, KNT, kweight_smem_bytes(), h->stream>>>(d_proc, g.d_tracks, h->d_plans, d_kw));
+        else                LAUNCH("k_kweight", k_kweight<1, int16_t><<<g.n_tracks, KNT, kweight_smem_bytes(), h->stream>>>(d_proc, g.d_tracks, h->d_plans, d_kw));
+        const dim3 gb((g.max_blocks + 127) / 128, g.n_tracks);
+        if (g.max_blocks > 0) LAUNCH("k_blocks", k_blocks<<<gb, 128, 0, h->stream>>>(d_kw, g.d_tracks, h->d_plans, d_z));
+    }
+    LAUNCH("k_gate", k_gate<<<g.n_tracks, 32, 0, h->stream>>>(g.d_tracks, h->d_plans, d_z, d_zsel, d_loud));
+    CK(cudaGetLastError());
+    return B200M_OK;
+}
+
+static int num_blocks(int64_t frames, int rate)
+{
+    // pyloudnorm: T = numSamples / rate; numBlocks = int(np.round((T - T_g) / (T_g * step)) + 1)
+    const double T = (double)frames / (double)rate, Tg = 0.4, step = 0.25;
+    const double nb = std::nearbyint((T - Tg) / (Tg * step)) + 1;
+    return nb < 0 ? 0 : (int)nb;
+}
+
+// ------------------------------------------------------------------------------------
+// b200m_master_batch
+// ------------------------------------------------------------------------------------
+static int run_group(b200m_handle *h, const int16_t *pcm_in, bool in_dev, int t_begin, int t_end,
+                     const int64_t *in_offsets, const int64_t *in_frames, const int64_t *out_frames,
+                     const b200m_plan *plans, const int32_t *plan_index,
+                     int16_t *pcm_out, bool out_dev, int64_t out_base,
+                     double *loudness_out, double *gain_out)
+{
+    const int ch = plans[0].channels, rate = plans[0].sample_rate;
+    const int64_t chunk = 30LL * rate;          // ENG:48: 30 000 ms -> int(ms * rate / 1000) frames
+    Group g;
+    g.ch = ch;
+    g.n_tracks = t_end - t_begin;
+    std::vector<StreamDesc> streams;
+    std::vector<TrackDesc> tracks(g.n_tracks);
+    int64_t F = 0, in_total = 0, zoff = 0;
+    for (int t = t_begin; t < t_end; ++t) {
+        const b200m_plan &p = plans[plan_index[t]];
+        TrackDesc &td = tracks[t - t_begin];
+        td.off = F; td.frames = out_frames[t]; td.plan = plan_index[t];
+        td.nblocks = p.has_lufs ? num_blocks(out_frames[t], rate) : 0;
+        td.zoff = zoff; zoff += td.nblocks;
+        g.max_blocks = std::max(g.max_blocks, td.nblocks);
+        g.max_track_frames = std::max(g.max_track_frames, td.frames);
+        g.any_multiband |= p.multiband != 0;
+        g.any_lufs |= p.has_lufs != 0;
+        if (p.multiband) for (int b = 0; b < 3; ++b) g.max_look = std::max(g.max_look, p.band[b].look_frames);
+        const int64_t in_base = in_dev ? in_offsets[t] : in_total;
+        for (int64_t s = 0; s < out_frames[t]; s += chunk) {
+            StreamDesc sd;
+            sd.in_off = in_base + s; sd.out_off = F + s;
+            sd.out_frames = (int32_t)std::min(chunk, out_frames[t] - s);
+            sd.in_frames = (int32_t)std::max<int64_t>(0, std::min<int64_t>(sd.out_frames, in_frames[t] - s));
+            sd.plan = plan_index[t]; sd.track = t - t_begin;
+            g.max_stream_frames = std::max(g.max_stream_frames, sd.out_frames);
+            streams.push_back(sd);
+        }
+        F += out_frames[t];
+        in_total += in_frames[t];
+    }
+    g.n_streams = (int)streams.size();
+    if (F == 0) {
+        for (int t = t_begin; t < t_end; ++t) {
+            if (loudness_out) loudness_out[t] = NAN;
+            if (gain_out) gain_out[t] = 1.0;
+        }
+        return B200M_OK;
+    }
+
+    // ---- workspace ---------------------------------------------------------------
+    const size_t desc_bytes = streams.size() * sizeof(StreamDesc) + tracks.size() * sizeof(TrackDesc);
+    size_t need = 4096 + desc_bytes + (size_t)g.n_tracks * 16 + (size_t)F * ch * 2 /*proc*/ + (size_t)F * 4 /*kw*/ +
+                  (size_t)zoff * 16 + 16 * 256;
+    if (!in_dev) need += (size_t)in_total * ch * 2;
+    if (!out_dev) need += (size_t)F * ch * 2;
+    if (g.any_multiband) need += (size_t)F * (3 * ch * 2 + 3 * 2 + 3 * 8) + 16 * 256;
+    int rc = ws_reserve(h, need);
+    if (rc) return rc;
+    rc = pin_reserve(h, desc_bytes + (size_t)g.n_tracks * 16);
+    if (rc) return rc;
+    Arena A(h->ws);
+    StreamDesc *d_streams = A.take<StreamDesc>(streams.size());
+    TrackDesc *d_tracks = A.take<TrackDesc>(tracks.size());
+    double2 *d_loud = A.take<double2>(g.n_tracks);
+    int16_t *d_proc = A.take<int16_t>((size_t)F * ch);
+    float *d_kw = A.take<float>(F);
+    double *d_z = A.take<double>(zoff + 1);
+    double *d_zsel = A.take<double>(zoff + 1);
+    int16_t *d_in = nullptr, *d_out = nullptr;
+    if (!in_dev) d_in = A.take<int16_t>((size_t)in_total * ch);
+    if (!out_dev) d_out = A.take<int16_t>((size_t)F * ch);
+    BandPtrs bp;
+    std::memset(&bp, 0, sizeof bp);
+    if (g.any_multiband) {
+        for (int b = 0; b < 3; ++b) bp.band[b] = A.take<int16_t>((size_t)F * ch);
+        for (int b = 0; b < 3; ++b) bp.rms[b] = A.take<uint16_t>(F);
+        for (int b = 0; b < 3; ++b) bp.att[b] = A.take<double>(F);
+    }
+    // descriptors: pinned staging -> device
+    CK(cudaStreamSynchronize(h->stream));       // pinned staging may still be in flight
+    std::memcpy(h->pin, streams.data(), streams.size() * sizeof(StreamDesc));
+    std::memcpy(h->pin + streams.size() * sizeof(StreamDesc), tracks.data(), tracks.size() * sizeof(TrackDesc));
+    CK(cudaMemcpyAsync(d_streams, h->pin, streams.size() * sizeof(StreamDesc), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(d_tracks, h->pin + streams.size() * sizeof(StreamDesc), tracks.size() * sizeof(TrackDesc),
+                       cudaMemcpyHostToDevice, h->stream));
+    g.d_streams = d_streams; g.d_tracks = d_tracks;
+
+    // ---- input staging -------------------------------------------------------------
+    const int16_t *d_src = pcm_in;
+    if (!in_dev) {
+        int64_t pos = 0;
+        for (int t = t_begin; t < t_end; ++t) {     // one cudaMemcpyAsync per track
+            if (in_frames[t] > 0)
+                CK(cudaMemcpyAsync(d_in + pos * ch, pcm_in + in_offsets[t] * ch, (size_t)in_frames[t] * ch * 2,
+                                   cudaMemcpyHostToDevice, h->stream));
+            pos += in_frames[t];
+        }
+        d_src = d_in;
+    }
+    int16_t *d_dst = out_dev ? pcm_out + out_base * ch : d_out;
+
+    // ---- kernels -------------------------------------------------------------------
+    if (ch == 2) LAUNCH("k_chain", k_chain<2><<<g.n_streams, NSEG * 2, chain_smem_bytes<2>(), h->stream>>>(d_src, d_streams, h->d_plans, d_proc, bp));
+    else         LAUNCH("k_chain", k_chain<1><<<g.n_streams, NSEG * 1, chain_smem_bytes<1>(), h->stream>>>(d_src, d_streams, h->d_plans, d_proc, bp));
+    CK(cudaGetLastError());
+    if (g.any_multiband) { rc = launch_compressor(h, g, bp, 3, 0, d_proc); if (rc) return rc; }
+    rc = launch_loudness(h, g, d_proc, nullptr, d_kw, d_z, d_zsel, d_loud);
+    if (rc) return rc;
+    const dim3 gf((unsigned)std::min<int64_t>((g.max_track_frames + 255) / 256, 8192), g.n_tracks);
+    if (ch == 2) LAUNCH("k_final", k_final<2><<<gf, 256, 0, h->stream>>>(d_proc, d_tracks, h->d_plans, d_loud, d_dst));
+    else         LAUNCH("k_final", k_final<1><<<gf, 256, 0, h->stream>>>(d_proc, d_tracks, h->d_plans, d_loud, d_dst));
+    CK(cudaGetLastError());
+
+    // ---- results -------------------------------------------------------------------
+    if (!out_dev) CK(cudaMemcpyAsync(pcm_out + out_base * ch, d_out, (size_t)F * ch * 2, cudaMemcpyDeviceToHost, h->stream));
+    if (loudness_out || gain_out) {
+        double2 *hl = reinterpret_cast<double2 *>(h->pin + desc_bytes);
+        CK(cudaMemcpyAsync(hl, d_loud, (size_t)g.n_tracks * 16, cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        for (int t = t_begin; t < t_end; ++t) {
+            if (loudness_out) loudness_out[t] = hl[t - t_begin].x;
+            if (gain_out) gain_out[t] = hl[t - t_begin].y;
+        }
+    } else if (!out_dev) {
+        CK(cudaStreamSynchronize(h->stream));
+    }
+    return B200M_OK;
+}
+
+extern "C" int b200m_master_batch(b200m_handle *h, const void *pcm_in, int in_on_device, int fmt, int n_tracks,
+                                  const int64_t *in_offsets, const int64_t *in_frames, const int64_t *out_frames,
+                                  const b200m_plan *plans, int n_plans, const int32_t *plan_index,
+                                  void *pcm_out, int out_on_device, double *loudness_out, double *gain_out)
+{
+    if (!h) return B200M_ERR_INVALID;
+    if (!pcm_in || !pcm_out || n_tracks <= 0 || !in_offsets || !in_frames || !out_frames || !plans || n_plans <= 0 || !plan_index)
+        return fail(h, B200M_ERR_INVALID, "b200m_master_batch: null or empty argument");
+    if (fmt != B200M_FMT_S16) return fail(h, B200M_ERR_INVALID, "b200m_master_batch: only B200M_FMT_S16 is implemented");
+    CK(cudaSetDevice(h->device));
+    const int ch = plans[0].channels, rate = plans[0].sample_rate;
+    for (int i = 0; i < n_plans; ++i)
+        if (plans[i].channels != ch || plans[i].sample_rate != rate || rate <= 0)
+            return fail(h, B200M_ERR_INVALID, "all plans of a batch must share sample rate and channel count");
+    for (int t = 0; t < n_tracks; ++t) {
+        if (plan_index[t] < 0 || plan_index[t] >= n_plans) return fail(h, B200M_ERR_INVALID, "plan_index[%d] out of range", t);
+        if (in_frames[t] < 0 || out_frames[t] < 0 || in_offsets[t] < 0) return fail(h, B200M_ERR_INVALID, "negative frame count for track %d", t);
+        if (out_frames[t] >= ((int64_t)1 << 40)) return fail(h, B200M_ERR_INVALID, "track %d too long", t);
+        // pyloudnorm valid_audio: data.shape[0] < block_size * rate -> ValueError
+        if (plans[plan_index[t]].has_lufs && (double)out_frames[t] < 0.4 * rate)
+            return fail(h, B200M_ERR_TOO_SHORT, "track %d: audio must have length greater than the block size (400 ms)", t);
+    }
+    int rc = ensure_plans(h, plans, n_plans);
+    if (rc) return rc;
+    // split into groups that fit the workspace limit
+    const double per_frame = ch * 2 * 3 + 4 + 3 * (ch * 2 + 2 + 8) + 1;
+    int t0 = 0;
+    int64_t out_base = 0;
+    while (t0 < n_tracks) {
+        int t1 = t0;
+        double bytes = 0;
+        int64_t frames = 0;
+        while (t1 < n_tracks) {
+            const double add = per_frame * (double)std::max(out_frames[t1], in_frames[t1]);
+            if (t1 > t0 && bytes + add > (double)h->ws_limit) break;
+            bytes += add; frames += out_frames[t1]; ++t1;
+        }
+        rc = run_group(h, (const int16_t *)pcm_in, in_on_device != 0, t0, t1, in_offsets, in_frames, out_frames,
+                       plans, plan_index, (int16_t *)pcm_out, out_on_device != 0, out_base, loudness_out, gain_out);
+        if (rc) return rc;
+        out_base += frames;
+        t0 = t1;
+    }
+    return B200M_OK;
+}
+
+// ------------------------------------------------------------------------------------
+// Stage-level entry points (host arrays in, host arrays out)
+// ------------------------------------------------------------------------------------
+static int grid_for(int64_t n) { return (int)std::min<int64_t>((n + 255) / 256, 148 * 16); }
+
+template <typename F>
+static int elementwise(b200m_handle *h, const void *x, size_t in_bytes, void *out, size_t out_bytes, F launch)
+{
+    if (!h) return B200M_ERR_INVALID;
+    CK(cudaSetDevice(h->device));
+    if (in_bytes == 0) return B200M_OK;
+    int rc = ws_reserve(h, in_bytes + out_bytes + 1024);
+    if (rc) return rc;
+    Arena A(h->ws);
+    char *d_in = A.take<char>(in_bytes);
+    char *d_out = A.take<char>(out_bytes);
+    CK(cudaMemcpyAsync(d_in, x, in_bytes, cudaMemcpyHostToDevice, h->stream));
+    launch(d_in, d_out);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(out, d_out, out_bytes, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return B200M_OK;
+}
+
+extern "C" int b200m_pcm16_to_float(b200m_handle *h, const int16_t *pcm, int64_t n, float *out)
+{
+    if (!h || n < 0 || (n && (!pcm || !out))) return h ? fail(h, B200M_ERR_INVALID, "pcm16_to_float: bad argument") : B200M_ERR_INVALID;
+    return elementwise(h, pcm, n * 2, out, n * 4, [&](char *di, char *dn) {
+        LAUNCH("k_pcm16_to_float", k_pcm16_to_float<<<grid_for(n), 256, 0, h->stream>>>((const int16_t *)di, n, (float *)dn));
+    });
+}
+
+extern "C" int b200m_float_to_pcm16(b200m_handle *h, const void *x, int is_f64, int64_t n, int16_t *out)
+{
+    if (!h || n < 0 || (n && (!x || !out))) return h ? fail(h, B200M_ERR_INVALID, "float_to_pcm16: bad argument") : B200M_ERR_INVALID;
+    return elementwise(h, x, n * (is_f64 ? 8 : 4), out, n * 2, [&](char *di, char *dn) {
+        if (is_f64) LAUNCH("k_float_to_pcm16", k_float_to_pcm16<double><<<grid_for(n), 256, 0, h->stream>>>((const double *)di, n, (int16_t *)dn));
+        else        LAUNCH("k_float_to_pcm16", k_float_to_pcm16<float><<<grid_for(n), 256, 0, h->stream>>>((const float *)di, n, (int16_t *)dn));
+    });
+}
+
+extern "C" int b200m_saturation(b200m_handle *h, const float *x, int64_t n, double pct, float *out)
+{
+    if (!h || n < 0 || (n && (!x || !out))) return h ? fail(h, B200M_ERR_INVALID, "saturation: bad argument") : B200M_ERR_INVALID;
+    const double mix = (pct / 100.0) * (pct / 100.0);
+    if (pct == 0) { if (out != x) std::memcpy(out, x, n * 4); return B200M_OK; }      // ENG:129 bypass
+    return elementwise(h, x, n * 4, out, n * 4, [&](char *di, char *dn) {
+        LAUNCH("k_saturation", k_saturation<<<grid_for(n), 256, 0, h->stream>>>((const float *)di, n, (float)(1 - mix), (float)mix,
+                                                                                  (float)(1 + mix * 4), (float *)dn));
+    });
+}
+
+extern "C" int b200m_stereo_width(b200m_handle *h, const void *x, int is_f64, int64_t nframes, double width, void *out)
+{
+    if (!h || nframes < 0 || (nframes && (!x || !out))) return h ? fail(h, B200M_ERR_INVALID, "stereo_width: bad argument") : B200M_ERR_INVALID;
+    const size_t bytes = (size_t)nframes * 2 * (is_f64 ? 8 : 4);
+    return elementwise(h, x, bytes, out, bytes, [&](char *di, char *dn) {
+        if (is_f64) LAUNCH("k_width", k_width<double><<<grid_for(nframes), 256, 0, h->stream>>>((const double *)di, nframes, width, (double *)dn));
+        else        LAUNCH("k_width", k_width<float><<<grid_for(nframes), 256, 0, h->stream>>>((const float *)di, nframes, width, (float *)dn));
+    });
+}
+
+extern "C" int b200m_soft_limiter(b200m_handle *h, const void *x, int is_f64, int64_t n, double thr, void *out)
+{
+    if (!h || n < 0 || (n && (!x || !out))) return h ? fail(h, B200M_ERR_INVALID, "soft_limiter: bad argument") : B200M_ERR_INVALID;
+    const size_t bytes = (size_t)n * (is_f64 ? 8 : 4);
+    return elementwise(h, x, bytes, out, bytes, [&](char *di, char *dn) {
+        if (is_f64) LAUNCH("k_limiter", k_limiter<double><<<grid_for(n), 256, 0, h->stream>>>((const double *)di, n, thr, (double *)dn));
+        else        LAUNCH("k_limiter", k_limiter<float><<<grid_for(n), 256, 0, h->stream>>>((const float *)di, n, thr, (float *)dn));
+    });
+}
+
+extern "C" int b200m_sosfilt(b200m_handle *h, const b200m_biquad *sections, int nsec, const void *x, int is_f64,
+                             int64_t nframes, int channels, double *out)
+{
+    if (!h) return B200M_ERR_INVALID;
+    if (nsec < 0 || nsec > 8 || nframes < 0 || channels < 1 || (nsec && !sections) || (nframes && (!x || !out)))
+        return fail(h, B200M_ERR_INVALID, "sosfilt: bad argument (1..8 sections supported)");
+    CK(cudaSetDevice(h->device));
+    const size_t n = (size_t)nframes * channels, esz = is_f64 ? 8 : 4;
+    if (n == 0) return B200M_OK;
+    std::vector<SecTab> tabs(std::max(nsec, 1));
+    for (int s = 0; s < nsec; ++s) build_sectab(sections[s], tabs[s]);
+    int rc = ws_reserve(h, n * esz + n * 8 + tabs.size() * sizeof(SecTab) + 1024);
+    if (rc) return rc;
+    Arena A(h->ws);
+    SecTab *d_tabs = A.take<SecTab>(tabs.size());
+    char *d_in = A.take<char>(n * esz);
+    double *d_out = A.take<double>(n);
+    CK(cudaMemcpyAsync(d_tabs, tabs.data(), tabs.size() * sizeof(SecTab), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(d_in, x, n * esz, cudaMemcpyHostToDevice, h->stream));
+    if (is_f64) LAUNCH("k_sosfilt", k_sosfilt<double><<<channels, KNT, sosfilt_smem_bytes(), h->stream>>>((const double *)d_in, nframes, channels, d_tabs, nsec, d_out));
+    else        LAUNCH("k_sosfilt", k_sosfilt<float><<<channels, KNT, sosfilt_smem_bytes(), h->stream>>>((const float *)d_in, nframes, channels, d_tabs, nsec, d_out));
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(out, d_out, n * 8, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return B200M_OK;
+}
+
+// One int16 chunk through crossover + 3 compressors + overlay (zero state): the batch
+// path with a plan stripped down to the multiband stage.
+extern "C" int b200m_multiband(b200m_handle *h, const b200m_plan *plan, const int16_t *pcm, int64_t nframes, int16_t *out)
+{
+    if (!h) return B200M_ERR_INVALID;
+    if (!plan || nframes < 0 || nframes > 0x7fffffff || (nframes && (!pcm || !out)))
+        return fail(h, B200M_ERR_INVALID, "multiband: bad argument");
+    if (nframes == 0) return B200M_OK;
+    CK(cudaSetDevice(h->device));
+    b200m_plan p = *plan;
+    p.sat_on = 0; p.n_eq = 0; p.width_on = 0; p.has_lufs = 0; p.multiband = 1;
+    int rc = ensure_plans(h, &p, 1);
+    if (rc) return rc;
+    const int ch = p.channels;
+    const size_t F = (size_t)nframes;
+    rc = ws_reserve(h, 8192 + F * ch * 2 * 5 + F * (3 * 2 + 3 * 8) + 16 * 256);
+    if (rc) return rc;
+    Arena A(h->ws);
+    StreamDesc *d_streams = A.take<StreamDesc>(1);
+    int16_t *d_in = A.take<int16_t>(F * ch);
+    int16_t *d_proc = A.take<int16_t>(F * ch);
+    BandPtrs bp;
+    for (int b = 0; b < 3; ++b) bp.band[b] = A.take<int16_t>(F * ch);
+    for (int b = 0; b < 3; ++b) bp.rms[b] = A.take<uint16_t>(F);
+    for (int b = 0; b < 3; ++b) bp.att[b] = A.take<double>(F);
+    StreamDesc sd = {0, 0, (int32_t)nframes, (int32_t)nframes, 0, 0};
+    CK(cudaMemcpyAsync(d_streams, &sd, sizeof sd, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(d_in, pcm, F * ch * 2, cudaMemcpyHostToDevice, h->stream));
+    Group g;
+    g.ch = ch; g.n_streams = 1; g.n_tracks = 1; g.max_stream_frames = (int)nframes; g.d_streams = d_streams;
+    for (int b = 0; b < 3; ++b) g.max_look = std::max(g.max_look, p.band[b].look_frames);
+    if (ch == 2) LAUNCH("k_chain", k_chain<2><<<1, NSEG * 2, chain_smem_bytes<2>(), h->stream>>>(d_in, d_streams, h->d_plans, d_proc, bp));
+    else         LAUNCH("k_chain", k_chain<1><<<1, NSEG * 1, chain_smem_bytes<1>(), h->stream>>>(d_in, d_streams, h->d_plans, d_proc, bp));
+    CK(cudaGetLastError());
+    rc = launch_compressor(h, g, bp, 3, 0, d_proc);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(out, d_proc, F * ch * 2, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return B200M_OK;
+}
+
+extern "C" int b200m_compress_dynamic_range(b200m_handle *h, const int16_t *pcm, int64_t nframes, int channels,
+                                            const b200m_band *band, int16_t *out, double *att_out, uint32_t *rms_out)
+{
+    if (!h) return B200M_ERR_INVALID;
+    if (!band || nframes < 0 || nframes > 0x7fffffff || (channels != 1 && channels != 2) || (nframes && (!pcm || !out)))
+        return fail(h, B200M_ERR_INVALID, "compress_dynamic_range: bad argument");
+    if (nframes == 0) return B200M_OK;
+    CK(cudaSetDevice(h->device));
+    b200m_plan p;
+    std::memset(&p, 0, sizeof p);
+    p.sample_rate = 1; p.channels = channels; p.multiband = 1;
+    p.lp[0] = p.lp[1] = p.hp[0] = p.hp[1] = p.kw[0] = p.kw[1] = {1, 0, 0, 0, 0};
+    p.band[0] = p.band[1] = p.band[2] = *band;
+    int rc = ensure_plans(h, &p, 1);
+    if (rc) return rc;
+    const size_t F = (size_t)nframes;
+    rc = ws_reserve(h, 8192 + F * channels * 2 * 2 + F * (2 + 8) + 8 * 256);
+    if (rc) return rc;
+    Arena A(h->ws);
+    StreamDesc *d_streams = A.take<StreamDesc>(1);
+    int16_t *d_in = A.take<int16_t>(F * channels);
+    int16_t *d_proc = A.take<int16_t>(F * channels);
+    BandPtrs bp;
+    std::memset(&bp, 0, sizeof bp);
+    bp.band[0] = d_in;
+    bp.rms[0] = A.take<uint16_t>(F);
+    bp.att[0] = A.take<double>(F);
+    StreamDesc sd = {0, 0, (int32_t)nframes, (int32_t)nframes, 0, 0};
+    CK(cudaMemcpyAsync(d_streams, &sd, sizeof sd, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(d_in, pcm, F * channels * 2, cudaMemcpyHostToDevice, h->stream));
+    Group g;
+    g.ch = channels; g.n_streams = 1; g.n_tracks = 1; g.max_stream_frames = (int)nframes; g.d_streams = d_streams;
+    g.max_look = band->look_frames;
+    rc = launch_compressor(h, g, bp, 1, 0, d_proc);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(out, d_proc, F * channels * 2, cudaMemcpyDeviceToHost, h->stream));
+    if (att_out) CK(cudaMemcpyAsync(att_out, bp.att[0], F * 8, cudaMemcpyDeviceToHost, h->stream));
+    std::vector<uint16_t> r16;
+    if (rms_out) { r16.resize(F); CK(cudaMemcpyAsync(r16.data(), bp.rms[0], F * 2, cudaMemcpyDeviceToHost, h->stream)); }
+    CK(cudaStreamSynchronize(h->stream));
+    if (rms_out) for (size_t i = 0; i < F; ++i) rms_out[i] = r16[i];
+    return B200M_OK;
+}
+
+static int loudness_core(b200m_handle *h, const b200m_biquad *kw, const float *x, int64_t n, int channels, int rate,
+                         double target, double *scaled_out, double *lufs_out, double *gain_out)
+{
+    if ((double)n < 0.4 * rate) return fail(h, B200M_ERR_TOO_SHORT, "audio must have length greater than the block size (400 ms)");
+    CK(cudaSetDevice(h->device));
+    b200m_plan p;
+    std::memset(&p, 0, sizeof p);
+    p.sample_rate = rate; p.channels = 1; p.has_lufs = 1; p.lufs = target;
+    p.kw[0] = kw[0]; p.kw[1] = kw[1];
+    int rc = ensure_plans(h, &p, 1);
+    if (rc) return rc;
+    TrackDesc td = {0, n, 0, num_blocks(n, rate), 0};
+    const size_t ns = (size_t)n * channels;
+    rc = ws_reserve(h, 8192 + ns * 4 + (size_t)n * 8 + (scaled_out ? ns * 8 : 0) + (size_t)(td.nblocks + 2) * 16);
+    if (rc) return rc;
+    Arena A(h->ws);
+    TrackDesc *d_tracks = A.take<TrackDesc>(1);
+    double2 *d_loud = A.take<double2>(1);
+    float *d_x = A.take<float>(ns);
+    float *d_mono = channels == 2 ? A.take<float>(n) : d_x;
+    float *d_kw = A.take<float>(n);
+    double *d_z = A.take<double>(td.nblocks + 1);
+    double *d_zsel = A.take<double>(td.nblocks + 1);
+    double *d_scaled = scaled_out ? A.take<double>(ns) : nullptr;
+    CK(cudaMemcpyAsync(d_tracks, &td, sizeof td, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(d_x, x, ns * 4, cudaMemcpyHostToDevice, h->stream));
+    if (channels == 2) LAUNCH("k_mono_mean", k_mono_mean<<<grid_for(n), 256, 0, h->stream>>>(d_x, n, d_mono));
+    Group g;
+    g.ch = 1; g.n_tracks = 1; g.d_tracks = d_tracks; g.max_blocks = td.nblocks; g.any_lufs = true; g.max_track_frames = n;
+    rc = launch_loudness(h, g, nullptr, d_mono, d_kw, d_z, d_zsel, d_loud);
+    if (rc) return rc;
+    if (scaled_out) {
+        LAUNCH("k_scale", k_scale<<<grid_for((int64_t)ns), 256, 0, h->stream>>>(d_x, (int64_t)ns, d_loud, d_scaled));
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(scaled_out, d_scaled, ns * 8, cudaMemcpyDeviceToHost, h->stream));
+    }
+    double2 res;
+    CK(cudaMemcpyAsync(&res, d_loud, sizeof res, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    if (lufs_out) *lufs_out = res.x;
+    if (gain_out) *gain_out = res.y;
+    return B200M_OK;
+}
+
+extern "C" int b200m_integrated_loudness(b200m_handle *h, const b200m_biquad *kw, const float *mono, int64_t n, int rate, double *lufs_out)
+{
+    if (!h) return B200M_ERR_INVALID;
+    if (!kw || !mono || !lufs_out || n < 0 || rate <= 0) return fail(h, B200M_ERR_INVALID, "integrated_loudness: bad argument");
+    return loudness_core(h, kw, mono, n, 1, rate, 0.0, nullptr, lufs_out, nullptr);
+}
+
+extern "C" int b200m_normalize_to_lufs(b200m_handle *h, const b200m_biquad *kw, const float *x, int64_t n_frames, int channels,
+                                       int rate, double target_lufs, double *out, double *loudness_out, double *gain_out)
+{
+    if (!h) return B200M_ERR_INVALID;
+    if (!kw || !x || !out || n_frames < 0 || rate <= 0 || (channels != 1 && channels != 2))
+        return fail(h, B200M_ERR_INVALID, "normalize_to_lufs: bad argument");
+    return loudness_core(h, kw, x, n_frames, channels, rate, target_lufs, out, loudness_out, gain_out);
+}

@@ -1,0 +1,152 @@
+// b200m_device.cuh -- device-side data structures and kernels of the mastering hot path.
+//
+// Reference being replaced: /root/reference/worker/audio_mastering_engine.py ("ENG").
+// Layout of one batch in HBM (all buffers are flat over the batch; a frame = CH samples):
+//   pcm_in   interleaved int16 of every track                    (caller's or staged)
+//   proc     interleaved int16, the chunk-processed track (ENG:80 `processed_audio`)
+//   band[3]  interleaved int16 crossover bands after quantisation (ENG:204-206)
+//   rms[3]   uint16 window RMS per frame and band (audioop.rms inside pydub)
+//   att[3]   fp64 attenuation trajectory per frame and band (pydub's `attenuation`)
+//   kw       float32 K-weighted mono signal (pyloudnorm input_data after both stages)
+//   z        fp64 400 ms block mean squares per track
+//   out      interleaved int16 final output (ENG:89)
+// A *stream* is one (track, 30-s chunk): every filter and compressor restarts from zero
+// state there (ENG:48-54), so streams are the unit of parallel work ahead of loudness.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace b200m {
+
+constexpr int SEG = 16;            // samples per thread segment in the blocked IIR scan
+constexpr int NSEG = 128;          // segments per channel per tile (k_chain)
+constexpr int TILE = SEG * NSEG;   // 2048 frames per k_chain tile
+constexpr int TILE_PAD = TILE + NSEG;  // one pad word per segment: conflict-free smem
+constexpr unsigned FULL = 0xffffffffu;
+
+// One biquad section plus everything its blocked parallel-prefix evaluation needs.
+// State-space form of the DF2T section: s' = A s + B x, y = s[0] + b0 x with
+//   A = [[-a1, 1], [-a2, 0]],  B = [b1 - a1 b0, b2 - a2 b0].
+struct SecTab {
+    double b0, b1, b2, a1, a2;
+    double pad_[3];
+    double g[SEG][2];   // g[n] = A^(SEG-1-n) B : end state of a segment from zero state
+    double P[5][4];     // A^(SEG * 2^k), k = 0..4 : warp-shuffle scan steps (row major 2x2)
+    double PW[4];       // A^(SEG * 32)            : warp-to-warp carry
+    double Q[32][4];    // A^(SEG * lane)          : carry-in to each lane's segment start
+};
+static_assert(sizeof(SecTab) == 192 * 8, "SecTab layout");
+
+struct BandDev {
+    double thresh_rms, attack_frames, release_frames, slope;
+    int32_t look;       // int(attack_frames)
+    int32_t rthr;       // floor(thresh_rms): rms > thresh_rms  <=>  rms > rthr (rms integer)
+};
+
+// Compressor static curve, tabulated over the 32769 possible integer RMS values.
+struct CurveEntry { double max_att, inc, dec, pad_; };
+constexpr int CURVE_N = 32769;
+
+struct PlanDev {
+    int32_t rate, channels, sat_on, n_eq, width_on, multiband, has_lufs, pad0_;
+    float sat_clean, sat_mix, sat_drive, pad1_;
+    double width, lufs;
+    BandDev band[3];
+    const CurveEntry *curve[3];   // device pointers, CURVE_N entries each (NULL if !multiband)
+    SecTab eq[4], lp[2], hp[2], kw[2];
+};
+
+struct StreamDesc {     // one (track, chunk)
+    int64_t in_off;     // first frame in pcm_in
+    int64_t out_off;    // first frame in the flat workspace buffers
+    int32_t in_frames;  // frames available in pcm_in (the rest of out_frames reads as silence)
+    int32_t out_frames; // frames to produce
+    int32_t plan;
+    int32_t track;
+};
+
+struct TrackDesc {
+    int64_t off;        // first frame in the flat workspace buffers
+    int64_t frames;     // out frames
+    int64_t zoff;       // first block in z
+    int32_t nblocks;    // pyloudnorm numBlocks
+    int32_t plan;
+};
+
+// ------------------------------------------------------------------------------------
+// Blocked parallel-prefix evaluation of ONE biquad section over one tile.
+// Each thread owns SEG consecutive samples x[] of one channel (32*NW threads per channel).
+//   pass 1  end state of the segment from zero state = sum_n g[n] x[n]        (2 FMA/sample)
+//   scan    Kogge-Stone over the warp with 2x2 transfer-matrix powers P[k], then the
+//           NW warp totals are chained with PW and the tile carry-in            (shuffles)
+//   pass 2  the true DF2T recurrence from the now-known start state          (5 FMA/sample)
+// `carry` (smem, 2 doubles) holds the section state at the tile start and is advanced to
+// the tile end.  Contains exactly one __syncthreads(): call it uniformly across the CTA.
+template <int NW>
+__device__ __forceinline__ void section_round(double (&x)[SEG], const SecTab *__restrict__ T,
+                                              double *carry, double *wtot, int lane, int wid,
+                                              bool writer)
+{
+    double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+    for (int n = 0; n < SEG; ++n) {
+        s0 = fma(T->g[n][0], x[n], s0);
+        s1 = fma(T->g[n][1], x[n], s1);
+    }
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+        double t0 = __shfl_up_sync(FULL, s0, 1 << k);
+        double t1 = __shfl_up_sync(FULL, s1, 1 << k);
+        if (lane >= (1 << k)) {
+            s0 = fma(T->P[k][0], t0, fma(T->P[k][1], t1, s0));
+            s1 = fma(T->P[k][2], t0, fma(T->P[k][3], t1, s1));
+        }
+    }
+    double e0 = __shfl_up_sync(FULL, s0, 1);
+    double e1 = __shfl_up_sync(FULL, s1, 1);
+    if (lane == 0) { e0 = 0.0; e1 = 0.0; }
+    if (lane == 31) { wtot[2 * wid] = s0; wtot[2 * wid + 1] = s1; }
+    double w0 = carry[0], w1 = carry[1];
+    __syncthreads();
+    double m0 = w0, m1 = w1;
+#pragma unroll
+    for (int w = 0; w < NW; ++w) {
+        if (w == wid) { m0 = w0; m1 = w1; }
+        double n0 = fma(T->PW[0], w0, fma(T->PW[1], w1, wtot[2 * w]));
+        double n1 = fma(T->PW[2], w0, fma(T->PW[3], w1, wtot[2 * w + 1]));
+        w0 = n0; w1 = n1;
+    }
+    if (writer) { carry[0] = w0; carry[1] = w1; }
+    double z0 = fma(T->Q[lane][0], m0, fma(T->Q[lane][1], m1, e0));
+    double z1 = fma(T->Q[lane][2], m0, fma(T->Q[lane][3], m1, e1));
+    const double b0 = T->b0, b1 = T->b1, b2 = T->b2, na1 = -T->a1, na2 = -T->a2;
+#pragma unroll
+    for (int n = 0; n < SEG; ++n) {
+        double xn = x[n];
+        double y = fma(b0, xn, z0);                 // scipy _sosfilt: x_n = b0*x_c + z0
+        z0 = fma(b1, xn, fma(na1, y, z1));          //   z0 = b1*x_c - a1*x_n + z1
+        z1 = fma(b2, xn, na2 * y);                  //   z1 = b2*x_c - a2*x_n
+        x[n] = y;
+    }
+}
+
+// ENG:123-126: clip to [-1,1], * 2^15, astype(int16) = truncate toward zero, and the
+// +1.0 -> 32768 -> -32768 wrap.  NaN casts to 0 (x86 cvttsd2si + 16-bit truncation).
+__device__ __forceinline__ int quant16(double y)
+{
+    if (y != y) return 0;
+    double v = fmin(fmax(y, -1.0), 1.0);
+    int iv = (int)(v * 32768.0);
+    return (int)(short)iv;
+}
+
+// ENG:128-134 in float32 with every product / sum separately rounded (numpy semantics).
+__device__ __forceinline__ float exciter(float x, float clean, float mix, float drive)
+{
+    float t = tanhf(__fmul_rn(x, drive));
+    return __fadd_rn(__fmul_rn(clean, x), __fmul_rn(mix, t));
+}
+
+__device__ __forceinline__ int pidx(int f) { return f + (f / SEG); }
+
+}  // namespace b200m

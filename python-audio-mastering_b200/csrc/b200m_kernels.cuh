@@ -1,0 +1,787 @@
+// b200m_kernels.cuh -- the sm_100a kernels of the mastering chain (see b200m_device.cuh).
+#pragma once
+#include "b200m_device.cuh"
+
+namespace b200m {
+
+struct BandPtrs {
+    int16_t *band[3];
+    uint16_t *rms[3];
+    double *att[3];
+};
+
+// =====================================================================================
+// k_chain: per (track, chunk) stream, sequential over 2048-frame tiles:
+//   int16 -> float32 (ENG:117-121) -> exciter (ENG:128-134) -> up to 4 EQ biquads in
+//   fp64 (ENG:146-194) -> M/S width (ENG:136-144) -> quantise #1 (ENG:123-126)
+//   and, when the plan is multiband, straight on with ENG:197-206:
+//   LP4 / HP4 crossover in fp64, mid = x - low - high, quantise #2 per band.
+// One CTA per stream; 128 threads per channel, each owning SEG consecutive samples of a
+// tile; every biquad is a section_round (blocked parallel prefix).  Filter state is
+// carried tile to tile in shared memory and starts at zero (chunk-boundary semantics).
+// =====================================================================================
+template <int CH>
+__global__ void __launch_bounds__(NSEG * CH, (CH == 2 ? 2 : 4))
+k_chain(const int16_t *__restrict__ pcm_in, const StreamDesc *__restrict__ streams,
+        const PlanDev *__restrict__ plans, int16_t *__restrict__ proc, BandPtrs bp)
+{
+    constexpr int NT = NSEG * CH;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    SecTab *tabs = reinterpret_cast<SecTab *>(smem_raw);                 // eq[4] lp[2] hp[2]
+    double *sy = reinterpret_cast<double *>(smem_raw + 8 * sizeof(SecTab));  // [CH][TILE_PAD]
+    float *sx = reinterpret_cast<float *>(sy + CH * TILE_PAD);           // [CH][TILE_PAD]
+    double *carry = reinterpret_cast<double *>(sx + CH * TILE_PAD);      // [8][CH][2]
+    double *wtot = carry + 8 * CH * 2;                                   // [2][CH][4][2]
+    int16_t *stg = reinterpret_cast<int16_t *>(sy);                      // aliases sy: [3][TILE_PAD][CH]
+
+    const StreamDesc sd = streams[blockIdx.x];
+    const PlanDev *__restrict__ pl = plans + sd.plan;
+    const int tid = threadIdx.x;
+    const int c = tid / NSEG, j = tid % NSEG, lane = tid & 31, wid = j >> 5;
+
+    {   // stage this plan's section tables, zero the carries
+        const double *src = reinterpret_cast<const double *>(pl->eq);
+        double *dst = reinterpret_cast<double *>(tabs);
+        for (int i = tid; i < 8 * (int)(sizeof(SecTab) / 8); i += NT) dst[i] = src[i];
+        for (int i = tid; i < 8 * CH * 2; i += NT) carry[i] = 0.0;
+    }
+    const int sat_on = pl->sat_on, n_eq = pl->n_eq, width_on = pl->width_on, multiband = pl->multiband;
+    const float s_clean = pl->sat_clean, s_mix = pl->sat_mix, s_drive = pl->sat_drive;
+    const double width = pl->width;
+    const float widthf = (float)width;
+    __syncthreads();
+
+    const int16_t *__restrict__ in = pcm_in + sd.in_off * CH;
+    float *myx = sx + c * TILE_PAD + j * (SEG + 1);
+    unsigned round = 0;
+
+    for (int t0 = 0; t0 < sd.out_frames; t0 += TILE) {
+        const int nvalid = min(TILE, sd.out_frames - t0);
+        // ---- stage: coalesced interleaved int16 -> planar float32 (+ exciter) ----------
+        for (int f = tid; f < TILE; f += NT) {
+            const int gf = t0 + f;
+            float v[CH];
+#pragma unroll
+            for (int k = 0; k < CH; ++k) v[k] = 0.0f;
+            if (gf < sd.in_frames) {
+                if (CH == 2) {
+                    const short2 q = *reinterpret_cast<const short2 *>(in + (int64_t)gf * 2);
+                    v[0] = (float)q.x * (1.0f / 32768.0f);
+                    v[CH - 1] = (float)q.y * (1.0f / 32768.0f);
+                } else {
+                    v[0] = (float)in[gf] * (1.0f / 32768.0f);
+                }
+                if (sat_on) {
+#pragma unroll
+                    for (int k = 0; k < CH; ++k) v[k] = exciter(v[k], s_clean, s_mix, s_drive);
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < CH; ++k) sx[k * TILE_PAD + pidx(f)] = v[k];
+        }
+        __syncthreads();
+
+        double x[SEG];
+#pragma unroll
+        for (int n = 0; n < SEG; ++n) x[n] = (double)myx[n];
+
+        // ---- EQ: one section_round per active biquad (bypassed sections were dropped
+        //      at plan time, exactly like ENG:171,186) ------------------------------------
+#pragma unroll
+        for (int s = 0; s < 4; ++s) {
+            if (s < n_eq) {
+                section_round<4>(x, &tabs[s], carry + (s * CH + c) * 2,
+                                 wtot + (((round & 1) * CH + c) * 4) * 2, lane, wid, j == 0);
+                ++round;
+            }
+        }
+
+        // ---- M/S width (needs the other channel: exchange through smem) ----------------
+        if (CH == 2 && width_on) {
+            double *myy = sy + c * TILE_PAD + j * (SEG + 1);
+#pragma unroll
+            for (int n = 0; n < SEG; ++n) myy[n] = x[n];
+            __syncthreads();
+            const double *oy = sy + (1 - c) * TILE_PAD + j * (SEG + 1);
+            if (n_eq > 0) {     // float64 arithmetic (EQ output is float64)
+#pragma unroll
+                for (int n = 0; n < SEG; ++n) {
+                    const double o = oy[n];
+                    const double l = c == 0 ? x[n] : o, r = c == 0 ? o : x[n];
+                    const double mid = __dmul_rn(__dadd_rn(l, r), 0.5);
+                    const double side = __dmul_rn(__dmul_rn(__dsub_rn(l, r), 0.5), width);
+                    x[n] = c == 0 ? __dadd_rn(mid, side) : __dsub_rn(mid, side);
+                }
+            } else {            // EQ fully bypassed: the reference stays in float32
+#pragma unroll
+                for (int n = 0; n < SEG; ++n) {
+                    const float o = (float)oy[n], me = (float)x[n];
+                    const float l = c == 0 ? me : o, r = c == 0 ? o : me;
+                    const float mid = __fmul_rn(__fadd_rn(l, r), 0.5f);
+                    const float side = __fmul_rn(__fmul_rn(__fsub_rn(l, r), 0.5f), widthf);
+                    x[n] = (double)(c == 0 ? __fadd_rn(mid, side) : __fsub_rn(mid, side));
+                }
+            }
+            __syncthreads();    // sy is reused as the int16 staging area below
+        }
+
+        const int pb = j * (SEG + 1);
+        if (!multiband) {
+            // ---- quantise #1 -> proc --------------------------------------------------
+#pragma unroll
+            for (int n = 0; n < SEG; ++n) stg[(pb + n) * CH + c] = (int16_t)quant16(x[n]);
+            __syncthreads();
+            int16_t *__restrict__ dst = proc + (sd.out_off + t0) * CH;
+            for (int f = tid; f < nvalid; f += NT) {
+                if (CH == 2)
+                    *reinterpret_cast<short2 *>(dst + (int64_t)f * 2) =
+                        *reinterpret_cast<const short2 *>(stg + pidx(f) * 2);
+                else
+                    dst[f] = stg[pidx(f)];
+            }
+            __syncthreads();
+        } else {
+            // ---- quantise #1, re-float (ENG:199), crossover ------------------------------
+#pragma unroll
+            for (int n = 0; n < SEG; ++n) {
+                const float u = (float)quant16(x[n]) * (1.0f / 32768.0f);
+                myx[n] = u;
+                x[n] = (double)u;
+            }
+            section_round<4>(x, &tabs[4], carry + (4 * CH + c) * 2,
+                             wtot + (((round & 1) * CH + c) * 4) * 2, lane, wid, j == 0); ++round;
+            section_round<4>(x, &tabs[5], carry + (5 * CH + c) * 2,
+                             wtot + (((round & 1) * CH + c) * 4) * 2, lane, wid, j == 0); ++round;
+            double low[SEG];
+#pragma unroll
+            for (int n = 0; n < SEG; ++n) { low[n] = x[n]; x[n] = (double)myx[n]; }
+            section_round<4>(x, &tabs[6], carry + (6 * CH + c) * 2,
+                             wtot + (((round & 1) * CH + c) * 4) * 2, lane, wid, j == 0); ++round;
+            section_round<4>(x, &tabs[7], carry + (7 * CH + c) * 2,
+                             wtot + (((round & 1) * CH + c) * 4) * 2, lane, wid, j == 0); ++round;
+            // ---- mid = x - low - high (ENG:202), quantise #2 per band --------------------
+#pragma unroll
+            for (int n = 0; n < SEG; ++n) {
+                const double u = (double)myx[n];
+                const double mid = __dsub_rn(__dsub_rn(u, low[n]), x[n]);
+                stg[(0 * TILE_PAD + pb + n) * CH + c] = (int16_t)quant16(low[n]);
+                stg[(1 * TILE_PAD + pb + n) * CH + c] = (int16_t)quant16(mid);
+                stg[(2 * TILE_PAD + pb + n) * CH + c] = (int16_t)quant16(x[n]);
+            }
+            __syncthreads();
+#pragma unroll
+            for (int b = 0; b < 3; ++b) {
+                int16_t *__restrict__ dst = bp.band[b] + (sd.out_off + t0) * CH;
+                const int16_t *src = stg + b * TILE_PAD * CH;
+                for (int f = tid; f < nvalid; f += NT) {
+                    if (CH == 2)
+                        *reinterpret_cast<short2 *>(dst + (int64_t)f * 2) =
+                            *reinterpret_cast<const short2 *>(src + pidx(f) * 2);
+                    else
+                        dst[f] = src[pidx(f)];
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+template <int CH>
+constexpr size_t chain_smem_bytes()
+{
+    return 8 * sizeof(SecTab) + (size_t)CH * TILE_PAD * 8 + (size_t)CH * TILE_PAD * 4 +
+           8 * CH * 2 * 8 + 2 * CH * 4 * 2 * 8;
+}
+
+// =====================================================================================
+// k_detect: audioop.rms over the look-back window [i-look, i) of both channels, for every
+// frame of every band (pydub rms_at, called from compress_dynamic_range; ENG:207-209).
+// Exact integer arithmetic: per-tile prefix sums of frame energies in uint64, window sum
+// by difference, rms = (unsigned)sqrt(sum/n) reproduced as an integer square root.
+// grid = (tiles, streams, bands).
+// =====================================================================================
+constexpr int DT = 4096;        // frames per tile
+constexpr int DNT = 256;
+
+__device__ __forceinline__ unsigned window_rms(unsigned long long S, unsigned n)
+{
+    if (n == 0) return 0u;
+    // largest r with r*r*n <= S  ==  (unsigned)sqrt((double)S / n): the quotient is a
+    // multiple of 1/n, so it can never sit within double rounding of a perfect square
+    // without being one.
+    unsigned r = (unsigned)sqrtf(__fdividef((float)S, (float)n));
+    if (r > 32768u) r = 32768u;
+    while ((unsigned long long)r * r * n > S) --r;
+    while ((unsigned long long)(r + 1) * (r + 1) * n <= S) ++r;
+    return r;
+}
+
+template <int CH>
+__global__ void __launch_bounds__(DNT)
+k_detect(const StreamDesc *__restrict__ streams, const PlanDev *__restrict__ plans, BandPtrs bp,
+         int band_base)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const StreamDesc sd = streams[blockIdx.y];
+    const PlanDev *__restrict__ pl = plans + sd.plan;
+    const int band = band_base + blockIdx.z;
+    const int t0 = blockIdx.x * DT;
+    if (!pl->multiband || t0 >= sd.out_frames) return;
+    const int H = pl->band[band].look;
+    const int total = H + DT;                       // local element k <-> frame t0 - H + k
+    int K = (total + DNT) / DNT;                    // covers k = 0..total
+    K |= 1;                                         // odd stride: conflict-free smem walks
+    unsigned long long *P = reinterpret_cast<unsigned long long *>(smem_raw);   // [total + 1]
+    unsigned *se = reinterpret_cast<unsigned *>(P + (total + 1));              // [DNT * K]
+    __shared__ unsigned long long wsum[DNT / 32];
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+
+    const int16_t *__restrict__ src = bp.band[band] + sd.out_off * CH;
+    for (int k = tid; k < DNT * K; k += DNT) {
+        const int f = t0 - H + k;
+        unsigned e = 0;
+        if (k < total && f >= 0 && f < sd.out_frames) {
+            if (CH == 2) {
+                const short2 q = *reinterpret_cast<const short2 *>(src + (int64_t)f * 2);
+                e = (unsigned)((int)q.x * q.x) + (unsigned)((int)q.y * q.y);
+            } else {
+                const int q = src[f];
+                e = (unsigned)(q * q);
+            }
+        }
+        se[k] = e;
+    }
+    __syncthreads();
+    unsigned long long mine = 0;
+    for (int m = 0; m < K; ++m) mine += se[tid * K + m];
+    unsigned long long inc = mine;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        unsigned long long t = __shfl_up_sync(FULL, inc, d);
+        if (lane >= d) inc += t;
+    }
+    if (lane == 31) wsum[wid] = inc;
+    __syncthreads();
+    unsigned long long base = 0;
+    for (int w = 0; w < wid; ++w) base += wsum[w];
+    unsigned long long run = base + inc - mine;     // exclusive prefix at this thread's first element
+    for (int m = 0; m < K; ++m) {
+        const int k = tid * K + m;
+        if (k <= total) P[k] = run;
+        run += se[k];
+    }
+    __syncthreads();
+    uint16_t *__restrict__ dst = bp.rms[band] + sd.out_off;
+    const int nvalid = min(DT, sd.out_frames - t0);
+    for (int i = tid; i < nvalid; i += DNT) {
+        const int f = t0 + i;
+        const unsigned long long S = P[i + H] - P[i];
+        const unsigned n = (unsigned)CH * (unsigned)min(f, H);
+        dst[f] = (uint16_t)window_rms(S, n);
+    }
+}
+
+// =====================================================================================
+// k_recur: the attenuation recurrence of pydub compress_dynamic_range, one lane per
+// (stream, band) chain, state reset to 0 at every chunk (ENG:207-209 are per chunk):
+//   if rms > thr and att <= M:  att = min(att + M/A, M)   else  att = max(att - M/R, 0)
+// M, M/A and M/R come from the per-band curve table indexed by the integer RMS, so the
+// only work on the dependent chain is one add, one min/max and one select per frame.
+// =====================================================================================
+__global__ void __launch_bounds__(32)
+k_recur(const StreamDesc *__restrict__ streams, const PlanDev *__restrict__ plans, int n_streams,
+        int nbands, int band_base, BandPtrs bp)
+{
+    const int chain = blockIdx.x * 32 + threadIdx.x;
+    if (chain >= n_streams * nbands) return;
+    const int s = chain / nbands, band = band_base + chain % nbands;
+    const StreamDesc sd = streams[s];
+    const PlanDev *__restrict__ pl = plans + sd.plan;
+    if (!pl->multiband) return;
+    const uint16_t *__restrict__ r = bp.rms[band] + sd.out_off;
+    double *__restrict__ out = bp.att[band] + sd.out_off;
+    const CurveEntry *__restrict__ cv = pl->curve[band];
+    const int rthr = pl->band[band].rthr;
+    const int n = sd.out_frames;
+    double a = 0.0;
+    int i = 0;
+    for (; i + 8 <= n; i += 8) {
+        unsigned rr[8];
+        double M[8], up[8], dn[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) rr[k] = r[i + k];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const double2 md = *reinterpret_cast<const double2 *>(&cv[rr[k]].max_att);
+            M[k] = md.x; up[k] = md.y; dn[k] = cv[rr[k]].dec;
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const bool p = ((int)rr[k] > rthr) && (a <= M[k]);
+            const double u = fmin(a + up[k], M[k]);
+            const double d = fmax(a - dn[k], 0.0);
+            a = p ? u : d;
+            out[i + k] = a;
+        }
+    }
+    for (; i < n; ++i) {
+        const unsigned rr = r[i];
+        const CurveEntry e = cv[rr];
+        const bool p = ((int)rr > rthr) && (a <= e.max_att);
+        const double u = fmin(a + e.inc, e.max_att);
+        const double d = fmax(a - e.dec, 0.0);
+        a = p ? u : d;
+        out[i] = a;
+    }
+}
+
+// =====================================================================================
+// k_apply: gain = 10^(-att/20) per frame and band, audioop.mul (floor of the clamped
+// product), then low.overlay(mid).overlay(high) = two saturating int16 adds (ENG:210).
+// grid = (tiles, streams).  nbands == 1 backs the single-band helper entry point.
+// =====================================================================================
+__device__ __forceinline__ int mul_floor16(int v, double g)
+{
+    double val = __dmul_rn((double)v, g);           // audioop.mul: fbound(val * factor)
+    if (val > 32767.0) val = 32767.0;
+    else if (val < -32767.0) val = -32768.0;
+    return (int)floor(val);
+}
+
+template <int CH>
+__global__ void __launch_bounds__(256)
+k_apply(const StreamDesc *__restrict__ streams, const PlanDev *__restrict__ plans, BandPtrs bp,
+        int nbands, int band_base, int16_t *__restrict__ proc)
+{
+    const StreamDesc sd = streams[blockIdx.y];
+    if (!plans[sd.plan].multiband) return;
+    const int f = blockIdx.x * 256 + threadIdx.x;
+    if (f >= sd.out_frames) return;
+    const int64_t gi = sd.out_off + f;
+    int acc[CH];
+#pragma unroll
+    for (int k = 0; k < CH; ++k) acc[k] = 0;
+    for (int b = 0; b < nbands; ++b) {
+        const int band = band_base + b;
+        const double a = bp.att[band][gi];
+        int v[CH];
+        if (CH == 2) {
+            const short2 q = *reinterpret_cast<const short2 *>(bp.band[band] + gi * 2);
+            v[0] = q.x; v[CH - 1] = q.y;
+        } else {
+            v[0] = bp.band[band][gi];
+        }
+        if (a != 0.0) {                             // pydub: `if attenuation != 0.0`
+            const double g = exp10(a * -0.05);      // db_to_float(-att) = 10 ** (-att / 20)
+#pragma unroll
+            for (int k = 0; k < CH; ++k) v[k] = mul_floor16(v[k], g);
+        }
+#pragma unroll
+        for (int k = 0; k < CH; ++k) acc[k] = b == 0 ? v[k] : max(-32768, min(32767, acc[k] + v[k]));
+    }
+    if (CH == 2)
+        *reinterpret_cast<short2 *>(proc + gi * 2) = make_short2((short)acc[0], (short)acc[CH - 1]);
+    else
+        proc[gi] = (int16_t)acc[0];
+}
+
+// =====================================================================================
+// k_kweight: pyloudnorm K-weighting of the (L+R)/2 mean of the processed track
+// (ENG:214-218): shelf then high-pass, float64 DF2T (scipy lfilter), each stage stored
+// back to float32.  One CTA per track, sequential over 4096-sample tiles; the filter
+// state runs through the WHOLE track (loudness is measured after chunk concatenation).
+// IN = int16 (proc, CH interleaved) or float (mono helper entry point, CH must be 1).
+// =====================================================================================
+constexpr int KNT = 256;
+constexpr int KTILE = SEG * KNT;               // 4096
+constexpr int KTILE_PAD = KTILE + KNT;
+
+template <int CH, typename IN>
+__global__ void __launch_bounds__(KNT, 2)
+k_kweight(const IN *__restrict__ src_all, const TrackDesc *__restrict__ tracks,
+          const PlanDev *__restrict__ plans, float *__restrict__ kw)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    SecTab *tabs = reinterpret_cast<SecTab *>(smem_raw);                    // kw[2]
+    float *sx = reinterpret_cast<float *>(smem_raw + 2 * sizeof(SecTab));   // [KTILE_PAD]
+    double *carry = reinterpret_cast<double *>(sx + KTILE_PAD + (KTILE_PAD & 1)); // [2][2]
+    double *wtot = carry + 4;                                               // [2][8][2]
+    const TrackDesc td = tracks[blockIdx.x];
+    const PlanDev *__restrict__ pl = plans + td.plan;
+    if (!pl->has_lufs) return;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    {
+        const double *s = reinterpret_cast<const double *>(pl->kw);
+        double *d = reinterpret_cast<double *>(tabs);
+        for (int i = tid; i < 2 * (int)(sizeof(SecTab) / 8); i += KNT) d[i] = s[i];
+        if (tid < 4) carry[tid] = 0.0;
+    }
+    __syncthreads();
+    const IN *__restrict__ src = src_all + td.off * CH;
+    float *__restrict__ dst = kw + td.off;
+    float *myx = sx + tid * (SEG + 1);
+    unsigned round = 0;
+    for (int64_t t0 = 0; t0 < td.frames; t0 += KTILE) {
+        const int nvalid = (int)min((int64_t)KTILE, td.frames - t0);
+        for (int f = tid; f < KTILE; f += KNT) {
+            float m = 0.0f;
+            if (f < nvalid) {
+                if (sizeof(IN) == 2) {
+                    if (CH == 2) {
+                        const short2 q = *reinterpret_cast<const short2 *>(
+                            reinterpret_cast<const int16_t *>(src) + (t0 + f) * 2);
+                        // float32 (vL + vR) / 2 with vL, vR multiples of 2^-15: exact
+                        m = (float)((int)q.x + (int)q.y) * (1.0f / 65536.0f);
+                    } else {
+                        m = (float)reinterpret_cast<const int16_t *>(src)[t0 + f] * (1.0f / 32768.0f);
+                    }
+                } else {
+                    m = (float)src[t0 + f];
+                }
+            }
+            sx[pidx(f)] = m;
+        }
+        __syncthreads();
+        double x[SEG];
+#pragma unroll
+        for (int n = 0; n < SEG; ++n) x[n] = (double)myx[n];
+        section_round<8>(x, &tabs[0], carry + 0, wtot + (round & 1) * 16, lane, wid, tid == 0); ++round;
+#pragma unroll
+        for (int n = 0; n < SEG; ++n) x[n] = (double)(float)x[n];   // input_data[:,ch] = ... (float32 store)
+        section_round<8>(x, &tabs[1], carry + 2, wtot + (round & 1) * 16, lane, wid, tid == 0); ++round;
+#pragma unroll
+        for (int n = 0; n < SEG; ++n) myx[n] = (float)x[n];
+        __syncthreads();
+        for (int f = tid; f < nvalid; f += KNT) dst[t0 + f] = sx[pidx(f)];
+        __syncthreads();
+    }
+}
+
+constexpr size_t kweight_smem_bytes()
+{
+    return 2 * sizeof(SecTab) + (size_t)(KTILE_PAD + (KTILE_PAD & 1)) * 4 + 4 * 8 + 2 * 8 * 2 * 8;
+}
+
+// =====================================================================================
+// numpy's pairwise summation (numpy/_core/src/umath/loops_utils.h.src, @TYPE@_pairwise_sum),
+// reproduced operation for operation so block energies and gated means round exactly
+// like np.sum / np.mean do inside pyloudnorm.  `get(i)` yields element i.
+// =====================================================================================
+struct F32 {   // float whose adds can never be contracted into FMAs
+    float v;
+    __device__ F32() : v(0.f) {}
+    __device__ explicit F32(int) : v(0.f) {}
+    __device__ F32(float f) : v(f) {}
+    __device__ F32 operator+(const F32 &o) const { return F32(__fadd_rn(v, o.v)); }
+};
+
+template <typename T, typename Get>
+__device__ __forceinline__ T np_pairwise_leaf(Get get, int64_t off, int n)
+{
+    if (n < 8) {
+        T res = (T)0;
+        for (int i = 0; i < n; ++i) res = res + get(off + i);
+        return res;
+    }
+    T r[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) r[k] = get(off + k);
+    int i = 8;
+    for (; i < n - (n % 8); i += 8) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) r[k] = r[k] + get(off + i + k);
+    }
+    T res = ((r[0] + r[1]) + (r[2] + r[3])) + ((r[4] + r[5]) + (r[6] + r[7]));
+    for (; i < n; ++i) res = res + get(off + i);
+    return res;
+}
+
+template <typename T, typename Get>
+__device__ T np_pairwise_sum(Get get, int64_t n)
+{
+    if (n <= 128) return np_pairwise_leaf<T>(get, 0, (int)n);
+    int64_t s_off[40], s_n[40];
+    T s_acc[40];
+    int s_stage[40];
+    int sp = 0;
+    s_off[0] = 0; s_n[0] = n; s_stage[0] = 0; s_acc[0] = (T)0;
+    T ret = (T)0;
+    while (sp >= 0) {
+        if (s_n[sp] <= 128) { ret = np_pairwise_leaf<T>(get, s_off[sp], (int)s_n[sp]); --sp; continue; }
+        int64_t n2 = s_n[sp] / 2;
+        n2 -= n2 % 8;
+        if (s_stage[sp] == 0) {
+            s_stage[sp] = 1;
+            s_off[sp + 1] = s_off[sp]; s_n[sp + 1] = n2; s_stage[sp + 1] = 0; ++sp;
+        } else if (s_stage[sp] == 1) {
+            s_acc[sp] = ret; s_stage[sp] = 2;
+            s_off[sp + 1] = s_off[sp] + n2; s_n[sp + 1] = s_n[sp] - n2; s_stage[sp + 1] = 0; ++sp;
+        } else {
+            ret = s_acc[sp] + ret; --sp;
+        }
+    }
+    return ret;
+}
+
+// =====================================================================================
+// k_blocks: 400 ms / 75 %-overlap block mean squares z_j (pyloudnorm meter.py):
+//   l = int(T_g*(j*step)*rate), u = int(T_g*(j*step+1)*rate)
+//   z_j = float32(1/(T_g*rate)) * np.sum(np.square(y[l:u]))        (float32 throughout)
+// One thread per block; np.sum's pairwise order is reproduced exactly.
+// =====================================================================================
+__global__ void __launch_bounds__(128)
+k_blocks(const float *__restrict__ kw, const TrackDesc *__restrict__ tracks,
+         const PlanDev *__restrict__ plans, double *__restrict__ z)
+{
+    const TrackDesc td = tracks[blockIdx.y];
+    const PlanDev *__restrict__ pl = plans + td.plan;
+    const int j = blockIdx.x * 128 + threadIdx.x;
+    if (!pl->has_lufs || j >= td.nblocks) return;
+    const double rate = (double)pl->rate, Tg = 0.4, step = 0.25;
+    int64_t l = (int64_t)__dmul_rn(__dmul_rn(Tg, __dmul_rn((double)j, step)), rate);
+    int64_t u = (int64_t)__dmul_rn(__dmul_rn(Tg, __dadd_rn(__dmul_rn((double)j, step), 1.0)), rate);
+    if (u > td.frames) u = td.frames;       // numpy slicing clamps
+    if (l > u) l = u;
+    const float *__restrict__ y = kw + td.off + l;
+    auto get = [y](int64_t i) { const float v = y[i]; return __fmul_rn(v, v); };
+    auto getF = [get](int64_t i) { return F32(get(i)); };
+    const float sum = np_pairwise_sum<F32>(getF, u - l).v;
+    const float scale = (float)(1.0 / (Tg * rate));
+    z[td.zoff + j] = (double)__fmul_rn(scale, sum);
+}
+
+// =====================================================================================
+// k_gate: absolute (-70 LUFS) and relative (-10 LU) gating over the block energies,
+// integrated loudness and the linear gain of ENG:219-220.  One CTA (one warp does the
+// ordered compaction, thread 0 the pairwise fp64 means) per track.
+// out[track] = {loudness, gain}
+// =====================================================================================
+__global__ void __launch_bounds__(32)
+k_gate(const TrackDesc *__restrict__ tracks, const PlanDev *__restrict__ plans,
+       const double *__restrict__ z, double *__restrict__ zsel, double2 *__restrict__ out)
+{
+    const TrackDesc td = tracks[blockIdx.x];
+    const PlanDev *__restrict__ pl = plans + td.plan;
+    const int lane = threadIdx.x;
+    if (!pl->has_lufs) {
+        if (lane == 0) out[blockIdx.x] = make_double2(__longlong_as_double(0x7ff8000000000000LL), 1.0);
+        return;
+    }
+    const double *__restrict__ zt = z + td.zoff;
+    double *__restrict__ sel = zsel + td.zoff;
+    const int nb = td.nblocks;
+    const double nan = __longlong_as_double(0x7ff8000000000000LL);
+    double gamma_r = 0.0;
+    double mean = nan;
+    for (int pass = 0; pass < 2; ++pass) {
+        int cnt = 0;
+        for (int j0 = 0; j0 < nb; j0 += 32) {
+            const int j = j0 + lane;
+            bool keep = false;
+            double zj = 0.0;
+            if (j < nb) {
+                zj = zt[j];
+                const double lj = __dadd_rn(-0.691, __dmul_rn(10.0, log10(zj)));
+                keep = pass == 0 ? (lj >= -70.0) : (lj > gamma_r && lj > -70.0);
+            }
+            const unsigned m = __ballot_sync(FULL, keep);
+            if (keep) sel[cnt + __popc(m & ((1u << lane) - 1u))] = zj;
+            cnt += __popc(m);
+        }
+        __syncwarp();
+        if (lane == 0) {
+            if (cnt > 0) {
+                const double *s = sel;
+                auto get = [s](int64_t i) { return s[i]; };
+                mean = np_pairwise_sum<double>(get, cnt) / (double)cnt;
+            } else {
+                mean = nan;                     // np.mean([]) -> nan
+            }
+        }
+        mean = __shfl_sync(FULL, mean, 0);
+        if (pass == 0) gamma_r = __dsub_rn(__dadd_rn(-0.691, __dmul_rn(10.0, log10(mean))), 10.0);
+        __syncwarp();
+    }
+    if (lane == 0) {
+        if (mean != mean) mean = 0.0;           // np.nan_to_num
+        const double lufs = __dadd_rn(-0.691, __dmul_rn(10.0, log10(mean)));
+        const double gain = pow(10.0, (pl->lufs - lufs) / 20.0);
+        out[blockIdx.x] = make_double2(lufs, gain);
+    }
+}
+
+// =====================================================================================
+// k_final: re-float the processed track (ENG:82), one gain (ENG:222, float64 because the
+// loudness is a numpy float64 scalar), rational soft limiter (ENG:224-227), quantise #3
+// (ENG:89).  Without a loudness target the limiter runs in float32, as in the reference.
+// grid = (tiles, tracks).
+// =====================================================================================
+__device__ __forceinline__ double limiter64(double x, double thr)
+{
+    const double ax = fabs(x);
+    if (ax > thr) {
+        const double d = __dsub_rn(ax, thr);
+        const double t = __ddiv_rn(d, 0.02);
+        const double r = __ddiv_rn(d, __dsqrt_rn(__dadd_rn(1.0, __dmul_rn(t, t))));
+        const double sgn = x > 0.0 ? 1.0 : (x < 0.0 ? -1.0 : x);   // np.sign
+        return __dmul_rn(__dadd_rn(thr, r), sgn);
+    }
+    return x;
+}
+
+__device__ __forceinline__ float limiter32(float x, float thr)
+{
+    const float ax = fabsf(x);
+    if (ax > thr) {
+        const float d = __fsub_rn(ax, thr);
+        const float t = __fdiv_rn(d, 0.02f);
+        const float r = __fdiv_rn(d, __fsqrt_rn(__fadd_rn(1.0f, __fmul_rn(t, t))));
+        const float sgn = x > 0.0f ? 1.0f : (x < 0.0f ? -1.0f : x);
+        return __fmul_rn(__fadd_rn(thr, r), sgn);
+    }
+    return x;
+}
+
+template <int CH>
+__global__ void __launch_bounds__(256)
+k_final(const int16_t *__restrict__ proc, const TrackDesc *__restrict__ tracks,
+        const PlanDev *__restrict__ plans, const double2 *__restrict__ loud,
+        int16_t *__restrict__ out)
+{
+    const TrackDesc td = tracks[blockIdx.y];
+    const PlanDev *__restrict__ pl = plans + td.plan;
+    const bool has = pl->has_lufs != 0;
+    const double gain = has ? loud[blockIdx.y].y : 1.0;
+    const int16_t *__restrict__ src = proc + td.off * CH;
+    int16_t *__restrict__ dst = out + td.off * CH;
+    // one frame per thread: 4-byte (stereo) accesses, fully coalesced
+    for (int64_t f = (int64_t)blockIdx.x * 256 + threadIdx.x; f < td.frames; f += (int64_t)gridDim.x * 256) {
+        int q[CH], r[CH];
+        if (CH == 2) {
+            const short2 s = *reinterpret_cast<const short2 *>(src + f * 2);
+            q[0] = s.x; q[CH - 1] = s.y;
+        } else {
+            q[0] = src[f];
+        }
+#pragma unroll
+        for (int k = 0; k < CH; ++k) {
+            const float v = (float)q[k] * (1.0f / 32768.0f);
+            if (has) r[k] = quant16(limiter64(__dmul_rn((double)v, gain), 0.98));
+            else     r[k] = quant16((double)limiter32(v, 0.98f));
+        }
+        if (CH == 2) *reinterpret_cast<short2 *>(dst + f * 2) = make_short2((short)r[0], (short)r[CH - 1]);
+        else dst[f] = (int16_t)r[0];
+    }
+}
+
+// =====================================================================================
+// Stage-level helper kernels (back the reference's per-function API; parity tests).
+// =====================================================================================
+__global__ void k_pcm16_to_float(const int16_t *__restrict__ in, int64_t n, float *__restrict__ out)
+{
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        out[i] = (float)in[i] * (1.0f / 32768.0f);
+}
+
+template <typename T>
+__global__ void k_float_to_pcm16(const T *__restrict__ in, int64_t n, int16_t *__restrict__ out)
+{
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        out[i] = (int16_t)quant16((double)in[i]);
+}
+
+__global__ void k_saturation(const float *__restrict__ in, int64_t n, float clean, float mix, float drive,
+                             float *__restrict__ out)
+{
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        out[i] = exciter(in[i], clean, mix, drive);
+}
+
+template <typename T>
+__global__ void k_width(const T *__restrict__ in, int64_t nframes, double width, T *__restrict__ out)
+{
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nframes; i += (int64_t)gridDim.x * blockDim.x) {
+        const T l = in[2 * i], r = in[2 * i + 1];
+        if (sizeof(T) == 8) {
+            const double mid = __dmul_rn(__dadd_rn((double)l, (double)r), 0.5);
+            const double side = __dmul_rn(__dmul_rn(__dsub_rn((double)l, (double)r), 0.5), width);
+            out[2 * i] = (T)__dadd_rn(mid, side);
+            out[2 * i + 1] = (T)__dsub_rn(mid, side);
+        } else {
+            const float mid = __fmul_rn(__fadd_rn((float)l, (float)r), 0.5f);
+            const float side = __fmul_rn(__fmul_rn(__fsub_rn((float)l, (float)r), 0.5f), (float)width);
+            out[2 * i] = (T)__fadd_rn(mid, side);
+            out[2 * i + 1] = (T)__fsub_rn(mid, side);
+        }
+    }
+}
+
+template <typename T>
+__global__ void k_limiter(const T *__restrict__ in, int64_t n, double thr, T *__restrict__ out)
+{
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        if (sizeof(T) == 8) out[i] = (T)limiter64((double)in[i], thr);
+        else out[i] = (T)limiter32((float)in[i], (float)thr);
+    }
+}
+
+// ENG:215 samples.mean(axis=1) in float32: fl(l + r) / 2
+__global__ void k_mono_mean(const float *__restrict__ in, int64_t nframes, float *__restrict__ out)
+{
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nframes; i += (int64_t)gridDim.x * blockDim.x)
+        out[i] = __fmul_rn(__fadd_rn(in[2 * i], in[2 * i + 1]), 0.5f);
+}
+
+// ENG:222 samples * gain_linear (float32 array * float64 scalar -> float64)
+__global__ void k_scale(const float *__restrict__ in, int64_t n, const double2 *__restrict__ loud, double *__restrict__ out)
+{
+    const double gain = loud[0].y;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        out[i] = __dmul_rn((double)in[i], gain);
+}
+
+// scipy.signal.sosfilt from zero state on `channels` interleaved channels: one CTA per
+// channel, sequential 4096-sample tiles, up to 8 sections.  IN float or double, out double.
+template <typename IN>
+__global__ void __launch_bounds__(KNT, 2)
+k_sosfilt(const IN *__restrict__ in, int64_t nframes, int channels, const SecTab *__restrict__ secs,
+          int nsec, double *__restrict__ out)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    SecTab *tabs = reinterpret_cast<SecTab *>(smem_raw);                       // [8]
+    double *sx = reinterpret_cast<double *>(smem_raw + 8 * sizeof(SecTab));    // [KTILE_PAD]
+    double *carry = sx + KTILE_PAD;                                            // [8][2]
+    double *wtot = carry + 16;                                                 // [2][8][2]
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, ch = blockIdx.x;
+    {
+        const double *s = reinterpret_cast<const double *>(secs);
+        double *d = reinterpret_cast<double *>(tabs);
+        for (int i = tid; i < nsec * (int)(sizeof(SecTab) / 8); i += KNT) d[i] = s[i];
+        if (tid < 16) carry[tid] = 0.0;
+    }
+    __syncthreads();
+    double *myx = sx + tid * (SEG + 1);
+    unsigned round = 0;
+    for (int64_t t0 = 0; t0 < nframes; t0 += KTILE) {
+        const int nvalid = (int)min((int64_t)KTILE, nframes - t0);
+        for (int f = tid; f < KTILE; f += KNT)
+            sx[pidx(f)] = f < nvalid ? (double)in[(t0 + f) * channels + ch] : 0.0;
+        __syncthreads();
+        double x[SEG];
+#pragma unroll
+        for (int n = 0; n < SEG; ++n) x[n] = myx[n];
+        for (int s = 0; s < nsec; ++s) {
+            section_round<8>(x, &tabs[s], carry + 2 * s, wtot + (round & 1) * 16, lane, wid, tid == 0);
+            ++round;
+        }
+#pragma unroll
+        for (int n = 0; n < SEG; ++n) myx[n] = x[n];
+        __syncthreads();
+        for (int f = tid; f < nvalid; f += KNT) out[(t0 + f) * channels + ch] = sx[pidx(f)];
+        __syncthreads();
+    }
+}
+
+constexpr size_t sosfilt_smem_bytes() { return 8 * sizeof(SecTab) + (size_t)KTILE_PAD * 8 + 16 * 8 + 32 * 8; }
+
+}  // namespace b200m

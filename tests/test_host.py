@@ -1,0 +1,138 @@
+"""CPU tests of the host side: the C-ABI library loads and exports every declared symbol,
+the host-side filter design matches the oracle's, framing and settings logic."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+from scipy.signal import butter
+
+from conftest import ROOT
+from b200master import lib as L
+from b200master import ms_framing, normalize_settings
+from b200master.plan import make_plan, to_c_settings
+from oracle import port
+
+
+def _declared_symbols():
+    hdr = open(os.path.join(ROOT, "include", "b200_master.h")).read()
+    return sorted(set(re.findall(r"\b(b200m_[a-z0-9_]+)\s*\(", hdr)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = L.load()
+    names = _declared_symbols()
+    assert len(names) >= 20
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/b200_master.h but not exported"
+    assert set(names) == set(L.EXPORTS)
+    assert lib.b200m_abi_version() == 1
+
+
+def test_no_cpu_fallback_without_device(has_cuda):
+    if has_cuda:
+        pytest.skip("a CUDA device is present")
+    lib = L.load()
+    h = C.c_void_p()
+    assert lib.b200m_create(0, C.byref(h)) == L.ERR_CUDA
+    assert b"no CPU fallback" in lib.b200m_last_error(None)
+    from b200master import Engine
+    with pytest.raises(RuntimeError):
+        Engine(0)
+
+
+def _bq(b):
+    return np.array([b.b0, b.b1, b.b2, b.a1, b.a2])
+
+
+@pytest.mark.parametrize("rate", [44100, 48000, 96000])
+def test_python_plan_matches_oracle_design(rate):
+    st = dict(bass_boost=4.0, mid_cut=3.0, presence_boost=1.0, treble_boost=3.0, saturation=25, width=1.2,
+              multiband=True, lufs=-14.0)
+    p = make_plan(st, rate, 2)
+    secs = [s for s in port.eq_sections(rate, st) if s is not None]
+    assert p.n_eq == 4
+    for i, s in enumerate(secs):
+        assert np.array_equal(_bq(p.eq[i]), s[0, [0, 1, 2, 4, 5]])
+    lp = butter(4, 250, btype="lowpass", fs=rate, output="sos")
+    hp = butter(4, 4000, btype="highpass", fs=rate, output="sos")
+    for i in range(2):
+        assert np.array_equal(_bq(p.lp[i]), lp[i, [0, 1, 2, 4, 5]])
+        assert np.array_equal(_bq(p.hp[i]), hp[i, [0, 1, 2, 4, 5]])
+    from oracle import thirdparty
+    m = thirdparty.Meter(rate)
+    for i, f in enumerate(m._filters.values()):
+        assert np.array_equal(_bq(p.kw[i]), np.r_[f.b, f.a[1:]])
+    mix = (25 / 100.0) ** 2
+    assert p.sat_clean == np.float32(1 - mix) and p.sat_mix == np.float32(mix) and p.sat_drive == np.float32(1 + mix * 4)
+    # pydub compressor set-up
+    assert p.band[0].thresh_rms == 32768.0 * (10 ** (-25.0 / 20))
+    assert [p.band[i].look_frames for i in range(3)] == [int(10 * rate / 1000.0), int(5 * (rate / 1000.0)), int(1 * (rate / 1000.0))]
+
+
+@pytest.mark.parametrize("rate", [44100, 48000, 96000])
+def test_c_design_matches_python_design(rate):
+    """b200m_plan_from_settings (C, libm) vs the numpy/scipy design the reference uses."""
+    st = dict(bass_boost=5.0, mid_cut=-2.0, presence_boost=2.0, treble_boost=3.5, saturation=40, width=0.7,
+              multiband=True, lufs=-9.0, mid_thresh=-22.0, mid_ratio=2.5)
+    p = make_plan(st, rate, 2)
+    q = L.Plan()
+    s = to_c_settings(st)
+    assert L.load().b200m_plan_from_settings(C.byref(s), rate, 2, C.byref(q)) == 0
+    assert (p.n_eq, p.width_on, p.multiband, p.has_lufs, p.sat_on) == (q.n_eq, q.width_on, q.multiband, q.has_lufs, q.sat_on)
+    for a, b in [(p.eq[i], q.eq[i]) for i in range(4)] + [(p.lp[i], q.lp[i]) for i in range(2)] + \
+                [(p.hp[i], q.hp[i]) for i in range(2)] + [(p.kw[i], q.kw[i]) for i in range(2)]:
+        assert np.allclose(_bq(a), _bq(b), rtol=1e-13, atol=0)
+    for i in range(3):
+        assert p.band[i].thresh_rms == pytest.approx(q.band[i].thresh_rms, rel=1e-15)
+        assert (p.band[i].look_frames, p.band[i].attack_frames, p.band[i].release_frames, p.band[i].slope) == \
+               (q.band[i].look_frames, q.band[i].attack_frames, q.band[i].release_frames, q.band[i].slope)
+    assert (p.sat_clean, p.sat_mix, p.sat_drive, p.lufs, p.width) == (q.sat_clean, q.sat_mix, q.sat_drive, q.lufs, q.width)
+
+
+def test_bypassed_sections_are_dropped():
+    p = make_plan(dict(bass_boost=0, mid_cut=0.0, presence_boost=3.5, treble_boost=0), 44100, 2)
+    assert p.n_eq == 1 and p.width_on == 0 and p.multiband == 0 and p.has_lufs == 0 and p.sat_on == 0
+    assert make_plan(dict(width=1.3), 44100, 1).width_on == 0          # mono: widener is a no-op (ENG:137)
+
+
+def test_settings_defaults_and_gui_aliases():
+    s = normalize_settings({"low_band_threshold": -30.0, "mid_ratio": 2.0, "mid_band_ratio": 9.0, "compress": False,
+                            "original_filename": "x.wav"})
+    assert s["low_thresh"] == -30.0 and s["low_ratio"] == 6.0 and s["mid_ratio"] == 2.0
+    assert s["high_thresh"] == -15.0 and s["high_ratio"] == 4.0 and s["lufs"] is None and s["multiband"] is False
+    assert normalize_settings({"multiband": 1})["multiband"] is True
+
+
+@pytest.mark.parametrize("n,rate", [(44077, 44100), (44079, 44100), (7938021, 44100), (7938023, 44100),
+                                    (8640000, 48000), (341775, 11025), (1, 44100)])
+def test_ms_framing_matches_oracle_chunking(n, rate):
+    bounds = port.chunk_bounds(n, rate)
+    total = bounds[-1][1] if bounds else 0
+    assert ms_framing(n, rate) == total
+    for (s, e) in bounds[:-1]:
+        assert e - s == 30 * rate                                      # chunk = 30 * rate frames exactly
+
+
+def test_drop_in_module_imports_without_gpu():
+    import audio_mastering_engine as ame
+    assert set(ame.EQ_PRESETS) == {"techno", "dubstep", "pop", "rock"}
+    assert ame.EQ_PRESETS["rock"]["mid_cut"] == -2.0
+    for name in ["process_audio_from_gcs", "process_audio", "batch_process_audio", "audio_segment_to_float_array",
+                 "float_array_to_audio_segment", "apply_saturation", "apply_stereo_width", "apply_eq_to_samples",
+                 "apply_shelf_filter", "apply_peak_filter", "apply_multiband_compressor", "normalize_to_lufs", "soft_limiter"]:
+        assert callable(getattr(ame, name))
+    x = np.zeros((4, 2), dtype=np.float32)
+    assert ame.apply_saturation(x, 0) is x                             # ENG:129 bypass returns its argument
+    assert ame.apply_shelf_filter(x[:, 0], 44100, 250, 0, "low") is not None
+
+
+def test_product_does_not_import_oracle():
+    """The product path must never route through the oracle."""
+    pkg = os.path.join(ROOT, "python-audio-mastering_b200")
+    for dirpath, _d, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, re.M), f"{f} imports oracle"
