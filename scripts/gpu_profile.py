@@ -1,0 +1,36 @@
+"""Per-kernel timing of the batch path with the library's CUDA-event profiler."""
+import os, sys, time, json
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "python-audio-mastering_b200"))
+import numpy as np, torch
+from b200master import get_engine, synth, make_plan, ms_framing
+
+ntracks = int(sys.argv[1]) if len(sys.argv) > 1 else 8
+seconds = float(sys.argv[2]) if len(sys.argv) > 2 else 180.0
+rate = int(sys.argv[3]) if len(sys.argv) > 3 else 48000
+sat = float(sys.argv[4]) if len(sys.argv) > 4 else 25
+eng = get_engine(0)
+st = dict(bass_boost=4.0, mid_cut=3.0, presence_boost=1.0, treble_boost=3.0, saturation=sat, width=1.2, multiband=True, lufs=-14.0)
+t0 = time.time()
+d_in = synth.make_tracks_torch(0, ntracks, seconds, rate, "cuda")
+torch.cuda.synchronize(); print("synth", time.time() - t0)
+n = d_in.shape[1]
+d_out = torch.empty_like(d_in)
+plan = make_plan(st, rate, 2)
+offs = [i * n for i in range(ntracks)]; fr = [n] * ntracks; of = [ms_framing(n, rate)] * ntracks
+def step():
+    return eng.master_raw(d_in, True, offs, fr, of, [plan], [0] * ntracks, d_out, True, want_loudness=False)
+for _ in range(2): step()
+eng.synchronize()
+eng.set_profiling(True); eng.reset_profile()
+K = 3
+t0 = time.time()
+for _ in range(K): step()
+eng.synchronize(); dt = (time.time() - t0) / K
+tot = 0
+for k in ["k_chain", "k_detect", "k_recur", "k_apply", "k_kweight", "k_blocks", "k_gate", "k_final"]:
+    ms, cnt = eng.kernel_time_ms(k); tot += ms / K
+    print(f"{k:10s} {ms / K:9.3f} ms/step  ({cnt} launches)")
+print(f"sum {tot:.3f} ms ; wall {dt * 1e3:.3f} ms/step ; RTF {ntracks * seconds / dt:.0f} ; frames {ntracks * n} ; "
+      f"8B/frame roofline frac {ntracks * n * 8 / dt / 6450.6e9:.4f}")
+eng.set_profiling(False)
