@@ -117,6 +117,15 @@ int64_t b200m_launch_count(const b200m_handle *h);
 int b200m_set_profiling(b200m_handle *h, int on);
 int b200m_kernel_time_ms(b200m_handle *h, const char *kernel, double *total_ms, int64_t *launches);
 int b200m_reset_profile(b200m_handle *h);
+/* Compressor recurrence tiling: each (chunk, band) attenuation chain is cut into time tiles that
+ * run in parallel after a warm-up over the preceding `warm_frames` (k_recur_tiles), wrong guesses
+ * are repaired in `rounds` parallel passes and finally by an exact sequential pass (k_recur_fix).
+ * tile_frames = 0: automatic tile length; warm_frames = 0: default 32768; rounds < 0: default 4.
+ * Results never depend on any of the three. */
+int b200m_set_recur_tiling(b200m_handle *h, int tile_frames, int warm_frames, int rounds);
+/* Verification counters since the last reset: tiles repaired by the sequential pass, frames it
+ * re-ran, and tiles repaired in the parallel rounds. */
+int b200m_recur_stats(b200m_handle *h, int64_t *wrong_tiles, int64_t *rerun_frames, int64_t *round_repairs, int reset);
 
 /* ---- host-side design (replaces ENG:172-182, 187-193, 197-198 + pydub/pyloudnorm
  *      parameter set-up); pure C, no device work -------------------------------- */

@@ -78,6 +78,14 @@ class Engine:
         self._ck(self._lib.b200m_kernel_time_ms(self._h, name.encode(), C.byref(tot), C.byref(n)))
         return tot.value, n.value
 
+    def set_recur_tiling(self, tile_frames: int = 0, warm_frames: int = 0, rounds: int = -1):
+        self._ck(self._lib.b200m_set_recur_tiling(self._h, int(tile_frames), int(warm_frames), int(rounds)))
+
+    def recur_stats(self, reset: bool = False):
+        a, b, c = C.c_int64(), C.c_int64(), C.c_int64()
+        self._ck(self._lib.b200m_recur_stats(self._h, C.byref(a), C.byref(b), C.byref(c), int(reset)))
+        return {"wrong_tiles": a.value, "rerun_frames": b.value, "round_repairs": c.value}
+
     # -- the whole path ------------------------------------------------------------------
     def master_raw(self, pcm_in, in_on_device, in_offsets, in_frames, out_frames, plans, plan_index,
                    pcm_out, out_on_device, want_loudness=True):

@@ -34,7 +34,7 @@ struct b200m_handle {
     std::vector<PlanDev> plans_host;
     PlanDev *d_plans = nullptr;
     size_t d_plans_cap = 0;
-    std::map<std::tuple<double, double, double, double>, CurveEntry *> curves;
+    std::map<std::tuple<double, double>, double *> curves;
     // pinned staging for descriptors / small results
     char *pin = nullptr;
     size_t pin_cap = 0;
@@ -45,6 +45,9 @@ struct b200m_handle {
     std::vector<cudaEvent_t> ev_pool;
     std::map<std::string, std::pair<double, int64_t>> prof_acc;
     int64_t launches = 0;
+    // recurrence tiling (0 = automatic) and its verification counters
+    int recur_tile = 0, recur_warm = 32768, recur_rounds = 4;
+    unsigned long long *d_counters = nullptr;
 };
 
 static std::string g_create_err;
@@ -331,14 +334,11 @@ extern "C" int b200m_plan_from_settings(const b200m_settings *s, int sample_rate
 // ------------------------------------------------------------------------------------
 // Plan upload (device tables), cached across calls with identical plans
 // ------------------------------------------------------------------------------------
-static int get_curve(b200m_handle *h, const b200m_band &b, const CurveEntry **out)
+static int get_curve(b200m_handle *h, const b200m_band &b, const double **out, std::vector<double> *host_copy)
 {
-    auto key = std::make_tuple(b.thresh_rms, b.attack_frames, b.release_frames, b.slope);
-    auto it = h->curves.find(key);
-    if (it != h->curves.end()) { *out = it->second; return B200M_OK; }
     // pydub: db = 20 * math.log(rms / thresh_rms, 10) = 20 * (log(x) / log(10));
-    //        max_att = (1 - 1/ratio) * max(db, 0); inc = max_att / attack; dec = max_att / release
-    std::vector<CurveEntry> tab(CURVE_N);
+    //        max_attenuation = (1 - 1/ratio) * max(db, 0)      (0 whenever rms <= thresh_rms)
+    std::vector<double> tab(CURVE_N);
     const double l10 = std::log(10.0);
     for (int r = 0; r < CURVE_N; ++r) {
         double over = 0.0;
@@ -346,15 +346,34 @@ static int get_curve(b200m_handle *h, const b200m_band &b, const CurveEntry **ou
             const double db = 20 * (std::log((double)r / b.thresh_rms) / l10);
             over = db > 0 ? db : 0.0;
         }
-        const double M = b.slope * over;
-        tab[r] = {M, M / b.attack_frames, M / b.release_frames, 0.0};
+        double M = b.slope * over;
+        if (M == 0) M = 0.0;                     // no negative zero: decisions are integer compares
+        tab[r] = M;
     }
-    CurveEntry *d = nullptr;
-    CK(cudaMalloc(&d, CURVE_N * sizeof(CurveEntry)));
-    CK(cudaMemcpy(d, tab.data(), CURVE_N * sizeof(CurveEntry), cudaMemcpyHostToDevice));
+    if (host_copy) *host_copy = tab;
+    auto key = std::make_tuple(b.thresh_rms, b.slope);
+    auto it = h->curves.find(key);
+    if (it != h->curves.end()) { *out = it->second; return B200M_OK; }
+    double *d = nullptr;
+    CK(cudaMalloc(&d, CURVE_N * sizeof(double)));
+    CK(cudaMemcpy(d, tab.data(), CURVE_N * sizeof(double), cudaMemcpyHostToDevice));
     h->curves[key] = d;
     *out = d;
     return B200M_OK;
+}
+
+// Is q = fma(fma(-m*rc, c, m), rc, m*rc) the correctly rounded m / c for every curve value?
+static bool div_trick_exact(const std::vector<double> &tab, double c)
+{
+    if (!(c > 0) || !std::isfinite(c)) return false;
+    const double rc = 1.0 / c;
+    for (double m : tab) {
+        volatile double q = m * rc;
+        const double r = std::fma(-q, c, m);
+        const double q2 = std::fma(r, rc, q);
+        if (q2 != m / c) return false;
+    }
+    return true;
 }
 
 static int ensure_plans(b200m_handle *h, const b200m_plan *plans, int n)
@@ -383,9 +402,12 @@ static int ensure_plans(b200m_handle *h, const b200m_plan *plans, int n)
                 const b200m_band &bb = p.band[b];
                 if (bb.look_frames < 0 || bb.look_frames > 8192)
                     return fail(h, B200M_ERR_INVALID, "plan %d band %d: look_frames %d unsupported", i, b, bb.look_frames);
-                d.band[b] = {bb.thresh_rms, bb.attack_frames, bb.release_frames, bb.slope, bb.look_frames,
-                             (int32_t)std::floor(std::min(bb.thresh_rms, 1e9))};
-                int rc = get_curve(h, bb, &d.curve[b]);
+                std::vector<double> tab;
+                int rc = get_curve(h, bb, &d.curve[b], &tab);
+                if (rc) return rc;
+                const bool trick = div_trick_exact(tab, bb.attack_frames) && div_trick_exact(tab, bb.release_frames);
+                d.band[b] = {bb.thresh_rms, bb.attack_frames, bb.release_frames, bb.slope,
+                             1.0 / bb.attack_frames, 1.0 / bb.release_frames, bb.look_frames, trick ? 1 : 0};
                 if (rc) return rc;
             }
         }
@@ -449,6 +471,12 @@ extern "C" int b200m_create(int device, b200m_handle **out)
         delete h;
         return B200M_ERR_CUDA;
     }
+    if (cudaMalloc(&h->d_counters, 4 * sizeof(unsigned long long)) != cudaSuccess ||
+        cudaMemset(h->d_counters, 0, 4 * sizeof(unsigned long long)) != cudaSuccess) {
+        fail(nullptr, B200M_ERR_CUDA, "counter allocation failed");
+        delete h;
+        return B200M_ERR_CUDA;
+    }
     *out = h;
     return B200M_OK;
 }
@@ -461,6 +489,7 @@ extern "C" void b200m_destroy(b200m_handle *h)
     if (h->ws) cudaFree(h->ws);
     if (h->d_plans) cudaFree(h->d_plans);
     if (h->pin) cudaFreeHost(h->pin);
+    if (h->d_counters) cudaFree(h->d_counters);
     for (auto &kv : h->curves) cudaFree(kv.second);
     for (auto &r : h->prof_recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
     for (auto e : h->ev_pool) cudaEventDestroy(e);
@@ -513,6 +542,29 @@ extern "C" int b200m_kernel_time_ms(b200m_handle *h, const char *kernel, double 
     return B200M_OK;
 }
 
+extern "C" int b200m_set_recur_tiling(b200m_handle *h, int tile_frames, int warm_frames, int rounds)
+{
+    if (!h || tile_frames < 0 || warm_frames < 0 || rounds > 64) return B200M_ERR_INVALID;
+    h->recur_tile = tile_frames;
+    h->recur_warm = warm_frames > 0 ? warm_frames : 32768;
+    h->recur_rounds = rounds < 0 ? 4 : rounds;
+    return B200M_OK;
+}
+
+extern "C" int b200m_recur_stats(b200m_handle *h, int64_t *wrong_tiles, int64_t *rerun_frames, int64_t *round_repairs, int reset)
+{
+    if (!h) return B200M_ERR_INVALID;
+    CK(cudaSetDevice(h->device));
+    unsigned long long c[4];
+    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaMemcpy(c, h->d_counters, sizeof c, cudaMemcpyDeviceToHost));
+    if (wrong_tiles) *wrong_tiles = (int64_t)c[0];
+    if (rerun_frames) *rerun_frames = (int64_t)c[1];
+    if (round_repairs) *round_repairs = (int64_t)c[2];
+    if (reset) CK(cudaMemset(h->d_counters, 0, sizeof c));
+    return B200M_OK;
+}
+
 extern "C" int b200m_reset_profile(b200m_handle *h)
 {
     if (!h) return B200M_ERR_INVALID;
@@ -531,19 +583,66 @@ struct Group {
     int64_t max_track_frames = 0;
     int max_blocks = 0;
     int max_look = 0;
+    int64_t total_blocks = 0;        // hold-flag WORDS: sum over streams of ceil(out_frames / 1024)
     bool any_multiband = false, any_lufs = false;
     const StreamDesc *d_streams = nullptr;
     const TrackDesc *d_tracks = nullptr;
 };
 
-static int launch_compressor(b200m_handle *h, const Group &g, const BandPtrs &bp, int nbands, int band_base, int16_t *d_proc)
+static RecurParams recur_params(const b200m_handle *h, const Group &g, int nbands, int band_base)
+{
+    const int chains = std::max(1, g.n_streams * nbands);
+    RecurParams P;
+    P.nbands = nbands; P.band_base = band_base; P.n_streams = g.n_streams;
+    P.warm = std::max(32, (h->recur_warm + 31) & ~31);
+    if (h->recur_tile > 0) {
+        P.tile_len = std::max(32, (h->recur_tile + 31) & ~31);
+    } else {
+        // enough (chain, tile) lanes to give every SM several warps; tiles no shorter than 32768 frames
+        // (a wrong guess usually meets the true trajectory within a few 10^4 frames)
+        const int want = (148 * 512 + chains - 1) / chains;
+        const int tiles = std::max(1, std::min(want, g.max_stream_frames / 32768));
+        P.tile_len = ((g.max_stream_frames + tiles - 1) / tiles + 31) & ~31;
+    }
+    P.tiles = std::max(1, (g.max_stream_frames + P.tile_len - 1) / P.tile_len);
+    return P;
+}
+
+static size_t recur_spec_doubles(const b200m_handle *h, const Group &g, int nbands)
+{
+    const RecurParams P = recur_params(h, g, nbands, 0);
+    return 5 * (size_t)g.n_streams * nbands * P.tiles;       // ss / se ping-pong + per-tile activity counts
+}
+
+static int launch_compressor(b200m_handle *h, const Group &g, const BandPtrs &bp, int nbands, int band_base, int16_t *d_proc, double *d_spec)
 {
     const dim3 gd((g.max_stream_frames + DT - 1) / DT, g.n_streams, nbands);
     const size_t smem = detect_smem_bytes(g.max_look);
     if (g.ch == 2) LAUNCH("k_detect", k_detect<2><<<gd, DNT, smem, h->stream>>>(g.d_streams, h->d_plans, bp, band_base));
     else           LAUNCH("k_detect", k_detect<1><<<gd, DNT, smem, h->stream>>>(g.d_streams, h->d_plans, bp, band_base));
     const int chains = g.n_streams * nbands;
-    LAUNCH("k_recur", k_recur<<<(chains + 31) / 32, 32, 0, h->stream>>>(g.d_streams, h->d_plans, g.n_streams, nbands, band_base, bp));
+    const RecurParams P = recur_params(h, g, nbands, band_base);
+    const size_t lanes = (size_t)chains * P.tiles;
+    RecurParams P0 = P;
+    P0.mode = 0;
+    double *ss[2] = {d_spec, d_spec + 2 * lanes}, *se[2] = {d_spec + lanes, d_spec + 3 * lanes};
+    int *tcnt = reinterpret_cast<int *>(d_spec + 4 * lanes);
+    const unsigned gr = (unsigned)((lanes + 32 * RW - 1) / (32 * RW));
+    LAUNCH("k_recur_count", k_recur_count<<<(unsigned)((lanes + 127) / 128), 128, 0, h->stream>>>(g.d_streams, h->d_plans, P0, bp, tcnt));
+    LAUNCH("k_recur_tiles", k_recur_tiles<<<gr, 32 * RW, 0, h->stream>>>(g.d_streams, h->d_plans, P0, bp, tcnt, nullptr, nullptr,
+                                                                        ss[0], se[0], h->d_counters));
+    int cur = 0;
+    if (P.tiles > 1) {
+        RecurParams P1 = P;
+        P1.mode = 1;
+        for (int round = 0; round < h->recur_rounds; ++round) {      // parallel repair rounds
+            LAUNCH("k_recur_repair", k_recur_tiles<<<gr, 32 * RW, 0, h->stream>>>(g.d_streams, h->d_plans, P1, bp, tcnt, ss[cur], se[cur],
+                                                                             ss[cur ^ 1], se[cur ^ 1], h->d_counters));
+            cur ^= 1;
+        }
+    }
+    LAUNCH("k_recur_fix", k_recur_fix<<<(chains + 31) / 32, 32, 0, h->stream>>>(
+                              g.d_streams, h->d_plans, P, bp, ss[cur], se[cur], h->d_counters));
     const dim3 ga((g.max_stream_frames + 255) / 256, g.n_streams);
     if (g.ch == 2) LAUNCH("k_apply", k_apply<2><<<ga, 256, 0, h->stream>>>(g.d_streams, h->d_plans, bp, nbands, band_base, d_proc));
     else           LAUNCH("k_apply", k_apply<1><<<ga, 256, 0, h->stream>>>(g.d_streams, h->d_plans, bp, nbands, band_base, d_proc));
@@ -609,6 +708,8 @@ static int run_group(b200m_handle *h, const int16_t *pcm_in, bool in_dev, int t_
             sd.out_frames = (int32_t)std::min(chunk, out_frames[t] - s);
             sd.in_frames = (int32_t)std::max<int64_t>(0, std::min<int64_t>(sd.out_frames, in_frames[t] - s));
             sd.plan = plan_index[t]; sd.track = t - t_begin;
+            sd.blk_off = (int32_t)g.total_blocks; sd.pad_ = 0;
+            g.total_blocks += (sd.out_frames + 1023) / 1024;
             g.max_stream_frames = std::max(g.max_stream_frames, sd.out_frames);
             streams.push_back(sd);
         }
@@ -630,7 +731,7 @@ static int run_group(b200m_handle *h, const int16_t *pcm_in, bool in_dev, int t_
                   (size_t)zoff * 16 + 16 * 256;
     if (!in_dev) need += (size_t)in_total * ch * 2;
     if (!out_dev) need += (size_t)F * ch * 2;
-    if (g.any_multiband) need += (size_t)F * (3 * ch * 2 + 3 * 2 + 3 * 8) + 16 * 256;
+    if (g.any_multiband) need += (size_t)F * (3 * ch * 2 + 3 * 8 + 3 * 8) + 3 * 4 * (size_t)g.total_blocks + 20 * 256 + recur_spec_doubles(h, g, 3) * 8;
     int rc = ws_reserve(h, need);
     if (rc) return rc;
     rc = pin_reserve(h, desc_bytes + (size_t)g.n_tracks * 16);
@@ -647,11 +748,14 @@ static int run_group(b200m_handle *h, const int16_t *pcm_in, bool in_dev, int t_
     if (!in_dev) d_in = A.take<int16_t>((size_t)in_total * ch);
     if (!out_dev) d_out = A.take<int16_t>((size_t)F * ch);
     BandPtrs bp;
+    double *d_spec = nullptr;
     std::memset(&bp, 0, sizeof bp);
     if (g.any_multiband) {
         for (int b = 0; b < 3; ++b) bp.band[b] = A.take<int16_t>((size_t)F * ch);
-        for (int b = 0; b < 3; ++b) bp.rms[b] = A.take<uint16_t>(F);
+        for (int b = 0; b < 3; ++b) bp.matt[b] = A.take<double>(F);
         for (int b = 0; b < 3; ++b) bp.att[b] = A.take<double>(F);
+        for (int b = 0; b < 3; ++b) bp.hold[b] = A.take<uint32_t>(g.total_blocks + 1);
+        d_spec = A.take<double>(recur_spec_doubles(h, g, 3));
     }
     // descriptors: pinned staging -> device
     CK(cudaStreamSynchronize(h->stream));       // pinned staging may still be in flight
@@ -680,7 +784,7 @@ static int run_group(b200m_handle *h, const int16_t *pcm_in, bool in_dev, int t_
     if (ch == 2) LAUNCH("k_chain", k_chain<2><<<g.n_streams, NSEG * 2, chain_smem_bytes<2>(), h->stream>>>(d_src, d_streams, h->d_plans, d_proc, bp));
     else         LAUNCH("k_chain", k_chain<1><<<g.n_streams, NSEG * 1, chain_smem_bytes<1>(), h->stream>>>(d_src, d_streams, h->d_plans, d_proc, bp));
     CK(cudaGetLastError());
-    if (g.any_multiband) { rc = launch_compressor(h, g, bp, 3, 0, d_proc); if (rc) return rc; }
+    if (g.any_multiband) { rc = launch_compressor(h, g, bp, 3, 0, d_proc, d_spec); if (rc) return rc; }
     rc = launch_loudness(h, g, d_proc, nullptr, d_kw, d_z, d_zsel, d_loud);
     if (rc) return rc;
     const dim3 gf((unsigned)std::min<int64_t>((g.max_track_frames + 255) / 256, 8192), g.n_tracks);
@@ -729,7 +833,7 @@ extern "C" int b200m_master_batch(b200m_handle *h, const void *pcm_in, int in_on
     int rc = ensure_plans(h, plans, n_plans);
     if (rc) return rc;
     // split into groups that fit the workspace limit
-    const double per_frame = ch * 2 * 3 + 4 + 3 * (ch * 2 + 2 + 8) + 1;
+    const double per_frame = ch * 2 * 3 + 4 + 3 * (ch * 2 + 8 + 8) + 1;
     int t0 = 0;
     int64_t out_base = 0;
     while (t0 < n_tracks) {
@@ -864,26 +968,32 @@ extern "C" int b200m_multiband(b200m_handle *h, const b200m_plan *plan, const in
     if (rc) return rc;
     const int ch = p.channels;
     const size_t F = (size_t)nframes;
-    rc = ws_reserve(h, 8192 + F * ch * 2 * 5 + F * (3 * 2 + 3 * 8) + 16 * 256);
+    Group g;
+    g.ch = ch; g.n_streams = 1; g.n_tracks = 1; g.max_stream_frames = (int)nframes;
+    for (int b = 0; b < 3; ++b) g.max_look = std::max(g.max_look, p.band[b].look_frames);
+    const size_t nspec = recur_spec_doubles(h, g, 3);
+    g.total_blocks = (nframes + 1023) / 1024;
+    rc = ws_reserve(h, 8192 + F * ch * 2 * 5 + F * (3 * 8 + 3 * 8) + 12 * (size_t)g.total_blocks + nspec * 8 + 20 * 256);
     if (rc) return rc;
     Arena A(h->ws);
     StreamDesc *d_streams = A.take<StreamDesc>(1);
     int16_t *d_in = A.take<int16_t>(F * ch);
     int16_t *d_proc = A.take<int16_t>(F * ch);
     BandPtrs bp;
+    std::memset(&bp, 0, sizeof bp);
     for (int b = 0; b < 3; ++b) bp.band[b] = A.take<int16_t>(F * ch);
-    for (int b = 0; b < 3; ++b) bp.rms[b] = A.take<uint16_t>(F);
+    for (int b = 0; b < 3; ++b) bp.matt[b] = A.take<double>(F);
     for (int b = 0; b < 3; ++b) bp.att[b] = A.take<double>(F);
-    StreamDesc sd = {0, 0, (int32_t)nframes, (int32_t)nframes, 0, 0};
+    for (int b = 0; b < 3; ++b) bp.hold[b] = A.take<uint32_t>(g.total_blocks + 1);
+    double *d_spec = A.take<double>(nspec);
+    StreamDesc sd = {0, 0, (int32_t)nframes, (int32_t)nframes, 0, 0, 0, 0};
     CK(cudaMemcpyAsync(d_streams, &sd, sizeof sd, cudaMemcpyHostToDevice, h->stream));
     CK(cudaMemcpyAsync(d_in, pcm, F * ch * 2, cudaMemcpyHostToDevice, h->stream));
-    Group g;
-    g.ch = ch; g.n_streams = 1; g.n_tracks = 1; g.max_stream_frames = (int)nframes; g.d_streams = d_streams;
-    for (int b = 0; b < 3; ++b) g.max_look = std::max(g.max_look, p.band[b].look_frames);
+    g.d_streams = d_streams;
     if (ch == 2) LAUNCH("k_chain", k_chain<2><<<1, NSEG * 2, chain_smem_bytes<2>(), h->stream>>>(d_in, d_streams, h->d_plans, d_proc, bp));
     else         LAUNCH("k_chain", k_chain<1><<<1, NSEG * 1, chain_smem_bytes<1>(), h->stream>>>(d_in, d_streams, h->d_plans, d_proc, bp));
     CK(cudaGetLastError());
-    rc = launch_compressor(h, g, bp, 3, 0, d_proc);
+    rc = launch_compressor(h, g, bp, 3, 0, d_proc, d_spec);
     if (rc) return rc;
     CK(cudaMemcpyAsync(out, d_proc, F * ch * 2, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
@@ -906,7 +1016,12 @@ extern "C" int b200m_compress_dynamic_range(b200m_handle *h, const int16_t *pcm,
     int rc = ensure_plans(h, &p, 1);
     if (rc) return rc;
     const size_t F = (size_t)nframes;
-    rc = ws_reserve(h, 8192 + F * channels * 2 * 2 + F * (2 + 8) + 8 * 256);
+    Group g;
+    g.ch = channels; g.n_streams = 1; g.n_tracks = 1; g.max_stream_frames = (int)nframes;
+    g.max_look = band->look_frames;
+    const size_t nspec = recur_spec_doubles(h, g, 1);
+    g.total_blocks = (nframes + 1023) / 1024;
+    rc = ws_reserve(h, 8192 + F * channels * 2 * 2 + F * (2 + 8 + 8) + 4 * (size_t)g.total_blocks + nspec * 8 + 10 * 256);
     if (rc) return rc;
     Arena A(h->ws);
     StreamDesc *d_streams = A.take<StreamDesc>(1);
@@ -916,14 +1031,15 @@ extern "C" int b200m_compress_dynamic_range(b200m_handle *h, const int16_t *pcm,
     std::memset(&bp, 0, sizeof bp);
     bp.band[0] = d_in;
     bp.rms[0] = A.take<uint16_t>(F);
+    bp.matt[0] = A.take<double>(F);
     bp.att[0] = A.take<double>(F);
-    StreamDesc sd = {0, 0, (int32_t)nframes, (int32_t)nframes, 0, 0};
+    bp.hold[0] = A.take<uint32_t>(g.total_blocks + 1);
+    double *d_spec = A.take<double>(nspec);
+    StreamDesc sd = {0, 0, (int32_t)nframes, (int32_t)nframes, 0, 0, 0, 0};
     CK(cudaMemcpyAsync(d_streams, &sd, sizeof sd, cudaMemcpyHostToDevice, h->stream));
     CK(cudaMemcpyAsync(d_in, pcm, F * channels * 2, cudaMemcpyHostToDevice, h->stream));
-    Group g;
-    g.ch = channels; g.n_streams = 1; g.n_tracks = 1; g.max_stream_frames = (int)nframes; g.d_streams = d_streams;
-    g.max_look = band->look_frames;
-    rc = launch_compressor(h, g, bp, 1, 0, d_proc);
+    g.d_streams = d_streams;
+    rc = launch_compressor(h, g, bp, 1, 0, d_proc, d_spec);
     if (rc) return rc;
     CK(cudaMemcpyAsync(out, d_proc, F * channels * 2, cudaMemcpyDeviceToHost, h->stream));
     if (att_out) CK(cudaMemcpyAsync(att_out, bp.att[0], F * 8, cudaMemcpyDeviceToHost, h->stream));

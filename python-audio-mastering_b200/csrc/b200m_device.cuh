@@ -39,12 +39,13 @@ static_assert(sizeof(SecTab) == 192 * 8, "SecTab layout");
 
 struct BandDev {
     double thresh_rms, attack_frames, release_frames, slope;
-    int32_t look;       // int(attack_frames)
-    int32_t rthr;       // floor(thresh_rms): rms > thresh_rms  <=>  rms > rthr (rms integer)
+    double r_attack, r_release;   // correctly rounded 1/attack_frames, 1/release_frames
+    int32_t look;                 // int(attack_frames)
+    int32_t div_trick;            // 1: M/A and M/R via div_const are exact for this band's curve
 };
 
-// Compressor static curve, tabulated over the 32769 possible integer RMS values.
-struct CurveEntry { double max_att, inc, dec, pad_; };
+// Compressor static curve: max attenuation M for each of the 32769 possible integer RMS
+// values (0.0 when rms <= threshold, which also encodes "hold").
 constexpr int CURVE_N = 32769;
 
 struct PlanDev {
@@ -52,7 +53,7 @@ struct PlanDev {
     float sat_clean, sat_mix, sat_drive, pad1_;
     double width, lufs;
     BandDev band[3];
-    const CurveEntry *curve[3];   // device pointers, CURVE_N entries each (NULL if !multiband)
+    const double *curve[3];       // device pointers, CURVE_N doubles each (NULL if !multiband)
     SecTab eq[4], lp[2], hp[2], kw[2];
 };
 
@@ -63,6 +64,8 @@ struct StreamDesc {     // one (track, chunk)
     int32_t out_frames; // frames to produce
     int32_t plan;
     int32_t track;
+    int32_t blk_off;    // first 32-frame block of this stream in the per-band hold-flag arrays
+    int32_t pad_;
 };
 
 struct TrackDesc {

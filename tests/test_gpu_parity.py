@@ -118,6 +118,34 @@ def test_compressor_trajectory_bit_exact(eng):
                           eng.compress_dynamic_range(mono, make_band(rate, -30.0, 2.0, 3.3, 77.0)))
 
 
+def test_recurrence_tiling_is_exact_for_any_tile_length(eng):
+    """k_recur_tiles speculates every time tile from a warm-up and k_recur_fix repairs wrong guesses:
+    the trajectory must be bit-identical to the sequential oracle for ANY tile / warm-up length,
+    including ones so short that most guesses are wrong."""
+    from b200master import synth
+    from b200master.plan import make_band
+    from oracle import port
+    rate = 48000
+    q1 = port.process_chunk(synth.make_track(41, 6.0, rate), rate, dict(bass_boost=4.0, treble_boost=3.0))
+    bands = port.split_bands(q1, rate)
+    try:
+        for tile, warm, rounds in [(32, 32, 0), (32, 32, 3), (256, 64, 2), (4096, 1024, 4), (8192, 32768, 1), (0, 0, -1)]:
+            eng.set_recur_tiling(tile, warm, rounds)
+            eng.recur_stats(reset=True)
+            for b, (thr, ratio), (att, rel) in zip(bands, port.band_params({"high_thresh": -30.0}), port.BAND_TIMES):
+                ro, ra, _ = port.compress_band(b, rate, thr, ratio, att, rel, debug=True)
+                go, ga, _ = eng.compress_dynamic_range(b, make_band(rate, thr, ratio, att, rel), debug=True)
+                assert np.array_equal(ra, ga), f"attenuation differs with tile={tile} warm={warm} rounds={rounds}"
+                assert np.array_equal(ro, go)
+            st = eng.recur_stats()
+            if tile == 32:
+                assert st["wrong_tiles"] + st["round_repairs"] > 0, "a 32-frame warm-up cannot always guess right: a repair path must have run"
+            if tile == 32 and rounds == 0:
+                assert st["wrong_tiles"] > 0 and st["round_repairs"] == 0
+    finally:
+        eng.set_recur_tiling(0, 0, -1)
+
+
 @pytest.mark.parametrize("rate,seconds", [(44100, 61.0), (48000, 35.0)])
 def test_oracle_multi_chunk(eng, rate, seconds):
     """Fresh seeded multi-chunk tracks (saturation 0 => bit-exact), oracle with the C compressor."""
