@@ -120,9 +120,15 @@ int b200m_reset_profile(b200m_handle *h);
 /* Compressor recurrence tiling: each (chunk, band) attenuation chain is cut into time tiles that
  * run in parallel after a warm-up over the preceding `warm_frames` (k_recur_tiles), wrong guesses
  * are repaired in `rounds` parallel passes and finally by an exact sequential pass (k_recur_fix).
- * tile_frames = 0: automatic tile length; warm_frames = 0: default 32768; rounds < 0: default 4.
+ * tile_frames = 0: automatic tile length; warm_frames = 0: default 8192 (counted in frames of
+ * 32-frame blocks with any activity; silent stretches carry the state unchanged); rounds < 0: default 4.
  * Results never depend on any of the three. */
 int b200m_set_recur_tiling(b200m_handle *h, int tile_frames, int warm_frames, int rounds);
+/* Time segmentation of the filter kernels: k_chain (2048-frame tiles) and k_kweight (4096-sample
+ * tiles) cut every stream / track into segments of this many tiles, one CTA each, joined by
+ * overlap-discard with a warm-up derived from the pole radii (fp64-exact decay).  0 = automatic,
+ * negative = off (one CTA walks the whole stream).  Results do not depend on it. */
+int b200m_set_segment_tiles(b200m_handle *h, int chain_tiles, int kweight_tiles);
 /* Verification counters since the last reset: tiles repaired by the sequential pass, frames it
  * re-ran, and tiles repaired in the parallel rounds. */
 int b200m_recur_stats(b200m_handle *h, int64_t *wrong_tiles, int64_t *rerun_frames, int64_t *round_repairs, int reset);

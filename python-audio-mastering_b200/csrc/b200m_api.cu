@@ -46,7 +46,9 @@ struct b200m_handle {
     std::map<std::string, std::pair<double, int64_t>> prof_acc;
     int64_t launches = 0;
     // recurrence tiling (0 = automatic) and its verification counters
-    int recur_tile = 0, recur_warm = 32768, recur_rounds = 4;
+    int recur_tile = 0, recur_warm = 8192, recur_rounds = 4;
+    // time segmentation of k_chain / k_kweight: 0 = automatic, < 0 = off, > 0 = tiles per segment
+    int seg_chain = 0, seg_kweight = 0;
     unsigned long long *d_counters = nullptr;
 };
 
@@ -298,6 +300,53 @@ static void design_band(double rate, double thr_db, double ratio, double attack_
     b->reserved = 0;
 }
 
+// Frames after which a section's homogeneous response has decayed below 2^-64 (nothing in fp64).
+static double settle_frames(const b200m_biquad &q)
+{
+    double r;
+    const double disc = q.a1 * q.a1 - 4.0 * q.a2;
+    if (disc < 0) r = std::sqrt(q.a2);
+    else r = std::max(std::fabs((-q.a1 + std::sqrt(disc)) / 2), std::fabs((-q.a1 - std::sqrt(disc)) / 2));
+    if (!(r < 1.0)) return 1e30;
+    if (r < 1e-6) return 3.0;
+    return std::ceil(44.4 / -std::log(r)) + 2.0;
+}
+
+// Warm-up (frames) that makes a k_chain / k_kweight segment independent of what came before it:
+// the sections of a cascade settle one after the other, parallel branches (LP / HP) together.
+static double chain_warm_frames(const b200m_plan &p)
+{
+    double w = 0;
+    for (int s = 0; s < p.n_eq; ++s) w += settle_frames(p.eq[s]);
+    if (p.multiband)
+        w += std::max(settle_frames(p.lp[0]) + settle_frames(p.lp[1]), settle_frames(p.hp[0]) + settle_frames(p.hp[1]));
+    return w;
+}
+
+static double kweight_warm_frames(const b200m_plan &p) { return settle_frames(p.kw[0]) + settle_frames(p.kw[1]); }
+
+// Cut [0, frames) into segments of about `seg_tiles` tiles (never shorter than twice the warm-up);
+// a single segment when seg_tiles <= 0 or the warm-up is unbounded / too long.
+static void make_segments(std::vector<SegDesc> &out, int owner, int64_t frames, int tile, double warm_frames, int seg_tiles)
+{
+    if (frames <= 0) return;
+    const int64_t ntiles = (frames + tile - 1) / tile;
+    const double warm_tiles = std::ceil(warm_frames / tile);
+    if (seg_tiles <= 0 || !(warm_tiles <= 64)) { out.push_back({0, frames, owner, 0}); return; }
+    const int64_t seg = std::max<int64_t>(seg_tiles, 2 * (int64_t)warm_tiles);
+    if (ntiles <= seg) { out.push_back({0, frames, owner, 0}); return; }
+    const int warm = (int)warm_tiles * tile;
+    for (int64_t t = 0; t < ntiles; t += seg) {
+        const int64_t b = t * tile, e = std::min<int64_t>(frames, (t + seg) * tile);
+        out.push_back({b, e, owner, b == 0 ? 0 : warm});
+    }
+}
+
+static int auto_seg_tiles(int64_t total_tiles, int lo, int hi)
+{
+    return (int)std::max<int64_t>(lo, std::min<int64_t>(hi, total_tiles / (148 * 6)));
+}
+
 extern "C" int b200m_plan_from_settings(const b200m_settings *s, int sample_rate, int channels, b200m_plan *p)
 {
     if (!s || !p || sample_rate <= 0 || (channels != 1 && channels != 2)) return B200M_ERR_INVALID;
@@ -546,8 +595,16 @@ extern "C" int b200m_set_recur_tiling(b200m_handle *h, int tile_frames, int warm
 {
     if (!h || tile_frames < 0 || warm_frames < 0 || rounds > 64) return B200M_ERR_INVALID;
     h->recur_tile = tile_frames;
-    h->recur_warm = warm_frames > 0 ? warm_frames : 32768;
+    h->recur_warm = warm_frames > 0 ? warm_frames : 8192;
     h->recur_rounds = rounds < 0 ? 4 : rounds;
+    return B200M_OK;
+}
+
+extern "C" int b200m_set_segment_tiles(b200m_handle *h, int chain_tiles, int kweight_tiles)
+{
+    if (!h) return B200M_ERR_INVALID;
+    h->seg_chain = chain_tiles;
+    h->seg_kweight = kweight_tiles;
     return B200M_OK;
 }
 
@@ -587,6 +644,8 @@ struct Group {
     bool any_multiband = false, any_lufs = false;
     const StreamDesc *d_streams = nullptr;
     const TrackDesc *d_tracks = nullptr;
+    const SegDesc *d_csegs = nullptr, *d_ksegs = nullptr;   // k_chain / k_kweight segments
+    int n_csegs = 0, n_ksegs = 0;
 };
 
 static RecurParams recur_params(const b200m_handle *h, const Group &g, int nbands, int band_base)
@@ -598,10 +657,9 @@ static RecurParams recur_params(const b200m_handle *h, const Group &g, int nband
     if (h->recur_tile > 0) {
         P.tile_len = std::max(32, (h->recur_tile + 31) & ~31);
     } else {
-        // enough (chain, tile) lanes to give every SM several warps; tiles no shorter than 32768 frames
-        // (a wrong guess usually meets the true trajectory within a few 10^4 frames)
-        const int want = (148 * 512 + chains - 1) / chains;
-        const int tiles = std::max(1, std::min(want, g.max_stream_frames / 32768));
+        // enough (chain, tile) lanes to fill every SM with warps; tiles no shorter than 8192 frames
+        const int want = (148 * 1024 + chains - 1) / chains;
+        const int tiles = std::max(1, std::min(want, g.max_stream_frames / 8192));
         P.tile_len = ((g.max_stream_frames + tiles - 1) / tiles + 31) & ~31;
     }
     P.tiles = std::max(1, (g.max_stream_frames + P.tile_len - 1) / P.tile_len);
@@ -654,9 +712,9 @@ static int launch_loudness(b200m_handle *h, const Group &g, const int16_t *d_pro
                            float *d_kw, double *d_z, double *d_zsel, double2 *d_loud)
 {
     if (g.any_lufs) {
-        if (d_mono)         LAUNCH("k_kweight", k_kweight<1, float><<<g.n_tracks, KNT, kweight_smem_bytes(), h->stream>>>(d_mono, g.d_tracks, h->d_plans, d_kw));
-        else if (g.ch == 2) LAUNCH("k_kweight", k_kweight<2, int16_t><<<g.n_tracks, KNT, kweight_smem_bytes(), h->stream>>>(d_proc, g.d_tracks, h->d_plans, d_kw));
-        else                LAUNCH("k_kweight", k_kweight<1, int16_t><<<g.n_tracks, KNT, kweight_smem_bytes(), h->stream>>>(d_proc, g.d_tracks, h->d_plans, d_kw));
+        if (d_mono)         LAUNCH("k_kweight", k_kweight<1, float><<<g.n_ksegs, KNT, kweight_smem_bytes(), h->stream>>>(d_mono, g.d_tracks, g.d_ksegs, h->d_plans, d_kw));
+        else if (g.ch == 2) LAUNCH("k_kweight", k_kweight<2, int16_t><<<g.n_ksegs, KNT, kweight_smem_bytes(), h->stream>>>(d_proc, g.d_tracks, g.d_ksegs, h->d_plans, d_kw));
+        else                LAUNCH("k_kweight", k_kweight<1, int16_t><<<g.n_ksegs, KNT, kweight_smem_bytes(), h->stream>>>(d_proc, g.d_tracks, g.d_ksegs, h->d_plans, d_kw));
         const dim3 gb((g.max_blocks + 127) / 128, g.n_tracks);
         if (g.max_blocks > 0) LAUNCH("k_blocks", k_blocks<<<gb, 128, 0, h->stream>>>(d_kw, g.d_tracks, h->d_plans, d_z));
     }
@@ -717,6 +775,20 @@ static int run_group(b200m_handle *h, const int16_t *pcm_in, bool in_dev, int t_
         in_total += in_frames[t];
     }
     g.n_streams = (int)streams.size();
+    std::vector<SegDesc> csegs, ksegs;
+    {
+        int64_t ctiles = 0, ktiles = 0;
+        for (auto &sd : streams) ctiles += (sd.out_frames + TILE - 1) / TILE;
+        for (auto &td : tracks) ktiles += (td.frames + KTILE - 1) / KTILE;
+        const int cs = h->seg_chain == 0 ? auto_seg_tiles(ctiles, 8, 48) : h->seg_chain;
+        const int ks = h->seg_kweight == 0 ? auto_seg_tiles(ktiles, 8, 32) : h->seg_kweight;
+        for (size_t i = 0; i < streams.size(); ++i)
+            make_segments(csegs, (int)i, streams[i].out_frames, TILE, chain_warm_frames(plans[streams[i].plan]), cs);
+        for (size_t i = 0; i < tracks.size(); ++i)
+            if (plans[tracks[i].plan].has_lufs)
+                make_segments(ksegs, (int)i, tracks[i].frames, KTILE, kweight_warm_frames(plans[tracks[i].plan]), ks);
+        g.n_csegs = (int)csegs.size(); g.n_ksegs = (int)ksegs.size();
+    }
     if (F == 0) {
         for (int t = t_begin; t < t_end; ++t) {
             if (loudness_out) loudness_out[t] = NAN;
@@ -726,19 +798,23 @@ static int run_group(b200m_handle *h, const int16_t *pcm_in, bool in_dev, int t_
     }
 
     // ---- workspace ---------------------------------------------------------------
-    const size_t desc_bytes = streams.size() * sizeof(StreamDesc) + tracks.size() * sizeof(TrackDesc);
-    size_t need = 4096 + desc_bytes + (size_t)g.n_tracks * 16 + (size_t)F * ch * 2 /*proc*/ + (size_t)F * 4 /*kw*/ +
+    const size_t desc_bytes = streams.size() * sizeof(StreamDesc) + tracks.size() * sizeof(TrackDesc) +
+                              (csegs.size() + ksegs.size()) * sizeof(SegDesc);
+    size_t need = 8192 + desc_bytes + (size_t)g.n_tracks * 16 + (size_t)F * ch * 2 /*proc*/ + (size_t)F * 4 /*kw*/ +
                   (size_t)zoff * 16 + 16 * 256;
     if (!in_dev) need += (size_t)in_total * ch * 2;
     if (!out_dev) need += (size_t)F * ch * 2;
     if (g.any_multiband) need += (size_t)F * (3 * ch * 2 + 3 * 8 + 3 * 8) + 3 * 4 * (size_t)g.total_blocks + 20 * 256 + recur_spec_doubles(h, g, 3) * 8;
     int rc = ws_reserve(h, need);
     if (rc) return rc;
-    rc = pin_reserve(h, desc_bytes + (size_t)g.n_tracks * 16);
+    const size_t res_off = (desc_bytes + 63) & ~(size_t)63;     // double2 results: 16-byte aligned slot after the descriptors
+    rc = pin_reserve(h, res_off + (size_t)g.n_tracks * 16);
     if (rc) return rc;
     Arena A(h->ws);
     StreamDesc *d_streams = A.take<StreamDesc>(streams.size());
     TrackDesc *d_tracks = A.take<TrackDesc>(tracks.size());
+    SegDesc *d_csegs = A.take<SegDesc>(csegs.size() + 1);
+    SegDesc *d_ksegs = A.take<SegDesc>(ksegs.size() + 1);
     double2 *d_loud = A.take<double2>(g.n_tracks);
     int16_t *d_proc = A.take<int16_t>((size_t)F * ch);
     float *d_kw = A.take<float>(F);
@@ -759,12 +835,21 @@ static int run_group(b200m_handle *h, const int16_t *pcm_in, bool in_dev, int t_
     }
     // descriptors: pinned staging -> device
     CK(cudaStreamSynchronize(h->stream));       // pinned staging may still be in flight
-    std::memcpy(h->pin, streams.data(), streams.size() * sizeof(StreamDesc));
-    std::memcpy(h->pin + streams.size() * sizeof(StreamDesc), tracks.data(), tracks.size() * sizeof(TrackDesc));
-    CK(cudaMemcpyAsync(d_streams, h->pin, streams.size() * sizeof(StreamDesc), cudaMemcpyHostToDevice, h->stream));
-    CK(cudaMemcpyAsync(d_tracks, h->pin + streams.size() * sizeof(StreamDesc), tracks.size() * sizeof(TrackDesc),
-                       cudaMemcpyHostToDevice, h->stream));
-    g.d_streams = d_streams; g.d_tracks = d_tracks;
+    {
+        char *pp = h->pin;
+        auto up = [&](void *dst, const void *src, size_t bytes) -> cudaError_t {
+            if (!bytes) return cudaSuccess;
+            std::memcpy(pp, src, bytes);
+            cudaError_t e = cudaMemcpyAsync(dst, pp, bytes, cudaMemcpyHostToDevice, h->stream);
+            pp += bytes;
+            return e;
+        };
+        CK(up(d_streams, streams.data(), streams.size() * sizeof(StreamDesc)));
+        CK(up(d_tracks, tracks.data(), tracks.size() * sizeof(TrackDesc)));
+        CK(up(d_csegs, csegs.data(), csegs.size() * sizeof(SegDesc)));
+        CK(up(d_ksegs, ksegs.data(), ksegs.size() * sizeof(SegDesc)));
+    }
+    g.d_streams = d_streams; g.d_tracks = d_tracks; g.d_csegs = d_csegs; g.d_ksegs = d_ksegs;
 
     // ---- input staging -------------------------------------------------------------
     const int16_t *d_src = pcm_in;
@@ -781,8 +866,8 @@ static int run_group(b200m_handle *h, const int16_t *pcm_in, bool in_dev, int t_
     int16_t *d_dst = out_dev ? pcm_out + out_base * ch : d_out;
 
     // ---- kernels -------------------------------------------------------------------
-    if (ch == 2) LAUNCH("k_chain", k_chain<2><<<g.n_streams, NSEG * 2, chain_smem_bytes<2>(), h->stream>>>(d_src, d_streams, h->d_plans, d_proc, bp));
-    else         LAUNCH("k_chain", k_chain<1><<<g.n_streams, NSEG * 1, chain_smem_bytes<1>(), h->stream>>>(d_src, d_streams, h->d_plans, d_proc, bp));
+    if (ch == 2) LAUNCH("k_chain", k_chain<2><<<g.n_csegs, NSEG * 2, chain_smem_bytes<2>(), h->stream>>>(d_src, d_streams, d_csegs, h->d_plans, d_proc, bp));
+    else         LAUNCH("k_chain", k_chain<1><<<g.n_csegs, NSEG * 1, chain_smem_bytes<1>(), h->stream>>>(d_src, d_streams, d_csegs, h->d_plans, d_proc, bp));
     CK(cudaGetLastError());
     if (g.any_multiband) { rc = launch_compressor(h, g, bp, 3, 0, d_proc, d_spec); if (rc) return rc; }
     rc = launch_loudness(h, g, d_proc, nullptr, d_kw, d_z, d_zsel, d_loud);
@@ -795,7 +880,7 @@ static int run_group(b200m_handle *h, const int16_t *pcm_in, bool in_dev, int t_
     // ---- results -------------------------------------------------------------------
     if (!out_dev) CK(cudaMemcpyAsync(pcm_out + out_base * ch, d_out, (size_t)F * ch * 2, cudaMemcpyDeviceToHost, h->stream));
     if (loudness_out || gain_out) {
-        double2 *hl = reinterpret_cast<double2 *>(h->pin + desc_bytes);
+        double2 *hl = reinterpret_cast<double2 *>(h->pin + res_off);
         CK(cudaMemcpyAsync(hl, d_loud, (size_t)g.n_tracks * 16, cudaMemcpyDeviceToHost, h->stream));
         CK(cudaStreamSynchronize(h->stream));
         for (int t = t_begin; t < t_end; ++t) {
@@ -977,6 +1062,7 @@ extern "C" int b200m_multiband(b200m_handle *h, const b200m_plan *plan, const in
     if (rc) return rc;
     Arena A(h->ws);
     StreamDesc *d_streams = A.take<StreamDesc>(1);
+    SegDesc *d_csegs = A.take<SegDesc>(1);
     int16_t *d_in = A.take<int16_t>(F * ch);
     int16_t *d_proc = A.take<int16_t>(F * ch);
     BandPtrs bp;
@@ -989,9 +1075,11 @@ extern "C" int b200m_multiband(b200m_handle *h, const b200m_plan *plan, const in
     StreamDesc sd = {0, 0, (int32_t)nframes, (int32_t)nframes, 0, 0, 0, 0};
     CK(cudaMemcpyAsync(d_streams, &sd, sizeof sd, cudaMemcpyHostToDevice, h->stream));
     CK(cudaMemcpyAsync(d_in, pcm, F * ch * 2, cudaMemcpyHostToDevice, h->stream));
+    SegDesc sg = {0, (int64_t)nframes, 0, 0};
+    CK(cudaMemcpyAsync(d_csegs, &sg, sizeof sg, cudaMemcpyHostToDevice, h->stream));
     g.d_streams = d_streams;
-    if (ch == 2) LAUNCH("k_chain", k_chain<2><<<1, NSEG * 2, chain_smem_bytes<2>(), h->stream>>>(d_in, d_streams, h->d_plans, d_proc, bp));
-    else         LAUNCH("k_chain", k_chain<1><<<1, NSEG * 1, chain_smem_bytes<1>(), h->stream>>>(d_in, d_streams, h->d_plans, d_proc, bp));
+    if (ch == 2) LAUNCH("k_chain", k_chain<2><<<1, NSEG * 2, chain_smem_bytes<2>(), h->stream>>>(d_in, d_streams, d_csegs, h->d_plans, d_proc, bp));
+    else         LAUNCH("k_chain", k_chain<1><<<1, NSEG * 1, chain_smem_bytes<1>(), h->stream>>>(d_in, d_streams, d_csegs, h->d_plans, d_proc, bp));
     CK(cudaGetLastError());
     rc = launch_compressor(h, g, bp, 3, 0, d_proc, d_spec);
     if (rc) return rc;
@@ -1063,10 +1151,13 @@ static int loudness_core(b200m_handle *h, const b200m_biquad *kw, const float *x
     if (rc) return rc;
     TrackDesc td = {0, n, 0, num_blocks(n, rate), 0};
     const size_t ns = (size_t)n * channels;
-    rc = ws_reserve(h, 8192 + ns * 4 + (size_t)n * 8 + (scaled_out ? ns * 8 : 0) + (size_t)(td.nblocks + 2) * 16);
+    rc = ws_reserve(h, 65536 + ns * 4 + (size_t)n * 8 + (scaled_out ? ns * 8 : 0) + (size_t)(td.nblocks + 2) * 16 + (size_t)(n / KTILE + 2) * sizeof(SegDesc));
     if (rc) return rc;
     Arena A(h->ws);
     TrackDesc *d_tracks = A.take<TrackDesc>(1);
+    std::vector<SegDesc> ksegs;
+    make_segments(ksegs, 0, n, KTILE, kweight_warm_frames(p), h->seg_kweight == 0 ? auto_seg_tiles((n + KTILE - 1) / KTILE, 8, 32) : h->seg_kweight);
+    SegDesc *d_ksegs = A.take<SegDesc>(ksegs.size());
     double2 *d_loud = A.take<double2>(1);
     float *d_x = A.take<float>(ns);
     float *d_mono = channels == 2 ? A.take<float>(n) : d_x;
@@ -1075,10 +1166,12 @@ static int loudness_core(b200m_handle *h, const b200m_biquad *kw, const float *x
     double *d_zsel = A.take<double>(td.nblocks + 1);
     double *d_scaled = scaled_out ? A.take<double>(ns) : nullptr;
     CK(cudaMemcpyAsync(d_tracks, &td, sizeof td, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(d_ksegs, ksegs.data(), ksegs.size() * sizeof(SegDesc), cudaMemcpyHostToDevice, h->stream));
     CK(cudaMemcpyAsync(d_x, x, ns * 4, cudaMemcpyHostToDevice, h->stream));
     if (channels == 2) LAUNCH("k_mono_mean", k_mono_mean<<<grid_for(n), 256, 0, h->stream>>>(d_x, n, d_mono));
     Group g;
     g.ch = 1; g.n_tracks = 1; g.d_tracks = d_tracks; g.max_blocks = td.nblocks; g.any_lufs = true; g.max_track_frames = n;
+    g.d_ksegs = d_ksegs; g.n_ksegs = (int)ksegs.size();
     rc = launch_loudness(h, g, nullptr, d_mono, d_kw, d_z, d_zsel, d_loud);
     if (rc) return rc;
     if (scaled_out) {

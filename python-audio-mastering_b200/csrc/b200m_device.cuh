@@ -68,6 +68,17 @@ struct StreamDesc {     // one (track, chunk)
     int32_t pad_;
 };
 
+// A time segment of a stream (k_chain) or of a track (k_kweight): one CTA each.  Segments are
+// joined by overlap-discard: the CTA starts `warm` frames early from zero state and only
+// stores [begin, end).  `warm` is chosen at plan time from the pole radii so that the
+// homogeneous response has decayed below 2^-64 (i.e. to nothing in fp64) by `begin`; segments
+// that start at frame 0 of their owner are exact by construction (zero state, ENG:48-54).
+struct SegDesc {
+    int64_t begin, end; // frames relative to the owner's first frame; begin is a tile multiple
+    int32_t owner;      // stream index (k_chain) or track index (k_kweight)
+    int32_t warm;       // tile multiple
+};
+
 struct TrackDesc {
     int64_t off;        // first frame in the flat workspace buffers
     int64_t frames;     // out frames

@@ -24,7 +24,7 @@ struct BandPtrs {
 // =====================================================================================
 template <int CH>
 __global__ void __launch_bounds__(NSEG * CH, (CH == 2 ? 2 : 4))
-k_chain(const int16_t *__restrict__ pcm_in, const StreamDesc *__restrict__ streams,
+k_chain(const int16_t *__restrict__ pcm_in, const StreamDesc *__restrict__ streams, const SegDesc *__restrict__ segs,
         const PlanDev *__restrict__ plans, int16_t *__restrict__ proc, BandPtrs bp)
 {
     constexpr int NT = NSEG * CH;
@@ -36,7 +36,8 @@ k_chain(const int16_t *__restrict__ pcm_in, const StreamDesc *__restrict__ strea
     double *wtot = carry + 8 * CH * 2;                                   // [2][CH][4][2]
     int16_t *stg = reinterpret_cast<int16_t *>(sy);                      // aliases sy: [3][TILE_PAD][CH]
 
-    const StreamDesc sd = streams[blockIdx.x];
+    const SegDesc sg = segs[blockIdx.x];
+    const StreamDesc sd = streams[sg.owner];
     const PlanDev *__restrict__ pl = plans + sd.plan;
     const int tid = threadIdx.x;
     const int c = tid / NSEG, j = tid % NSEG, lane = tid & 31, wid = j >> 5;
@@ -57,8 +58,10 @@ k_chain(const int16_t *__restrict__ pcm_in, const StreamDesc *__restrict__ strea
     float *myx = sx + c * TILE_PAD + j * (SEG + 1);
     unsigned round = 0;
 
-    for (int t0 = 0; t0 < sd.out_frames; t0 += TILE) {
-        const int nvalid = min(TILE, sd.out_frames - t0);
+    const int seg_begin = (int)sg.begin, seg_end = (int)sg.end;
+    for (int t0 = max(0, seg_begin - sg.warm); t0 < seg_end; t0 += TILE) {
+        const bool store = t0 >= seg_begin;          // warm-up tiles only advance the filter states
+        const int nvalid = store ? min(TILE, seg_end - t0) : 0;
         // ---- stage: coalesced interleaved int16 -> planar float32 (+ exciter) ----------
         for (int f = tid; f < TILE; f += NT) {
             const int gf = t0 + f;
@@ -383,6 +386,7 @@ k_recur_tiles(const StreamDesc *__restrict__ streams, const PlanDev *__restrict_
               unsigned long long *__restrict__ counters)
 {
     __shared__ double s_m[RW][32][33];      // M rows in, attenuation rows out (same slots)
+    __shared__ ulonglong2 s_in[RW][32], s_out[RW][32];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int gl = (blockIdx.x * RW + warp) * 32 + lane;
     const int chain = gl / P.tiles, tile = gl % P.tiles;
@@ -430,6 +434,7 @@ k_recur_tiles(const StreamDesc *__restrict__ streams, const PlanDev *__restrict_
         }
     }
     const double a_in = a;
+    const bool all_exact = __all_sync(FULL, exact || !live);
     // Every lane walks its own cursor over 32-frame blocks [wstart, end): held blocks of the
     // warm-up are skipped outright (the state cannot change there), so the warp iterates
     // max-over-lanes of the blocks that need work, not the span.
@@ -456,49 +461,51 @@ k_recur_tiles(const StreamDesc *__restrict__ streams, const PlanDev *__restrict_
         // the value this tile stored earlier at the end of this block (repair rounds only)
         double old_last = 0.0;
         if (P.mode == 1 && on) old_last = out[i0 + cnt - 1];
-        const int ldc = held ? 0 : cnt;
-        // ---- coalesced row loads: row q = lane q's next 32 values of M --------------------
-        const unsigned long long rp = (unsigned long long)(m + i0);
+        // ---- row descriptors through smem: {pointer, count} of every lane's next block ----
+        s_in[warp][lane] = make_ulonglong2((unsigned long long)(m + i0), (unsigned long long)(held ? 0 : cnt));
+        s_out[warp][lane] = make_ulonglong2((unsigned long long)(out + i0), (unsigned long long)(is_main ? cnt : 0));
+        __syncwarp();
+        // ---- coalesced row loads: row q = lane q's next 32 values of M (0 beyond its count:
+        //      M = 0 is a hold, i.e. an identity step, so partial and held rows need no branches)
 #pragma unroll
         for (int q0 = 0; q0 < 32; q0 += 8) {
             double v[8];
-            int cc[8];
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-                const unsigned long long p = __shfl_sync(FULL, rp, q0 + j);
-                cc[j] = __shfl_sync(FULL, ldc, q0 + j);
-                v[j] = lane < cc[j] ? __ldg(reinterpret_cast<const double *>(p) + lane) : 0.0;
+                const ulonglong2 dsc = s_in[warp][q0 + j];
+                v[j] = lane < (int)dsc.y ? __ldg(reinterpret_cast<const double *>(dsc.x) + lane) : 0.0;
             }
 #pragma unroll
-            for (int j = 0; j < 8; ++j)
-                if (lane < cc[j]) s_m[warp][q0 + j][lane] = v[j];
+            for (int j = 0; j < 8; ++j) s_m[warp][q0 + j][lane] = v[j];
         }
         __syncwarp();
-        // ---- up to 32 dependent steps -----------------------------------------------------
-        if (on) {
-            if (held) {
-#pragma unroll 8
-                for (int k = 0; k < 32; ++k) s_m[warp][lane][k] = a;
-            } else {
+        // ---- 32 dependent steps -------------------------------------------------------------
+        if (all_exact) {            // warp-uniform: every band of this warp passed the plan-time division check
+            if (on) {
 #pragma unroll 8
                 for (int k = 0; k < 32; ++k) {
-                    const double M = k < cnt ? s_m[warp][lane][k] : 0.0;
-                    const double inc = div_const(M, A, rA, exact), dec = div_const(M, R, rR, exact);
-                    const double an = recur_step(a, M, inc, dec);
-                    a = k < cnt ? an : a;
+                    const double M = s_m[warp][lane][k];
+                    const double inc = div_const(M, A, rA, true), dec = div_const(M, R, rR, true);
+                    a = recur_step(a, M, inc, dec);
                     s_m[warp][lane][k] = a;
                 }
+            }
+        } else if (on) {
+#pragma unroll 1
+            for (int k = 0; k < 32; ++k) {
+                const double M = s_m[warp][lane][k];
+                const double inc = div_const(M, A, rA, exact), dec = div_const(M, R, rR, exact);
+                a = recur_step(a, M, inc, dec);
+                s_m[warp][lane][k] = a;
             }
         }
         __syncwarp();
         // ---- coalesced row stores of the attenuation (main part of the tile only) ---------
-        const unsigned long long op = (unsigned long long)(out + i0);
         if (__any_sync(FULL, is_main)) {
-#pragma unroll 4
+#pragma unroll 8
             for (int q = 0; q < 32; ++q) {
-                const unsigned long long p = __shfl_sync(FULL, op, q);
-                const int c = __shfl_sync(FULL, is_main ? cnt : 0, q);
-                if (lane < c) reinterpret_cast<double *>(p)[lane] = s_m[warp][q][lane];
+                const ulonglong2 dsc = s_out[warp][q];
+                if (lane < (int)dsc.y) reinterpret_cast<double *>(dsc.x)[lane] = s_m[warp][q][lane];
             }
         }
         if (P.mode == 1 && on && __double_as_longlong(a) == __double_as_longlong(old_last)) merged = true;
@@ -619,7 +626,7 @@ constexpr int KTILE_PAD = KTILE + KNT;
 
 template <int CH, typename IN>
 __global__ void __launch_bounds__(KNT, 2)
-k_kweight(const IN *__restrict__ src_all, const TrackDesc *__restrict__ tracks,
+k_kweight(const IN *__restrict__ src_all, const TrackDesc *__restrict__ tracks, const SegDesc *__restrict__ segs,
           const PlanDev *__restrict__ plans, float *__restrict__ kw)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -627,7 +634,8 @@ k_kweight(const IN *__restrict__ src_all, const TrackDesc *__restrict__ tracks,
     float *sx = reinterpret_cast<float *>(smem_raw + 2 * sizeof(SecTab));   // [KTILE_PAD]
     double *carry = reinterpret_cast<double *>(sx + KTILE_PAD + (KTILE_PAD & 1)); // [2][2]
     double *wtot = carry + 4;                                               // [2][8][2]
-    const TrackDesc td = tracks[blockIdx.x];
+    const SegDesc sg = segs[blockIdx.x];
+    const TrackDesc td = tracks[sg.owner];
     const PlanDev *__restrict__ pl = plans + td.plan;
     if (!pl->has_lufs) return;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -642,11 +650,13 @@ k_kweight(const IN *__restrict__ src_all, const TrackDesc *__restrict__ tracks,
     float *__restrict__ dst = kw + td.off;
     float *myx = sx + tid * (SEG + 1);
     unsigned round = 0;
-    for (int64_t t0 = 0; t0 < td.frames; t0 += KTILE) {
-        const int nvalid = (int)min((int64_t)KTILE, td.frames - t0);
+    for (int64_t t0 = max((int64_t)0, sg.begin - sg.warm); t0 < sg.end; t0 += KTILE) {
+        const bool store = t0 >= sg.begin;           // warm-up tiles only advance the filter states
+        const int nload = (int)min((int64_t)KTILE, td.frames - t0);
+        const int nvalid = store ? (int)min((int64_t)KTILE, sg.end - t0) : 0;
         for (int f = tid; f < KTILE; f += KNT) {
             float m = 0.0f;
-            if (f < nvalid) {
+            if (f < nload) {
                 if (sizeof(IN) == 2) {
                     if (CH == 2) {
                         const short2 q = *reinterpret_cast<const short2 *>(

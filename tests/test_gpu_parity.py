@@ -5,9 +5,13 @@ engine and (2) the CPU oracle on freshly seeded inputs.
 Tolerances (north star: <= 1e-4 FS, loudness within 0.01 LU, 16-bit within +-1 LSB):
   * every stage except the float32 tanh exciter is compared BIT-EXACT;
   * whole-chain cases with saturation == 0 are BIT-EXACT (samples and loudness);
-  * whole-chain cases with saturation != 0 inherit numpy's <= 1-ulp float32 tanh (a SIMD
-    approximation that is not IEEE-reproducible): >= 99 % of samples exact, the rest within
-    SAT_MAX_LSB, loudness within 1e-5 LU.
+  * whole-chain cases with saturation != 0 inherit numpy's float32 tanh, a SIMD polynomial
+    that is neither correctly rounded nor the same on every CPU (AVX-512 / AVX2 / libm
+    dispatch): CUDA tanhf agrees with it on ~90 % of inputs and is within 1 ulp on the rest.
+    A 1-ulp difference flips a truncating quantiser (ENG:125) on ~1e-3 of samples by ONE LSB;
+    that LSB then passes through the make-up gain of ENG:219-222.  The bound is therefore
+    one LSB *ahead of the gain*: |diff| <= ceil(gain) LSB at the output, >= 99 % of samples
+    bit-exact, loudness within 1e-5 LU (north star: 0.01 LU).
 """
 import json
 import math
@@ -20,8 +24,7 @@ from conftest import golden_names, load_golden
 
 pytestmark = pytest.mark.gpu
 
-SAT_MAX_LSB = 4          # 1.2e-4 FS, reached on < 1e-4 of samples; see module docstring
-SAT_MIN_EXACT = 0.99
+SAT_MIN_EXACT = 0.99     # see module docstring
 
 
 @pytest.fixture(scope="module")
@@ -35,15 +38,15 @@ def eng():
     assert e.launch_count() > n0, "no CUDA kernel was launched: the native path did not run"
 
 
-def _compare(out, ref, saturated):
+def _compare(out, ref, saturated, gain=None):
     assert out.shape == ref.shape
     d = np.abs(out.astype(np.int32) - ref.astype(np.int32))
     if not saturated:
         assert d.max(initial=0) == 0, f"{int((d != 0).sum())} samples differ, max {int(d.max())} LSB"
     else:
-        assert d.max(initial=0) <= SAT_MAX_LSB
+        lim = 1 if gain is None or not math.isfinite(gain) else max(1, math.ceil(gain))
+        assert d.max(initial=0) <= lim, f"max {int(d.max())} LSB > {lim} (= one LSB ahead of the x{gain} make-up gain)"
         assert np.mean(d == 0) >= SAT_MIN_EXACT
-        assert np.mean(d <= 1) >= 0.999
 
 
 @pytest.mark.parametrize("name", golden_names())
@@ -51,7 +54,7 @@ def test_golden_whole_chain(eng, name):
     g = load_golden(name)
     outs, infos = eng.master([g["pcm"]], g["rate"], g["settings"])
     sat = g["settings"].get("saturation", 0) != 0
-    _compare(outs[0], g["out"], sat)
+    _compare(outs[0], g["out"], sat, infos[0]["gain"])
     if g["settings"].get("lufs") is not None:
         got, ref = infos[0]["loudness"], g["loudness"]
         if math.isinf(ref):
@@ -67,8 +70,8 @@ def test_golden_batch_mixed_settings(eng):
     names = ["cfg1_pop_44k", "cfg2_full_44k", "no_lufs_no_eq", "rock_custom_bands", "ragged_tail_a", "silence"]
     gs = [load_golden(n) for n in names]
     outs, infos = eng.master([g["pcm"] for g in gs], 44100, [g["settings"] for g in gs])
-    for g, o in zip(gs, outs):
-        _compare(o, g["out"], g["settings"].get("saturation", 0) != 0)
+    for g, o, i in zip(gs, outs, infos):
+        _compare(o, g["out"], g["settings"].get("saturation", 0) != 0, i["gain"])
 
 
 def test_stage_goldens(eng):
@@ -242,3 +245,23 @@ def test_drop_in_module_surface(eng, tmp_path):
     empty = tmp_path / "empty"; empty.mkdir()
     ame.batch_process_audio(st, str(empty), str(tmp_path / "o3"), msgs.append)
     assert "no audio files" in msgs[-1].lower()
+
+
+def test_time_segmentation_is_invisible(eng):
+    """k_chain / k_kweight cut streams into overlap-discard segments (warm-up from the pole radii):
+    the output must be bit-identical to the unsegmented walk, for any segment length."""
+    from b200master import synth
+    rate = 48000
+    pcm = synth.make_track(70, 20.0, rate)
+    st = dict(bass_boost=5.0, mid_cut=4.0, presence_boost=2.0, treble_boost=3.5, saturation=30, width=1.3,
+              multiband=True, lufs=-12.0)
+    try:
+        eng.set_segment_tiles(-1, -1)
+        base, binfo = eng.master([pcm], rate, st)
+        for ct, kt in [(8, 8), (16, 4), (0, 0)]:
+            eng.set_segment_tiles(ct, kt)
+            out, info = eng.master([pcm], rate, st)
+            assert np.array_equal(out[0], base[0]), f"segment tiles ({ct}, {kt}) changed the output"
+            assert info[0]["loudness"] == binfo[0]["loudness"]
+    finally:
+        eng.set_segment_tiles(0, 0)
