@@ -136,3 +136,19 @@ def test_product_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", src, re.M), f"{f} imports oracle"
+
+
+def test_struct_layouts_match_the_header(tmp_path):
+    """ctypes mirrors of include/b200_master.h have the C compiler's sizes (INTEGRATION.md quotes them)."""
+    import ctypes as C
+    import subprocess
+    from b200master import lib as L
+    src = tmp_path / "sz.c"
+    src.write_text('#include <stdio.h>\n#include "%s"\nint main(void){printf("%%zu %%zu %%zu %%zu\\n", sizeof(b200m_plan), '
+                   'sizeof(b200m_band), sizeof(b200m_biquad), sizeof(b200m_settings));return 0;}\n'
+                   % os.path.join(ROOT, "include", "b200_master.h"))
+    exe = tmp_path / "sz"
+    subprocess.check_call(["gcc", str(src), "-o", str(exe)])
+    sizes = [int(v) for v in subprocess.check_output([str(exe)]).split()]
+    assert sizes == [C.sizeof(L.Plan), C.sizeof(L.Band), C.sizeof(L.Biquad), C.sizeof(L.Settings)]
+    assert sizes[0] == 576
