@@ -129,6 +129,11 @@ int b200m_set_recur_tiling(b200m_handle *h, int tile_frames, int warm_frames, in
  * overlap-discard with a warm-up derived from the pole radii (fp64-exact decay).  0 = automatic,
  * negative = off (one CTA walks the whole stream).  Results do not depend on it. */
 int b200m_set_segment_tiles(b200m_handle *h, int chain_tiles, int kweight_tiles);
+/* Host-buffer pipeline of b200m_master_batch: with host PCM the batch is cut into groups of
+ * tracks and the H2D copy of group g+1 / D2H copy of group g-1 run on side streams while the
+ * kernels of group g run (two workspace slots).  on = 0 runs copy -> kernels -> copy in sequence.
+ * Default on.  Results do not depend on it. */
+int b200m_set_pipeline(b200m_handle *h, int on);
 /* Verification counters since the last reset: tiles repaired by the sequential pass, frames it
  * re-ran, and tiles repaired in the parallel rounds. */
 int b200m_recur_stats(b200m_handle *h, int64_t *wrong_tiles, int64_t *rerun_frames, int64_t *round_repairs, int reset);

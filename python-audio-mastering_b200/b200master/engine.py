@@ -84,6 +84,9 @@ class Engine:
     def set_segment_tiles(self, chain_tiles: int = 0, kweight_tiles: int = 0):
         self._ck(self._lib.b200m_set_segment_tiles(self._h, int(chain_tiles), int(kweight_tiles)))
 
+    def set_pipeline(self, on: bool = True):
+        self._ck(self._lib.b200m_set_pipeline(self._h, int(on)))
+
     def recur_stats(self, reset: bool = False):
         a, b, c = C.c_int64(), C.c_int64(), C.c_int64()
         self._ck(self._lib.b200m_recur_stats(self._h, C.byref(a), C.byref(b), C.byref(c), int(reset)))

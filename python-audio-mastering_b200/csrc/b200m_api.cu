@@ -35,6 +35,8 @@ struct b200m_handle {
     PlanDev *d_plans = nullptr;
     size_t d_plans_cap = 0;
     std::map<std::tuple<double, double>, double *> curves;
+    std::map<int, std::pair<int32_t *, int>> pw_trees;      // block length -> (device table, smem floats)
+    int blocks_smem_floats = 0;                              // max over the current plans
     // pinned staging for descriptors / small results
     char *pin = nullptr;
     size_t pin_cap = 0;
@@ -50,6 +52,10 @@ struct b200m_handle {
     // time segmentation of k_chain / k_kweight: 0 = automatic, < 0 = off, > 0 = tiles per segment
     int seg_chain = 0, seg_kweight = 0;
     unsigned long long *d_counters = nullptr;
+    // host-buffer pipeline: side streams for H2D / D2H and the events that order the groups
+    bool pipeline = true;
+    cudaStream_t s_in = nullptr, s_out = nullptr;
+    std::vector<cudaEvent_t> sync_events;
 };
 
 static std::string g_create_err;
@@ -411,6 +417,69 @@ static int get_curve(b200m_handle *h, const b200m_band &b, const double **out, s
     return B200M_OK;
 }
 
+// numpy's pairwise_sum recursion tree for n elements (numpy/_core/src/umath/loops_utils.h.src):
+//   n <= 128: leaf;  else n2 = n / 2, n2 -= n2 % 8, sum(a, n2) + sum(a + n2, n - n2).
+// Table: [n, nleaves, ninternal, nlevels, level_start[nlevels + 1], leaf_off[], leaf_n[], node_l[], node_r[]];
+// internal nodes are ordered deepest level first (the root is last) and store to value slot
+// nleaves + i; children are value slots.
+static void build_pw_tree(int n, std::vector<int32_t> &tab)
+{
+    struct Node { int l, r, depth; };
+    std::vector<int32_t> leaf_off, leaf_n;
+    std::vector<Node> internal;
+    struct Rec {
+        std::vector<int32_t> &lo, &ln; std::vector<Node> &in;
+        int run(int off, int cnt, int depth)
+        {
+            if (cnt <= 128) { lo.push_back(off); ln.push_back(cnt); return (int)lo.size() - 1; }
+            int n2 = cnt / 2;
+            n2 -= n2 % 8;
+            const int L = run(off, n2, depth + 1), R = run(off + n2, cnt - n2, depth + 1);
+            in.push_back({L, R, depth});
+            return -(int)in.size();
+        }
+    } rec{leaf_off, leaf_n, internal};
+    rec.run(0, n, 0);
+    const int nl = (int)leaf_off.size(), ni = (int)internal.size();
+    std::vector<int> order(ni), pos(ni);
+    for (int i = 0; i < ni; ++i) order[i] = i;
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return internal[a].depth > internal[b].depth; });
+    for (int i = 0; i < ni; ++i) pos[order[i]] = i;
+    std::vector<int32_t> lvl;
+    for (int i = 0; i < ni; ++i)
+        if (i == 0 || internal[order[i]].depth != internal[order[i - 1]].depth) lvl.push_back(i);
+    const int nlev = (int)lvl.size();
+    lvl.push_back(ni);
+    auto slot = [&](int id) { return id >= 0 ? id : nl + pos[-id - 1]; };
+    tab.clear();
+    tab.push_back(n); tab.push_back(nl); tab.push_back(ni); tab.push_back(nlev);
+    tab.insert(tab.end(), lvl.begin(), lvl.end());
+    tab.insert(tab.end(), leaf_off.begin(), leaf_off.end());
+    tab.insert(tab.end(), leaf_n.begin(), leaf_n.end());
+    for (int i = 0; i < ni; ++i) tab.push_back(slot(internal[order[i]].l));
+    for (int i = 0; i < ni; ++i) tab.push_back(slot(internal[order[i]].r));
+}
+
+static int get_pw_tree(b200m_handle *h, int n, const int32_t **out, int *smem_floats)
+{
+    *out = nullptr; *smem_floats = 0;
+    if (n < 8 || n > (1 << 22)) return B200M_OK;             // tiny / absurd block lengths: serial walk
+    auto it = h->pw_trees.find(n);
+    if (it == h->pw_trees.end()) {
+        std::vector<int32_t> tab;
+        build_pw_tree(n, tab);
+        const int floats = tab[1] + tab[2];
+        int32_t *d = nullptr;
+        if (floats * 4 <= 40 * 1024) {
+            CK(cudaMalloc(&d, tab.size() * sizeof(int32_t)));
+            CK(cudaMemcpy(d, tab.data(), tab.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+        }
+        it = h->pw_trees.emplace(n, std::make_pair(d, d ? floats : 0)).first;
+    }
+    *out = it->second.first; *smem_floats = it->second.second;
+    return B200M_OK;
+}
+
 // Is q = fma(fma(-m*rc, c, m), rc, m*rc) the correctly rounded m / c for every curve value?
 static bool div_trick_exact(const std::vector<double> &tab, double c)
 {
@@ -432,6 +501,7 @@ static int ensure_plans(b200m_handle *h, const b200m_plan *plans, int n)
         return B200M_OK;
     CK(cudaStreamSynchronize(h->stream));   // previous launches may still read d_plans
     h->plans_host.assign(n, PlanDev());
+    h->blocks_smem_floats = 0;
     for (int i = 0; i < n; ++i) {
         const b200m_plan &p = plans[i];
         PlanDev &d = h->plans_host[i];
@@ -445,6 +515,13 @@ static int ensure_plans(b200m_handle *h, const b200m_plan *plans, int n)
         for (int s = 0; s < p.n_eq; ++s) build_sectab(p.eq[s], d.eq[s]);
         build_sectab(p.kw[0], d.kw[0]);
         build_sectab(p.kw[1], d.kw[1]);
+        if (p.has_lufs) {
+            // full block length: u - l of pyloudnorm's block 0 = int(0.4 * 1.0 * rate) - 0
+            int fl = 0;
+            int rc = get_pw_tree(h, (int)(int64_t)(0.4 * (0.0 * 0.25 + 1.0) * (double)p.sample_rate), &d.ptree, &fl);
+            if (rc) return rc;
+            h->blocks_smem_floats = std::max(h->blocks_smem_floats, fl);
+        }
         if (p.multiband) {
             for (int s = 0; s < 2; ++s) { build_sectab(p.lp[s], d.lp[s]); build_sectab(p.hp[s], d.hp[s]); }
             for (int b = 0; b < 3; ++b) {
@@ -510,6 +587,7 @@ extern "C" int b200m_create(int device, b200m_handle **out)
     if (e == cudaSuccess) e = allow_smem(k_chain<2>, chain_smem_bytes<2>());
     if (e == cudaSuccess) e = allow_smem(k_detect<1>, detect_smem_bytes(8192));
     if (e == cudaSuccess) e = allow_smem(k_detect<2>, detect_smem_bytes(8192));
+    if (e == cudaSuccess) e = allow_smem(k_recur_tiles, recur_smem_bytes());
     if (e == cudaSuccess) e = allow_smem(k_kweight<1, int16_t>, kweight_smem_bytes());
     if (e == cudaSuccess) e = allow_smem(k_kweight<2, int16_t>, kweight_smem_bytes());
     if (e == cudaSuccess) e = allow_smem(k_kweight<1, float>, kweight_smem_bytes());
@@ -540,8 +618,12 @@ extern "C" void b200m_destroy(b200m_handle *h)
     if (h->pin) cudaFreeHost(h->pin);
     if (h->d_counters) cudaFree(h->d_counters);
     for (auto &kv : h->curves) cudaFree(kv.second);
+    for (auto &kv : h->pw_trees) if (kv.second.first) cudaFree(kv.second.first);
     for (auto &r : h->prof_recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
     for (auto e : h->ev_pool) cudaEventDestroy(e);
+    for (auto e : h->sync_events) cudaEventDestroy(e);
+    if (h->s_in) cudaStreamDestroy(h->s_in);
+    if (h->s_out) cudaStreamDestroy(h->s_out);
     delete h;
 }
 
@@ -605,6 +687,13 @@ extern "C" int b200m_set_segment_tiles(b200m_handle *h, int chain_tiles, int kwe
     if (!h) return B200M_ERR_INVALID;
     h->seg_chain = chain_tiles;
     h->seg_kweight = kweight_tiles;
+    return B200M_OK;
+}
+
+extern "C" int b200m_set_pipeline(b200m_handle *h, int on)
+{
+    if (!h) return B200M_ERR_INVALID;
+    h->pipeline = on != 0;
     return B200M_OK;
 }
 
@@ -687,14 +776,14 @@ static int launch_compressor(b200m_handle *h, const Group &g, const BandPtrs &bp
     int *tcnt = reinterpret_cast<int *>(d_spec + 4 * lanes);
     const unsigned gr = (unsigned)((lanes + 32 * RW - 1) / (32 * RW));
     LAUNCH("k_recur_count", k_recur_count<<<(unsigned)((lanes + 127) / 128), 128, 0, h->stream>>>(g.d_streams, h->d_plans, P0, bp, tcnt));
-    LAUNCH("k_recur_tiles", k_recur_tiles<<<gr, 32 * RW, 0, h->stream>>>(g.d_streams, h->d_plans, P0, bp, tcnt, nullptr, nullptr,
+    LAUNCH("k_recur_tiles", k_recur_tiles<<<gr, 32 * RW, recur_smem_bytes(), h->stream>>>(g.d_streams, h->d_plans, P0, bp, tcnt, nullptr, nullptr,
                                                                         ss[0], se[0], h->d_counters));
     int cur = 0;
     if (P.tiles > 1) {
         RecurParams P1 = P;
         P1.mode = 1;
         for (int round = 0; round < h->recur_rounds; ++round) {      // parallel repair rounds
-            LAUNCH("k_recur_repair", k_recur_tiles<<<gr, 32 * RW, 0, h->stream>>>(g.d_streams, h->d_plans, P1, bp, tcnt, ss[cur], se[cur],
+            LAUNCH("k_recur_repair", k_recur_tiles<<<gr, 32 * RW, recur_smem_bytes(), h->stream>>>(g.d_streams, h->d_plans, P1, bp, tcnt, ss[cur], se[cur],
                                                                              ss[cur ^ 1], se[cur ^ 1], h->d_counters));
             cur ^= 1;
         }
@@ -715,8 +804,8 @@ static int launch_loudness(b200m_handle *h, const Group &g, const int16_t *d_pro
         if (d_mono)         LAUNCH("k_kweight", k_kweight<1, float><<<g.n_ksegs, KNT, kweight_smem_bytes(), h->stream>>>(d_mono, g.d_tracks, g.d_ksegs, h->d_plans, d_kw));
         else if (g.ch == 2) LAUNCH("k_kweight", k_kweight<2, int16_t><<<g.n_ksegs, KNT, kweight_smem_bytes(), h->stream>>>(d_proc, g.d_tracks, g.d_ksegs, h->d_plans, d_kw));
         else                LAUNCH("k_kweight", k_kweight<1, int16_t><<<g.n_ksegs, KNT, kweight_smem_bytes(), h->stream>>>(d_proc, g.d_tracks, g.d_ksegs, h->d_plans, d_kw));
-        const dim3 gb((g.max_blocks + 127) / 128, g.n_tracks);
-        if (g.max_blocks > 0) LAUNCH("k_blocks", k_blocks<<<gb, 128, 0, h->stream>>>(d_kw, g.d_tracks, h->d_plans, d_z));
+        const dim3 gb(g.max_blocks, g.n_tracks);
+        if (g.max_blocks > 0) LAUNCH("k_blocks", k_blocks<<<gb, BNT, (size_t)h->blocks_smem_floats * 4 + 16, h->stream>>>(d_kw, g.d_tracks, h->d_plans, d_z));
     }
     LAUNCH("k_gate", k_gate<<<g.n_tracks, 32, 0, h->stream>>>(g.d_tracks, h->d_plans, d_z, d_zsel, d_loud));
     CK(cudaGetLastError());
@@ -733,24 +822,39 @@ static int num_blocks(int64_t frames, int rate)
 
 // ------------------------------------------------------------------------------------
 // b200m_master_batch
+//
+// The batch is cut into *groups* of whole tracks.  A group is planned on the host
+// (plan_group: stream / track / segment descriptors and its workspace need) and executed
+// from a workspace slot (exec_group).  With device-resident PCM there is one slot and
+// everything runs on the handle's stream.  With HOST buffers the groups are pipelined over
+// two slots and three streams: the H2D copy of group g+1 and the D2H copy of group g-1
+// overlap the kernels of group g (copy engines vs SMs), ordered by events.
 // ------------------------------------------------------------------------------------
-static int run_group(b200m_handle *h, const int16_t *pcm_in, bool in_dev, int t_begin, int t_end,
-                     const int64_t *in_offsets, const int64_t *in_frames, const int64_t *out_frames,
-                     const b200m_plan *plans, const int32_t *plan_index,
-                     int16_t *pcm_out, bool out_dev, int64_t out_base,
-                     double *loudness_out, double *gain_out)
+struct GroupPlan {
+    int t_begin = 0, t_end = 0;
+    Group g;
+    std::vector<StreamDesc> streams;
+    std::vector<TrackDesc> tracks;
+    std::vector<SegDesc> csegs, ksegs;
+    int64_t F = 0, in_total = 0, zoff = 0, out_base = 0;
+    size_t desc_bytes = 0, res_off = 0, pin_bytes = 0, need = 0;
+};
+
+static void plan_group(const b200m_handle *h, GroupPlan &gp, bool in_dev, bool out_dev, int t_begin, int t_end,
+                       const int64_t *in_offsets, const int64_t *in_frames, const int64_t *out_frames,
+                       const b200m_plan *plans, const int32_t *plan_index, int64_t out_base)
 {
     const int ch = plans[0].channels, rate = plans[0].sample_rate;
     const int64_t chunk = 30LL * rate;          // ENG:48: 30 000 ms -> int(ms * rate / 1000) frames
-    Group g;
+    Group &g = gp.g;
+    gp.t_begin = t_begin; gp.t_end = t_end; gp.out_base = out_base;
     g.ch = ch;
     g.n_tracks = t_end - t_begin;
-    std::vector<StreamDesc> streams;
-    std::vector<TrackDesc> tracks(g.n_tracks);
+    gp.tracks.resize(g.n_tracks);
     int64_t F = 0, in_total = 0, zoff = 0;
     for (int t = t_begin; t < t_end; ++t) {
         const b200m_plan &p = plans[plan_index[t]];
-        TrackDesc &td = tracks[t - t_begin];
+        TrackDesc &td = gp.tracks[t - t_begin];
         td.off = F; td.frames = out_frames[t]; td.plan = plan_index[t];
         td.nblocks = p.has_lufs ? num_blocks(out_frames[t], rate) : 0;
         td.zoff = zoff; zoff += td.nblocks;
@@ -769,59 +873,63 @@ static int run_group(b200m_handle *h, const int16_t *pcm_in, bool in_dev, int t_
             sd.blk_off = (int32_t)g.total_blocks; sd.pad_ = 0;
             g.total_blocks += (sd.out_frames + 1023) / 1024;
             g.max_stream_frames = std::max(g.max_stream_frames, sd.out_frames);
-            streams.push_back(sd);
+            gp.streams.push_back(sd);
         }
         F += out_frames[t];
         in_total += in_frames[t];
     }
-    g.n_streams = (int)streams.size();
-    std::vector<SegDesc> csegs, ksegs;
+    g.n_streams = (int)gp.streams.size();
     {
         int64_t ctiles = 0, ktiles = 0;
-        for (auto &sd : streams) ctiles += (sd.out_frames + TILE - 1) / TILE;
-        for (auto &td : tracks) ktiles += (td.frames + KTILE - 1) / KTILE;
+        for (auto &sd : gp.streams) ctiles += (sd.out_frames + TILE - 1) / TILE;
+        for (auto &td : gp.tracks) ktiles += (td.frames + KTILE - 1) / KTILE;
         const int cs = h->seg_chain == 0 ? auto_seg_tiles(ctiles, 8, 48) : h->seg_chain;
         const int ks = h->seg_kweight == 0 ? auto_seg_tiles(ktiles, 8, 32) : h->seg_kweight;
-        for (size_t i = 0; i < streams.size(); ++i)
-            make_segments(csegs, (int)i, streams[i].out_frames, TILE, chain_warm_frames(plans[streams[i].plan]), cs);
-        for (size_t i = 0; i < tracks.size(); ++i)
-            if (plans[tracks[i].plan].has_lufs)
-                make_segments(ksegs, (int)i, tracks[i].frames, KTILE, kweight_warm_frames(plans[tracks[i].plan]), ks);
-        g.n_csegs = (int)csegs.size(); g.n_ksegs = (int)ksegs.size();
+        for (size_t i = 0; i < gp.streams.size(); ++i)
+            make_segments(gp.csegs, (int)i, gp.streams[i].out_frames, TILE, chain_warm_frames(plans[gp.streams[i].plan]), cs);
+        for (size_t i = 0; i < gp.tracks.size(); ++i)
+            if (plans[gp.tracks[i].plan].has_lufs)
+                make_segments(gp.ksegs, (int)i, gp.tracks[i].frames, KTILE, kweight_warm_frames(plans[gp.tracks[i].plan]), ks);
+        g.n_csegs = (int)gp.csegs.size(); g.n_ksegs = (int)gp.ksegs.size();
     }
-    if (F == 0) {
-        for (int t = t_begin; t < t_end; ++t) {
-            if (loudness_out) loudness_out[t] = NAN;
-            if (gain_out) gain_out[t] = 1.0;
-        }
-        return B200M_OK;
-    }
-
-    // ---- workspace ---------------------------------------------------------------
-    const size_t desc_bytes = streams.size() * sizeof(StreamDesc) + tracks.size() * sizeof(TrackDesc) +
-                              (csegs.size() + ksegs.size()) * sizeof(SegDesc);
-    size_t need = 8192 + desc_bytes + (size_t)g.n_tracks * 16 + (size_t)F * ch * 2 /*proc*/ + (size_t)F * 4 /*kw*/ +
-                  (size_t)zoff * 16 + 16 * 256;
+    gp.F = F; gp.in_total = in_total; gp.zoff = zoff;
+    gp.desc_bytes = gp.streams.size() * sizeof(StreamDesc) + gp.tracks.size() * sizeof(TrackDesc) +
+                    (gp.csegs.size() + gp.ksegs.size()) * sizeof(SegDesc);
+    gp.res_off = (gp.desc_bytes + 63) & ~(size_t)63;       // double2 results: 16-byte aligned slot after the descriptors
+    gp.pin_bytes = (gp.res_off + (size_t)g.n_tracks * 16 + 255) & ~(size_t)255;
+    size_t need = 16384 + gp.desc_bytes + (size_t)g.n_tracks * 16 + (size_t)F * ch * 2 /*proc*/ + (size_t)F * 4 /*kw*/ +
+                  (size_t)zoff * 16 + 24 * 256;
     if (!in_dev) need += (size_t)in_total * ch * 2;
     if (!out_dev) need += (size_t)F * ch * 2;
     if (g.any_multiband) need += (size_t)F * (3 * ch * 2 + 3 * 8 + 3 * 8) + 3 * 4 * (size_t)g.total_blocks + 20 * 256 + recur_spec_doubles(h, g, 3) * 8;
-    int rc = ws_reserve(h, need);
-    if (rc) return rc;
-    const size_t res_off = (desc_bytes + 63) & ~(size_t)63;     // double2 results: 16-byte aligned slot after the descriptors
-    rc = pin_reserve(h, res_off + (size_t)g.n_tracks * 16);
-    if (rc) return rc;
-    Arena A(h->ws);
-    StreamDesc *d_streams = A.take<StreamDesc>(streams.size());
-    TrackDesc *d_tracks = A.take<TrackDesc>(tracks.size());
-    SegDesc *d_csegs = A.take<SegDesc>(csegs.size() + 1);
-    SegDesc *d_ksegs = A.take<SegDesc>(ksegs.size() + 1);
+    gp.need = (need + 1023) & ~(size_t)1023;
+}
+
+struct ExecStreams {
+    cudaStream_t in, comp, out;             // equal when the group is not pipelined
+    cudaEvent_t slot_free, h2d_done, comp_done, d2h_done;   // null when not pipelined
+};
+
+static int exec_group(b200m_handle *h, GroupPlan &gp, char *ws, char *pin, const ExecStreams &X,
+                      const int16_t *pcm_in, bool in_dev, const int64_t *in_offsets, const int64_t *in_frames,
+                      int16_t *pcm_out, bool out_dev)
+{
+    Group &g = gp.g;
+    const int ch = g.ch;
+    const int64_t F = gp.F;
+    if (F == 0) return B200M_OK;
+    Arena A(ws);
+    StreamDesc *d_streams = A.take<StreamDesc>(gp.streams.size());
+    TrackDesc *d_tracks = A.take<TrackDesc>(gp.tracks.size());
+    SegDesc *d_csegs = A.take<SegDesc>(gp.csegs.size() + 1);
+    SegDesc *d_ksegs = A.take<SegDesc>(gp.ksegs.size() + 1);
     double2 *d_loud = A.take<double2>(g.n_tracks);
     int16_t *d_proc = A.take<int16_t>((size_t)F * ch);
     float *d_kw = A.take<float>(F);
-    double *d_z = A.take<double>(zoff + 1);
-    double *d_zsel = A.take<double>(zoff + 1);
+    double *d_z = A.take<double>(gp.zoff + 1);
+    double *d_zsel = A.take<double>(gp.zoff + 1);
     int16_t *d_in = nullptr, *d_out = nullptr;
-    if (!in_dev) d_in = A.take<int16_t>((size_t)in_total * ch);
+    if (!in_dev) d_in = A.take<int16_t>((size_t)gp.in_total * ch);
     if (!out_dev) d_out = A.take<int16_t>((size_t)F * ch);
     BandPtrs bp;
     double *d_spec = nullptr;
@@ -833,42 +941,47 @@ static int run_group(b200m_handle *h, const int16_t *pcm_in, bool in_dev, int t_
         for (int b = 0; b < 3; ++b) bp.hold[b] = A.take<uint32_t>(g.total_blocks + 1);
         d_spec = A.take<double>(recur_spec_doubles(h, g, 3));
     }
-    // descriptors: pinned staging -> device
-    CK(cudaStreamSynchronize(h->stream));       // pinned staging may still be in flight
+    if (A.used > gp.need) return fail(h, B200M_ERR_NOMEM, "internal: workspace estimate too small (%zu > %zu)", A.used, gp.need);
+
+    // ---- input stream: descriptors (pinned staging) and PCM -> device ----------------------
+    if (X.slot_free) CK(cudaStreamWaitEvent(X.in, X.slot_free, 0));    // the slot's previous group has left it
     {
-        char *pp = h->pin;
+        char *pp = pin;
         auto up = [&](void *dst, const void *src, size_t bytes) -> cudaError_t {
             if (!bytes) return cudaSuccess;
             std::memcpy(pp, src, bytes);
-            cudaError_t e = cudaMemcpyAsync(dst, pp, bytes, cudaMemcpyHostToDevice, h->stream);
+            cudaError_t e = cudaMemcpyAsync(dst, pp, bytes, cudaMemcpyHostToDevice, X.in);
             pp += bytes;
             return e;
         };
-        CK(up(d_streams, streams.data(), streams.size() * sizeof(StreamDesc)));
-        CK(up(d_tracks, tracks.data(), tracks.size() * sizeof(TrackDesc)));
-        CK(up(d_csegs, csegs.data(), csegs.size() * sizeof(SegDesc)));
-        CK(up(d_ksegs, ksegs.data(), ksegs.size() * sizeof(SegDesc)));
+        CK(up(d_streams, gp.streams.data(), gp.streams.size() * sizeof(StreamDesc)));
+        CK(up(d_tracks, gp.tracks.data(), gp.tracks.size() * sizeof(TrackDesc)));
+        CK(up(d_csegs, gp.csegs.data(), gp.csegs.size() * sizeof(SegDesc)));
+        CK(up(d_ksegs, gp.ksegs.data(), gp.ksegs.size() * sizeof(SegDesc)));
     }
     g.d_streams = d_streams; g.d_tracks = d_tracks; g.d_csegs = d_csegs; g.d_ksegs = d_ksegs;
-
-    // ---- input staging -------------------------------------------------------------
     const int16_t *d_src = pcm_in;
     if (!in_dev) {
         int64_t pos = 0;
-        for (int t = t_begin; t < t_end; ++t) {     // one cudaMemcpyAsync per track
-            if (in_frames[t] > 0)
-                CK(cudaMemcpyAsync(d_in + pos * ch, pcm_in + in_offsets[t] * ch, (size_t)in_frames[t] * ch * 2,
-                                   cudaMemcpyHostToDevice, h->stream));
-            pos += in_frames[t];
+        for (int t = gp.t_begin; t < gp.t_end;) {       // one copy per run of tracks that are contiguous in the caller's buffer
+            int t2 = t + 1;
+            int64_t run = in_frames[t];
+            while (t2 < gp.t_end && in_offsets[t2] == in_offsets[t2 - 1] + in_frames[t2 - 1]) { run += in_frames[t2]; ++t2; }
+            if (run > 0)
+                CK(cudaMemcpyAsync(d_in + pos * ch, pcm_in + in_offsets[t] * ch, (size_t)run * ch * 2, cudaMemcpyHostToDevice, X.in));
+            pos += run;
+            t = t2;
         }
         d_src = d_in;
     }
-    int16_t *d_dst = out_dev ? pcm_out + out_base * ch : d_out;
+    if (X.h2d_done) { CK(cudaEventRecord(X.h2d_done, X.in)); CK(cudaStreamWaitEvent(X.comp, X.h2d_done, 0)); }
+    int16_t *d_dst = out_dev ? pcm_out + gp.out_base * ch : d_out;
 
-    // ---- kernels -------------------------------------------------------------------
+    // ---- kernels (all on the handle's stream) ------------------------------------------------
     if (ch == 2) LAUNCH("k_chain", k_chain<2><<<g.n_csegs, NSEG * 2, chain_smem_bytes<2>(), h->stream>>>(d_src, d_streams, d_csegs, h->d_plans, d_proc, bp));
     else         LAUNCH("k_chain", k_chain<1><<<g.n_csegs, NSEG * 1, chain_smem_bytes<1>(), h->stream>>>(d_src, d_streams, d_csegs, h->d_plans, d_proc, bp));
     CK(cudaGetLastError());
+    int rc;
     if (g.any_multiband) { rc = launch_compressor(h, g, bp, 3, 0, d_proc, d_spec); if (rc) return rc; }
     rc = launch_loudness(h, g, d_proc, nullptr, d_kw, d_z, d_zsel, d_loud);
     if (rc) return rc;
@@ -876,21 +989,23 @@ static int run_group(b200m_handle *h, const int16_t *pcm_in, bool in_dev, int t_
     if (ch == 2) LAUNCH("k_final", k_final<2><<<gf, 256, 0, h->stream>>>(d_proc, d_tracks, h->d_plans, d_loud, d_dst));
     else         LAUNCH("k_final", k_final<1><<<gf, 256, 0, h->stream>>>(d_proc, d_tracks, h->d_plans, d_loud, d_dst));
     CK(cudaGetLastError());
+    if (X.comp_done) { CK(cudaEventRecord(X.comp_done, X.comp)); CK(cudaStreamWaitEvent(X.out, X.comp_done, 0)); }
 
-    // ---- results -------------------------------------------------------------------
-    if (!out_dev) CK(cudaMemcpyAsync(pcm_out + out_base * ch, d_out, (size_t)F * ch * 2, cudaMemcpyDeviceToHost, h->stream));
-    if (loudness_out || gain_out) {
-        double2 *hl = reinterpret_cast<double2 *>(h->pin + res_off);
-        CK(cudaMemcpyAsync(hl, d_loud, (size_t)g.n_tracks * 16, cudaMemcpyDeviceToHost, h->stream));
-        CK(cudaStreamSynchronize(h->stream));
-        for (int t = t_begin; t < t_end; ++t) {
-            if (loudness_out) loudness_out[t] = hl[t - t_begin].x;
-            if (gain_out) gain_out[t] = hl[t - t_begin].y;
-        }
-    } else if (!out_dev) {
-        CK(cudaStreamSynchronize(h->stream));
-    }
+    // ---- output stream: PCM and {loudness, gain} -> host --------------------------------------
+    if (!out_dev) CK(cudaMemcpyAsync(pcm_out + gp.out_base * ch, d_out, (size_t)F * ch * 2, cudaMemcpyDeviceToHost, X.out));
+    CK(cudaMemcpyAsync(pin + gp.res_off, d_loud, (size_t)g.n_tracks * 16, cudaMemcpyDeviceToHost, X.out));
+    if (X.d2h_done) CK(cudaEventRecord(X.d2h_done, X.out));
     return B200M_OK;
+}
+
+static cudaEvent_t sync_event(b200m_handle *h, size_t i)
+{
+    while (h->sync_events.size() <= i) {
+        cudaEvent_t e = nullptr;
+        cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+        h->sync_events.push_back(e);
+    }
+    return h->sync_events[i];
 }
 
 extern "C" int b200m_master_batch(b200m_handle *h, const void *pcm_in, int in_on_device, int fmt, int n_tracks,
@@ -907,6 +1022,7 @@ extern "C" int b200m_master_batch(b200m_handle *h, const void *pcm_in, int in_on
     for (int i = 0; i < n_plans; ++i)
         if (plans[i].channels != ch || plans[i].sample_rate != rate || rate <= 0)
             return fail(h, B200M_ERR_INVALID, "all plans of a batch must share sample rate and channel count");
+    int64_t total_frames = 0;
     for (int t = 0; t < n_tracks; ++t) {
         if (plan_index[t] < 0 || plan_index[t] >= n_plans) return fail(h, B200M_ERR_INVALID, "plan_index[%d] out of range", t);
         if (in_frames[t] < 0 || out_frames[t] < 0 || in_offsets[t] < 0) return fail(h, B200M_ERR_INVALID, "negative frame count for track %d", t);
@@ -914,27 +1030,96 @@ extern "C" int b200m_master_batch(b200m_handle *h, const void *pcm_in, int in_on
         // pyloudnorm valid_audio: data.shape[0] < block_size * rate -> ValueError
         if (plans[plan_index[t]].has_lufs && (double)out_frames[t] < 0.4 * rate)
             return fail(h, B200M_ERR_TOO_SHORT, "track %d: audio must have length greater than the block size (400 ms)", t);
+        total_frames += std::max(out_frames[t], in_frames[t]);
     }
     int rc = ensure_plans(h, plans, n_plans);
     if (rc) return rc;
-    // split into groups that fit the workspace limit
+    const bool in_dev = in_on_device != 0, out_dev = out_on_device != 0;
+    const bool pipelined = h->pipeline && (!in_dev || !out_dev) && n_tracks > 1;
+    const int slots = pipelined ? 2 : 1;
+
+    // ---- cut the batch into groups ---------------------------------------------------------
+    // a group must fit one workspace slot; with host buffers it is also at most ~1/8 of the batch
+    // (and at least ~8 M frames) so that copies and kernels of neighbouring groups overlap
     const double per_frame = ch * 2 * 3 + 4 + 3 * (ch * 2 + 8 + 8) + 1;
-    int t0 = 0;
-    int64_t out_base = 0;
-    while (t0 < n_tracks) {
-        int t1 = t0;
-        double bytes = 0;
-        int64_t frames = 0;
-        while (t1 < n_tracks) {
-            const double add = per_frame * (double)std::max(out_frames[t1], in_frames[t1]);
-            if (t1 > t0 && bytes + add > (double)h->ws_limit) break;
-            bytes += add; frames += out_frames[t1]; ++t1;
+    const double slot_limit = (double)h->ws_limit / slots;
+    const double pipe_frames = pipelined ? std::max<double>(8e6, (double)total_frames / 8.0) : 1e300;
+    std::vector<GroupPlan> gps;
+    {
+        int t0 = 0;
+        int64_t out_base = 0;
+        while (t0 < n_tracks) {
+            int t1 = t0;
+            double bytes = 0, fr = 0;
+            int64_t frames = 0;
+            while (t1 < n_tracks) {
+                const double f = (double)std::max(out_frames[t1], in_frames[t1]);
+                if (t1 > t0 && (bytes + per_frame * f > slot_limit || fr + 0.5 * f > pipe_frames)) break;
+                bytes += per_frame * f; fr += f; frames += out_frames[t1]; ++t1;
+            }
+            gps.emplace_back();
+            plan_group(h, gps.back(), in_dev, out_dev, t0, t1, in_offsets, in_frames, out_frames, plans, plan_index, out_base);
+            out_base += frames;
+            t0 = t1;
         }
-        rc = run_group(h, (const int16_t *)pcm_in, in_on_device != 0, t0, t1, in_offsets, in_frames, out_frames,
-                       plans, plan_index, (int16_t *)pcm_out, out_on_device != 0, out_base, loudness_out, gain_out);
-        if (rc) return rc;
-        out_base += frames;
-        t0 = t1;
+    }
+    size_t max_need = 0, pin_total = 0;
+    for (auto &gp : gps) { max_need = std::max(max_need, gp.need); pin_total += gp.pin_bytes; }
+    rc = ws_reserve(h, max_need * slots);
+    if (rc) return rc;
+    rc = pin_reserve(h, pin_total);
+    if (rc) return rc;
+    CK(cudaStreamSynchronize(h->stream));       // pinned staging of an earlier call may still be in flight
+    if (pipelined && !h->s_in) {
+        CK(cudaStreamCreateWithFlags(&h->s_in, cudaStreamNonBlocking));
+        CK(cudaStreamCreateWithFlags(&h->s_out, cudaStreamNonBlocking));
+    }
+    cudaEvent_t start_ev = nullptr;
+    if (pipelined) {                            // the side streams start after whatever the caller queued on the handle's stream
+        start_ev = sync_event(h, 0);
+        CK(cudaEventRecord(start_ev, h->stream));
+        CK(cudaStreamWaitEvent(h->s_in, start_ev, 0));
+        CK(cudaStreamWaitEvent(h->s_out, start_ev, 0));
+    }
+    size_t pin_off = 0;
+    std::vector<size_t> pin_offs(gps.size());
+    for (size_t i = 0; i < gps.size(); ++i) {
+        GroupPlan &gp = gps[i];
+        pin_offs[i] = pin_off;
+        ExecStreams X;
+        if (pipelined) {
+            X.in = h->s_in; X.comp = h->stream; X.out = h->s_out;
+            X.h2d_done = sync_event(h, 1 + 3 * i); X.comp_done = sync_event(h, 2 + 3 * i); X.d2h_done = sync_event(h, 3 + 3 * i);
+            X.slot_free = i >= 2 ? sync_event(h, 3 + 3 * (i - 2)) : nullptr;      // D2H of the slot's previous group
+        } else {
+            X.in = X.comp = X.out = h->stream;
+            X.slot_free = X.h2d_done = X.comp_done = X.d2h_done = nullptr;
+        }
+        rc = exec_group(h, gp, h->ws + (i % slots) * max_need, h->pin + pin_off, X, (const int16_t *)pcm_in, in_dev, in_offsets,
+                        in_frames, (int16_t *)pcm_out, out_dev);
+        if (rc) break;
+        pin_off += gp.pin_bytes;
+    }
+    if (pipelined) {                            // the handle's stream observes the completion of everything
+        cudaEvent_t done = sync_event(h, 1 + 3 * gps.size());
+        cudaEventRecord(done, h->s_out);
+        cudaStreamWaitEvent(h->stream, done, 0);
+        cudaEvent_t done_in = sync_event(h, 2 + 3 * gps.size());
+        cudaEventRecord(done_in, h->s_in);
+        cudaStreamWaitEvent(h->stream, done_in, 0);
+    }
+    if (rc) { cudaStreamSynchronize(h->stream); return rc; }
+    if (loudness_out || gain_out || !out_dev) {
+        CK(cudaStreamSynchronize(h->stream));
+        for (size_t i = 0; i < gps.size(); ++i) {
+            const GroupPlan &gp = gps[i];
+            const double2 *hl = reinterpret_cast<const double2 *>(h->pin + pin_offs[i] + gp.res_off);
+            for (int t = gp.t_begin; t < gp.t_end; ++t) {
+                const bool has = gp.F > 0;
+                if (loudness_out) loudness_out[t] = has ? hl[t - gp.t_begin].x : NAN;
+                if (gain_out) gain_out[t] = has ? hl[t - gp.t_begin].y : 1.0;
+            }
+        }
     }
     return B200M_OK;
 }

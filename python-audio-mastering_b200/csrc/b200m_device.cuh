@@ -54,6 +54,7 @@ struct PlanDev {
     double width, lufs;
     BandDev band[3];
     const double *curve[3];       // device pointers, CURVE_N doubles each (NULL if !multiband)
+    const int32_t *ptree;         // numpy pairwise-sum tree of a full 400 ms block (k_blocks), or NULL
     SecTab eq[4], lp[2], hp[2], kw[2];
 };
 
@@ -145,12 +146,14 @@ __device__ __forceinline__ void section_round(double (&x)[SEG], const SecTab *__
 }
 
 // ENG:123-126: clip to [-1,1], * 2^15, astype(int16) = truncate toward zero, and the
-// +1.0 -> 32768 -> -32768 wrap.  NaN casts to 0 (x86 cvttsd2si + 16-bit truncation).
+// +1.0 -> 32768 -> -32768 wrap.  y * 2^15 is exact and F2I.F64.TRUNC truncates and saturates, so
+// the clip is done on the integer (ALU pipe, not the fp64 pipe).  NaN must cast to 0 (x86
+// cvttsd2si gives 0x80000000, whose low 16 bits are 0); F2I.F64 has no NaN-to-zero mode, so NaN is
+// detected on the bit pattern.
 __device__ __forceinline__ int quant16(double y)
 {
-    if (y != y) return 0;
-    double v = fmin(fmax(y, -1.0), 1.0);
-    int iv = (int)(v * 32768.0);
+    int iv = max(-32768, min(32768, __double2int_rz(y * 32768.0)));
+    if (((unsigned long long)__double_as_longlong(y) << 1) > 0xffe0000000000000ull) iv = 0;
     return (int)(short)iv;
 }
 

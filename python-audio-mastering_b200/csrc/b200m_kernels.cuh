@@ -22,19 +22,64 @@ struct BandPtrs {
 // tile; every biquad is a section_round (blocked parallel prefix).  Filter state is
 // carried tile to tile in shared memory and starts at zero (chunk-boundary semantics).
 // =====================================================================================
+// Quantised samples are staged planar in shared memory, 16 per thread packed into two 128-bit
+// stores; one pad of 8 int16 per 16-sample segment keeps them 16-byte aligned and conflict free.
+constexpr int QSEG = 24;                 // int16 slots per segment (16 used)
+constexpr int QW = QSEG / 2;             // the same in 32-bit words
+
+__device__ __forceinline__ void stage_q16(unsigned *dst32, const int (&q)[SEG])
+{
+    uint4 a, b;
+    a.x = (unsigned)(q[0] & 0xffff) | ((unsigned)q[1] << 16);   a.y = (unsigned)(q[2] & 0xffff) | ((unsigned)q[3] << 16);
+    a.z = (unsigned)(q[4] & 0xffff) | ((unsigned)q[5] << 16);   a.w = (unsigned)(q[6] & 0xffff) | ((unsigned)q[7] << 16);
+    b.x = (unsigned)(q[8] & 0xffff) | ((unsigned)q[9] << 16);   b.y = (unsigned)(q[10] & 0xffff) | ((unsigned)q[11] << 16);
+    b.z = (unsigned)(q[12] & 0xffff) | ((unsigned)q[13] << 16); b.w = (unsigned)(q[14] & 0xffff) | ((unsigned)q[15] << 16);
+    reinterpret_cast<uint4 *>(dst32)[0] = a;
+    reinterpret_cast<uint4 *>(dst32)[1] = b;
+}
+
+// planar staged tile -> interleaved int16 in global memory, two frames per thread and step
+template <int CH>
+__device__ __forceinline__ void store_q16_tile(int16_t *__restrict__ dst, const unsigned *src32, int nvalid, int tid)
+{
+    constexpr int NT = NSEG * CH;
+    if (CH == 2) {
+        const bool al8 = (reinterpret_cast<unsigned long long>(dst) & 7ull) == 0;
+        for (int p = tid; 2 * p < nvalid; p += NT) {
+            const int w = (p >> 3) * QW + (p & 7);
+            const unsigned L = src32[w], R = src32[NSEG * QW + w];
+            const unsigned o0 = __byte_perm(L, R, 0x5410), o1 = __byte_perm(L, R, 0x7632);
+            unsigned *g = reinterpret_cast<unsigned *>(dst) + 2 * p;
+            if (al8 && 2 * p + 1 < nvalid) *reinterpret_cast<uint2 *>(g) = make_uint2(o0, o1);
+            else { g[0] = o0; if (2 * p + 1 < nvalid) g[1] = o1; }
+        }
+    } else {
+        const bool al4 = (reinterpret_cast<unsigned long long>(dst) & 3ull) == 0;
+        for (int p = tid; 2 * p < nvalid; p += NT) {
+            const unsigned v = src32[(p >> 3) * QW + (p & 7)];
+            if (al4 && 2 * p + 1 < nvalid) reinterpret_cast<unsigned *>(dst)[p] = v;
+            else { dst[2 * p] = (int16_t)(v & 0xffff); if (2 * p + 1 < nvalid) dst[2 * p + 1] = (int16_t)(v >> 16); }
+        }
+    }
+}
+
 template <int CH>
 __global__ void __launch_bounds__(NSEG * CH, (CH == 2 ? 2 : 4))
 k_chain(const int16_t *__restrict__ pcm_in, const StreamDesc *__restrict__ streams, const SegDesc *__restrict__ segs,
         const PlanDev *__restrict__ plans, int16_t *__restrict__ proc, BandPtrs bp)
 {
     constexpr int NT = NSEG * CH;
+    constexpr int FPT = TILE / NT;                                       // frames staged per thread and tile
+    constexpr size_t SY_BYTES = (size_t)CH * TILE_PAD * 8 > (size_t)3 * CH * NSEG * QSEG * 2
+                                    ? (size_t)CH * TILE_PAD * 8 : (size_t)3 * CH * NSEG * QSEG * 2;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     SecTab *tabs = reinterpret_cast<SecTab *>(smem_raw);                 // eq[4] lp[2] hp[2]
-    double *sy = reinterpret_cast<double *>(smem_raw + 8 * sizeof(SecTab));  // [CH][TILE_PAD]
-    float *sx = reinterpret_cast<float *>(sy + CH * TILE_PAD);           // [CH][TILE_PAD]
+    double *sy = reinterpret_cast<double *>(smem_raw + 8 * sizeof(SecTab));  // [CH][TILE_PAD] (width exchange)
+    float *sx = reinterpret_cast<float *>(smem_raw + 8 * sizeof(SecTab) + SY_BYTES);   // [CH][TILE_PAD]
     double *carry = reinterpret_cast<double *>(sx + CH * TILE_PAD);      // [8][CH][2]
     double *wtot = carry + 8 * CH * 2;                                   // [2][CH][4][2]
-    int16_t *stg = reinterpret_cast<int16_t *>(sy);                      // aliases sy: [3][TILE_PAD][CH]
+    unsigned *stq = reinterpret_cast<unsigned *>(sy);                    // aliases sy: [3][CH][NSEG * QW]
+    int *sraw = reinterpret_cast<int *>(wtot + 2 * CH * 4 * 2);          // [TILE] raw frames of the next tile
 
     const SegDesc sg = segs[blockIdx.x];
     const StreamDesc sd = streams[sg.owner];
@@ -52,38 +97,62 @@ k_chain(const int16_t *__restrict__ pcm_in, const StreamDesc *__restrict__ strea
     const float s_clean = pl->sat_clean, s_mix = pl->sat_mix, s_drive = pl->sat_drive;
     const double width = pl->width;
     const float widthf = (float)width;
-    __syncthreads();
 
     const int16_t *__restrict__ in = pcm_in + sd.in_off * CH;
     float *myx = sx + c * TILE_PAD + j * (SEG + 1);
+    unsigned *myq = stq + (c * NSEG + j) * QW;
     unsigned round = 0;
 
+    // Raw PCM of the tile AFTER the one being filtered is brought in with cp.async (LDGSTS): no
+    // registers held, the copies are in flight during the filtering.  Every thread converts
+    // exactly the frames it fetched, so cp.async.wait_group is the only synchronisation needed.
+    // (Mono frames are 2 bytes, below cp.async's 4-byte minimum: plain loads.)
+    auto fetch = [&](int t0) {
+#pragma unroll
+        for (int k = 0; k < FPT; ++k) {
+            const int f = tid + k * NT, gf = t0 + f;
+            if (CH == 2) {
+                if (gf < sd.in_frames) {
+                    const unsigned sa = (unsigned)__cvta_generic_to_shared(sraw + f);
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(sa), "l"(reinterpret_cast<const int *>(in) + gf) : "memory");
+                } else {
+                    sraw[f] = 0;
+                }
+            } else {
+                sraw[f] = gf < sd.in_frames ? (int)__ldg(in + gf) : 0;
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+
     const int seg_begin = (int)sg.begin, seg_end = (int)sg.end;
-    for (int t0 = max(0, seg_begin - sg.warm); t0 < seg_end; t0 += TILE) {
+    const int t_first = max(0, seg_begin - sg.warm);
+    fetch(t_first);
+    __syncthreads();
+    for (int t0 = t_first; t0 < seg_end; t0 += TILE) {
         const bool store = t0 >= seg_begin;          // warm-up tiles only advance the filter states
         const int nvalid = store ? min(TILE, seg_end - t0) : 0;
-        // ---- stage: coalesced interleaved int16 -> planar float32 (+ exciter) ----------
-        for (int f = tid; f < TILE; f += NT) {
-            const int gf = t0 + f;
+        // ---- stage: interleaved int16 -> planar float32 (+ exciter), ENG:117-134 ---------
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+#pragma unroll
+        for (int k = 0; k < FPT; ++k) {
+            const int f = tid + k * NT;
+            const int rw = sraw[f];
             float v[CH];
+            if (CH == 2) {
+                v[0] = (float)(short)(rw & 0xffff) * (1.0f / 32768.0f);
+                v[CH - 1] = (float)(rw >> 16) * (1.0f / 32768.0f);
+            } else {
+                v[0] = (float)rw * (1.0f / 32768.0f);
+            }
+            if (sat_on) {
 #pragma unroll
-            for (int k = 0; k < CH; ++k) v[k] = 0.0f;
-            if (gf < sd.in_frames) {
-                if (CH == 2) {
-                    const short2 q = *reinterpret_cast<const short2 *>(in + (int64_t)gf * 2);
-                    v[0] = (float)q.x * (1.0f / 32768.0f);
-                    v[CH - 1] = (float)q.y * (1.0f / 32768.0f);
-                } else {
-                    v[0] = (float)in[gf] * (1.0f / 32768.0f);
-                }
-                if (sat_on) {
-#pragma unroll
-                    for (int k = 0; k < CH; ++k) v[k] = exciter(v[k], s_clean, s_mix, s_drive);
-                }
+                for (int q = 0; q < CH; ++q) v[q] = exciter(v[q], s_clean, s_mix, s_drive);
             }
 #pragma unroll
-            for (int k = 0; k < CH; ++k) sx[k * TILE_PAD + pidx(f)] = v[k];
+            for (int q = 0; q < CH; ++q) sx[q * TILE_PAD + pidx(f)] = v[q];
         }
+        if (t0 + TILE < seg_end) fetch(t0 + TILE);
         __syncthreads();
 
         double x[SEG];
@@ -108,42 +177,37 @@ k_chain(const int16_t *__restrict__ pcm_in, const StreamDesc *__restrict__ strea
             for (int n = 0; n < SEG; ++n) myy[n] = x[n];
             __syncthreads();
             const double *oy = sy + (1 - c) * TILE_PAD + j * (SEG + 1);
+            // L' = mid + side, R' = mid - side with side = (L - R) / 2 * w.  Seen from the R thread,
+            // (R - L) / 2 * w is exactly -side (IEEE sign symmetry), so both channels evaluate
+            // (me + other) / 2 + (me - other) / 2 * w with identical roundings to the reference.
             if (n_eq > 0) {     // float64 arithmetic (EQ output is float64)
 #pragma unroll
                 for (int n = 0; n < SEG; ++n) {
                     const double o = oy[n];
-                    const double l = c == 0 ? x[n] : o, r = c == 0 ? o : x[n];
-                    const double mid = __dmul_rn(__dadd_rn(l, r), 0.5);
-                    const double side = __dmul_rn(__dmul_rn(__dsub_rn(l, r), 0.5), width);
-                    x[n] = c == 0 ? __dadd_rn(mid, side) : __dsub_rn(mid, side);
+                    const double mid = __dmul_rn(__dadd_rn(x[n], o), 0.5);
+                    const double side = __dmul_rn(__dmul_rn(__dsub_rn(x[n], o), 0.5), width);
+                    x[n] = __dadd_rn(mid, side);
                 }
             } else {            // EQ fully bypassed: the reference stays in float32
 #pragma unroll
                 for (int n = 0; n < SEG; ++n) {
                     const float o = (float)oy[n], me = (float)x[n];
-                    const float l = c == 0 ? me : o, r = c == 0 ? o : me;
-                    const float mid = __fmul_rn(__fadd_rn(l, r), 0.5f);
-                    const float side = __fmul_rn(__fmul_rn(__fsub_rn(l, r), 0.5f), widthf);
-                    x[n] = (double)(c == 0 ? __fadd_rn(mid, side) : __fsub_rn(mid, side));
+                    const float mid = __fmul_rn(__fadd_rn(me, o), 0.5f);
+                    const float side = __fmul_rn(__fmul_rn(__fsub_rn(me, o), 0.5f), widthf);
+                    x[n] = (double)__fadd_rn(mid, side);
                 }
             }
             __syncthreads();    // sy is reused as the int16 staging area below
         }
 
-        const int pb = j * (SEG + 1);
+        int q[SEG];
         if (!multiband) {
             // ---- quantise #1 -> proc --------------------------------------------------
 #pragma unroll
-            for (int n = 0; n < SEG; ++n) stg[(pb + n) * CH + c] = (int16_t)quant16(x[n]);
+            for (int n = 0; n < SEG; ++n) q[n] = quant16(x[n]);
+            stage_q16(myq, q);
             __syncthreads();
-            int16_t *__restrict__ dst = proc + (sd.out_off + t0) * CH;
-            for (int f = tid; f < nvalid; f += NT) {
-                if (CH == 2)
-                    *reinterpret_cast<short2 *>(dst + (int64_t)f * 2) =
-                        *reinterpret_cast<const short2 *>(stg + pidx(f) * 2);
-                else
-                    dst[f] = stg[pidx(f)];
-            }
+            store_q16_tile<CH>(proc + (sd.out_off + t0) * CH, stq, nvalid, tid);
             __syncthreads();
         } else {
             // ---- quantise #1, re-float (ENG:199), crossover ------------------------------
@@ -157,35 +221,30 @@ k_chain(const int16_t *__restrict__ pcm_in, const StreamDesc *__restrict__ strea
                              wtot + (((round & 1) * CH + c) * 4) * 2, lane, wid, j == 0); ++round;
             section_round<4>(x, &tabs[5], carry + (5 * CH + c) * 2,
                              wtot + (((round & 1) * CH + c) * 4) * 2, lane, wid, j == 0); ++round;
-            double low[SEG];
+            // ---- low band staged now; mid = x - low - high (ENG:202) keeps x - low ---------
+            double rest[SEG];
 #pragma unroll
-            for (int n = 0; n < SEG; ++n) { low[n] = x[n]; x[n] = (double)myx[n]; }
+            for (int n = 0; n < SEG; ++n) {
+                const double u = (double)myx[n];
+                q[n] = quant16(x[n]);
+                rest[n] = __dsub_rn(u, x[n]);
+                x[n] = u;
+            }
+            stage_q16(myq + 0 * CH * NSEG * QW, q);
             section_round<4>(x, &tabs[6], carry + (6 * CH + c) * 2,
                              wtot + (((round & 1) * CH + c) * 4) * 2, lane, wid, j == 0); ++round;
             section_round<4>(x, &tabs[7], carry + (7 * CH + c) * 2,
                              wtot + (((round & 1) * CH + c) * 4) * 2, lane, wid, j == 0); ++round;
-            // ---- mid = x - low - high (ENG:202), quantise #2 per band --------------------
 #pragma unroll
-            for (int n = 0; n < SEG; ++n) {
-                const double u = (double)myx[n];
-                const double mid = __dsub_rn(__dsub_rn(u, low[n]), x[n]);
-                stg[(0 * TILE_PAD + pb + n) * CH + c] = (int16_t)quant16(low[n]);
-                stg[(1 * TILE_PAD + pb + n) * CH + c] = (int16_t)quant16(mid);
-                stg[(2 * TILE_PAD + pb + n) * CH + c] = (int16_t)quant16(x[n]);
-            }
+            for (int n = 0; n < SEG; ++n) q[n] = quant16(__dsub_rn(rest[n], x[n]));
+            stage_q16(myq + 1 * CH * NSEG * QW, q);
+#pragma unroll
+            for (int n = 0; n < SEG; ++n) q[n] = quant16(x[n]);
+            stage_q16(myq + 2 * CH * NSEG * QW, q);
             __syncthreads();
 #pragma unroll
-            for (int b = 0; b < 3; ++b) {
-                int16_t *__restrict__ dst = bp.band[b] + (sd.out_off + t0) * CH;
-                const int16_t *src = stg + b * TILE_PAD * CH;
-                for (int f = tid; f < nvalid; f += NT) {
-                    if (CH == 2)
-                        *reinterpret_cast<short2 *>(dst + (int64_t)f * 2) =
-                            *reinterpret_cast<const short2 *>(src + pidx(f) * 2);
-                    else
-                        dst[f] = src[pidx(f)];
-                }
-            }
+            for (int b = 0; b < 3; ++b)
+                store_q16_tile<CH>(bp.band[b] + (sd.out_off + t0) * CH, stq + b * CH * NSEG * QW, nvalid, tid);
             __syncthreads();
         }
     }
@@ -194,8 +253,9 @@ k_chain(const int16_t *__restrict__ pcm_in, const StreamDesc *__restrict__ strea
 template <int CH>
 constexpr size_t chain_smem_bytes()
 {
-    return 8 * sizeof(SecTab) + (size_t)CH * TILE_PAD * 8 + (size_t)CH * TILE_PAD * 4 +
-           8 * CH * 2 * 8 + 2 * CH * 4 * 2 * 8;
+    return 8 * sizeof(SecTab) +
+           ((size_t)CH * TILE_PAD * 8 > (size_t)3 * CH * NSEG * QSEG * 2 ? (size_t)CH * TILE_PAD * 8 : (size_t)3 * CH * NSEG * QSEG * 2) +
+           (size_t)CH * TILE_PAD * 4 + 8 * CH * 2 * 8 + 2 * CH * 4 * 2 * 8 + (size_t)TILE * 4;
 }
 
 // =====================================================================================
@@ -329,6 +389,8 @@ k_detect(const StreamDesc *__restrict__ streams, const PlanDev *__restrict__ pla
 // =====================================================================================
 constexpr int RW = 4;               // warps per CTA in k_recur_tiles
 
+constexpr size_t recur_smem_bytes() { return 2 * (size_t)RW * 32 * 33 * sizeof(double); }
+
 struct RecurParams {
     int tile_len, warm, tiles, nbands, band_base, n_streams, mode;
 };
@@ -385,7 +447,11 @@ k_recur_tiles(const StreamDesc *__restrict__ streams, const PlanDev *__restrict_
               const double *__restrict__ se_in, double *__restrict__ ss_out, double *__restrict__ se_out,
               unsigned long long *__restrict__ counters)
 {
-    __shared__ double s_m[RW][32][33];      // M rows in, attenuation rows out (same slots)
+    // M rows in, attenuation rows out (same slots); two buffers: the rows of the NEXT block are
+    // brought in with cp.async while the 32 dependent steps of the current block run.
+    extern __shared__ __align__(16) unsigned char recur_smem[];
+    typedef double RowBuf[RW][32][33];
+    RowBuf *s_m = reinterpret_cast<RowBuf *>(recur_smem);           // [2]
     __shared__ ulonglong2 s_in[RW][32], s_out[RW][32];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int gl = (blockIdx.x * RW + warp) * 32 + lane;
@@ -438,80 +504,97 @@ k_recur_tiles(const StreamDesc *__restrict__ streams, const PlanDev *__restrict_
     // Every lane walks its own cursor over 32-frame blocks [wstart, end): held blocks of the
     // warm-up are skipped outright (the state cannot change there), so the warp iterates
     // max-over-lanes of the blocks that need work, not the span.
-    int cb = wstart >> 5;
     const int sb = start >> 5, eb = (end + 31) >> 5;
-    double a_start = a;
-    bool merged = false;
-    for (;;) {
-        if (live && !merged) {
+    auto skip_held = [&](int cb) {               // first block >= cb that needs work (warm-up part only)
+        if (live) {
             while (cb < sb) {
                 const unsigned wv = hold[cb >> 5] >> (cb & 31);
                 if (!(wv & 1u)) break;
-                const int run = (~wv) ? __ffs(~wv) - 1 : 32;         // run of held blocks (shifted-in zeros end it)
+                const int run = (~wv) ? __ffs(~wv) - 1 : 32;     // run of held blocks (shifted-in zeros end it)
                 cb = min(cb + run, sb);
             }
         }
+        return cb;
+    };
+    // Row q of buffer `buf` <- lane q's 32 values of M for its block `cbn` (0 beyond its count and
+    // for held blocks: M = 0 is a hold, i.e. an identity step, so partial rows need no branches).
+    auto issue = [&](int buf, int cbn, bool valid) {
+        const bool on_n = valid && cbn < eb;
+        const int i0n = cbn << 5;
+        const int cntn = on_n ? min(32, end - i0n) : 0;
+        const bool heldn = on_n && ((hold[cbn >> 5] >> (cbn & 31)) & 1u);
+        s_in[warp][lane] = make_ulonglong2((unsigned long long)(m + i0n), (unsigned long long)(heldn ? 0 : cntn));
+        __syncwarp();
+#pragma unroll 8
+        for (int q = 0; q < 32; ++q) {
+            const ulonglong2 dsc = s_in[warp][q];
+            double *dstp = &s_m[buf][warp][q][lane];
+            if (lane < (int)dsc.y) {
+                const unsigned sa = (unsigned)__cvta_generic_to_shared(dstp);
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sa), "l"(reinterpret_cast<const double *>(dsc.x) + lane) : "memory");
+            } else {
+                *dstp = 0.0;
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        __syncwarp();
+    };
+    int cb = skip_held(wstart >> 5);
+    issue(0, cb, live);
+    int buf = 0;
+    double a_start = a;
+    bool merged = false;
+    for (;;) {
         const bool on = live && !merged && cb < eb;
         if (!__any_sync(FULL, on)) break;
         const int i0 = cb << 5;
         const int cnt = on ? min(32, end - i0) : 0;
         const bool is_main = on && cb >= sb;
-        const bool held = on && ((hold[cb >> 5] >> (cb & 31)) & 1u);   // nothing can change in this block
         if (on && cb == sb) a_start = a;
         // the value this tile stored earlier at the end of this block (repair rounds only)
         double old_last = 0.0;
         if (P.mode == 1 && on) old_last = out[i0 + cnt - 1];
-        // ---- row descriptors through smem: {pointer, count} of every lane's next block ----
-        s_in[warp][lane] = make_ulonglong2((unsigned long long)(m + i0), (unsigned long long)(held ? 0 : cnt));
-        s_out[warp][lane] = make_ulonglong2((unsigned long long)(out + i0), (unsigned long long)(is_main ? cnt : 0));
-        __syncwarp();
-        // ---- coalesced row loads: row q = lane q's next 32 values of M (0 beyond its count:
-        //      M = 0 is a hold, i.e. an identity step, so partial and held rows need no branches)
-#pragma unroll
-        for (int q0 = 0; q0 < 32; q0 += 8) {
-            double v[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const ulonglong2 dsc = s_in[warp][q0 + j];
-                v[j] = lane < (int)dsc.y ? __ldg(reinterpret_cast<const double *>(dsc.x) + lane) : 0.0;
-            }
-#pragma unroll
-            for (int j = 0; j < 8; ++j) s_m[warp][q0 + j][lane] = v[j];
-        }
+        // ---- rows of the next block start moving now -------------------------------------------
+        const int nb = on ? skip_held(cb + 1) : cb;
+        issue(buf ^ 1, nb, on);
+        asm volatile("cp.async.wait_group 1;" ::: "memory");
         __syncwarp();
         // ---- 32 dependent steps -------------------------------------------------------------
         if (all_exact) {            // warp-uniform: every band of this warp passed the plan-time division check
             if (on) {
 #pragma unroll 8
                 for (int k = 0; k < 32; ++k) {
-                    const double M = s_m[warp][lane][k];
+                    const double M = s_m[buf][warp][lane][k];
                     const double inc = div_const(M, A, rA, true), dec = div_const(M, R, rR, true);
                     a = recur_step(a, M, inc, dec);
-                    s_m[warp][lane][k] = a;
+                    s_m[buf][warp][lane][k] = a;
                 }
             }
         } else if (on) {
 #pragma unroll 1
             for (int k = 0; k < 32; ++k) {
-                const double M = s_m[warp][lane][k];
+                const double M = s_m[buf][warp][lane][k];
                 const double inc = div_const(M, A, rA, exact), dec = div_const(M, R, rR, exact);
                 a = recur_step(a, M, inc, dec);
-                s_m[warp][lane][k] = a;
+                s_m[buf][warp][lane][k] = a;
             }
         }
-        __syncwarp();
         // ---- coalesced row stores of the attenuation (main part of the tile only) ---------
+        s_out[warp][lane] = make_ulonglong2((unsigned long long)(out + i0), (unsigned long long)(is_main ? cnt : 0));
+        __syncwarp();
         if (__any_sync(FULL, is_main)) {
 #pragma unroll 8
             for (int q = 0; q < 32; ++q) {
                 const ulonglong2 dsc = s_out[warp][q];
-                if (lane < (int)dsc.y) reinterpret_cast<double *>(dsc.x)[lane] = s_m[warp][q][lane];
+                if (lane < (int)dsc.y) reinterpret_cast<double *>(dsc.x)[lane] = s_m[buf][warp][q][lane];
             }
         }
         if (P.mode == 1 && on && __double_as_longlong(a) == __double_as_longlong(old_last)) merged = true;
-        if (on) ++cb;
+        cb = nb;
+        buf ^= 1;
         __syncwarp();
     }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
     if (live) {
         const size_t slot = (size_t)chain * P.tiles + tile;
         if (P.mode == 0) {
@@ -758,15 +841,23 @@ __device__ T np_pairwise_sum(Get get, int64_t n)
 // k_blocks: 400 ms / 75 %-overlap block mean squares z_j (pyloudnorm meter.py):
 //   l = int(T_g*(j*step)*rate), u = int(T_g*(j*step+1)*rate)
 //   z_j = float32(1/(T_g*rate)) * np.sum(np.square(y[l:u]))        (float32 throughout)
-// One thread per block; np.sum's pairwise order is reproduced exactly.
+// np.sum's pairwise order is reproduced exactly AND in parallel: the recursion tree of numpy's
+// pairwise_sum depends only on the block length n, so the host tabulates it once per sample
+// rate (PlanDev::ptree: leaves of <= 128 elements in order, internal nodes by level).  One CTA
+// per block: 8 lanes per leaf play numpy's 8 partial accumulators r[0..7] (a 3-step xor
+// butterfly is exactly ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7))), then the internal nodes are added
+// level by level.  Blocks of any other length (clamped last block) take the serial walk.
 // =====================================================================================
-__global__ void __launch_bounds__(128)
+constexpr int BNT = 256;
+
+__global__ void __launch_bounds__(BNT)
 k_blocks(const float *__restrict__ kw, const TrackDesc *__restrict__ tracks,
          const PlanDev *__restrict__ plans, double *__restrict__ z)
 {
+    extern __shared__ float bval[];              // [nleaves + ninternal]
     const TrackDesc td = tracks[blockIdx.y];
     const PlanDev *__restrict__ pl = plans + td.plan;
-    const int j = blockIdx.x * 128 + threadIdx.x;
+    const int j = blockIdx.x, tid = threadIdx.x;
     if (!pl->has_lufs || j >= td.nblocks) return;
     const double rate = (double)pl->rate, Tg = 0.4, step = 0.25;
     int64_t l = (int64_t)__dmul_rn(__dmul_rn(Tg, __dmul_rn((double)j, step)), rate);
@@ -774,11 +865,46 @@ k_blocks(const float *__restrict__ kw, const TrackDesc *__restrict__ tracks,
     if (u > td.frames) u = td.frames;       // numpy slicing clamps
     if (l > u) l = u;
     const float *__restrict__ y = kw + td.off + l;
-    auto get = [y](int64_t i) { const float v = y[i]; return __fmul_rn(v, v); };
-    auto getF = [get](int64_t i) { return F32(get(i)); };
-    const float sum = np_pairwise_sum<F32>(getF, u - l).v;
     const float scale = (float)(1.0 / (Tg * rate));
-    z[td.zoff + j] = (double)__fmul_rn(scale, sum);
+    const int64_t n = u - l;
+    const int32_t *__restrict__ T = pl->ptree;
+    if (T == nullptr || (int64_t)T[0] != n) {
+        if (tid == 0) {
+            auto get = [y](int64_t i) { const float v = y[i]; return F32(__fmul_rn(v, v)); };
+            z[td.zoff + j] = (double)__fmul_rn(scale, np_pairwise_sum<F32>(get, n).v);
+        }
+        return;
+    }
+    const int nleaves = T[1], nint = T[2], nlev = T[3];
+    const int32_t *lvl = T + 4, *loff = lvl + nlev + 1, *ln = loff + nleaves, *nl = ln + nleaves, *nr = nl + nint;
+    const int sub = tid >> 3, k = tid & 7;
+    for (int L0 = 0; L0 < nleaves; L0 += BNT / 8) {
+        const int L = L0 + sub;
+        const bool on = L < nleaves;
+        const int cnt = on ? ln[L] : 8;
+        const float *p = y + (on ? loff[L] : 0);
+        const int lim = cnt - (cnt % 8);
+        float v0 = p[k];
+        float acc = __fmul_rn(v0, v0);
+#pragma unroll 4
+        for (int i = 8; i < lim; i += 8) {
+            const float v = p[i + k];
+            acc = __fadd_rn(acc, __fmul_rn(v, v));
+        }
+        acc = __fadd_rn(acc, __shfl_xor_sync(FULL, acc, 1));
+        acc = __fadd_rn(acc, __shfl_xor_sync(FULL, acc, 2));
+        acc = __fadd_rn(acc, __shfl_xor_sync(FULL, acc, 4));
+        if (on && k == 0) {
+            for (int i = lim; i < cnt; ++i) { const float v = p[i]; acc = __fadd_rn(acc, __fmul_rn(v, v)); }
+            bval[L] = acc;
+        }
+    }
+    __syncthreads();
+    for (int lv = 0; lv < nlev; ++lv) {
+        for (int i = lvl[lv] + tid; i < lvl[lv + 1]; i += BNT) bval[nleaves + i] = __fadd_rn(bval[nl[i]], bval[nr[i]]);
+        __syncthreads();
+    }
+    if (tid == 0) z[td.zoff + j] = (double)__fmul_rn(scale, nint ? bval[nleaves + nint - 1] : bval[0]);
 }
 
 // =====================================================================================

@@ -265,3 +265,22 @@ def test_time_segmentation_is_invisible(eng):
             assert info[0]["loudness"] == binfo[0]["loudness"]
     finally:
         eng.set_segment_tiles(0, 0)
+
+
+def test_host_pipeline_is_invisible(eng):
+    """Host-buffer batches are cut into groups whose copies overlap the kernels of their neighbours
+    (two workspace slots, three streams): same bytes as the sequential path, in the right places."""
+    from b200master import synth
+    rate = 48000
+    tracks = [synth.make_track(80 + i, 181.0 + 7.3 * (i % 3), rate) for i in range(5)]      # ~43 M frames: several groups
+    sts = [dict(bass_boost=4.0, mid_cut=3.0, treble_boost=3.0, width=1.2, multiband=(i % 2 == 0), lufs=-14.0 - i) for i in range(5)]
+    try:
+        eng.set_pipeline(False)
+        base, binfo = eng.master(tracks, rate, sts)
+        eng.set_pipeline(True)
+        out, info = eng.master(tracks, rate, sts)
+    finally:
+        eng.set_pipeline(True)
+    for a, b, ia, ib in zip(base, out, binfo, info):
+        assert np.array_equal(a, b)
+        assert ia["loudness"] == ib["loudness"] and ia["gain"] == ib["gain"]
