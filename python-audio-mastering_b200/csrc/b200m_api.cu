@@ -532,8 +532,17 @@ static int ensure_plans(b200m_handle *h, const b200m_plan *plans, int n)
                 int rc = get_curve(h, bb, &d.curve[b], &tab);
                 if (rc) return rc;
                 const bool trick = div_trick_exact(tab, bb.attack_frames) && div_trick_exact(tab, bb.release_frames);
+                // curve[r] == 0 for r <= hold_max and != 0 above it (the curve is monotone); if that
+                // does not hold for some odd parameter set, nothing is ever flagged "held"
+                int hold_max = -1;
+                {
+                    int r = 0;
+                    while (r < CURVE_N && tab[r] == 0.0) ++r;
+                    hold_max = r - 1;
+                    for (; r < CURVE_N; ++r) if (tab[r] == 0.0) { hold_max = -1; break; }
+                }
                 d.band[b] = {bb.thresh_rms, bb.attack_frames, bb.release_frames, bb.slope,
-                             1.0 / bb.attack_frames, 1.0 / bb.release_frames, bb.look_frames, trick ? 1 : 0};
+                             1.0 / bb.attack_frames, 1.0 / bb.release_frames, bb.look_frames, trick ? 1 : 0, hold_max, 0};
                 if (rc) return rc;
             }
         }
@@ -746,10 +755,13 @@ static RecurParams recur_params(const b200m_handle *h, const Group &g, int nband
     if (h->recur_tile > 0) {
         P.tile_len = std::max(32, (h->recur_tile + 31) & ~31);
     } else {
-        // enough (chain, tile) lanes to fill every SM with warps; tiles no shorter than 8192 frames
-        const int want = (148 * 1024 + chains - 1) / chains;
-        const int tiles = std::max(1, std::min(want, g.max_stream_frames / 8192));
-        P.tile_len = ((g.max_stream_frames + tiles - 1) / tiles + 31) & ~31;
+        // about half a resident wave of (chain, tile) lanes (148 SMs x 8 warps x 32); tiles of 2048 ..
+        // 65536 frames: every lane also runs the warm-up (`warm` active frames), so long tiles waste
+        // less work (measured: 32768-frame tiles beat 16384 by 1.28x on a 64-track batch) and short
+        // tiles give a small batch enough lanes
+        const double want_tiles = 148.0 * 8 * 32 / chains;
+        const double len = std::min(65536.0, std::max(2048.0, g.max_stream_frames / want_tiles));
+        P.tile_len = ((int)len + 1023) & ~1023;
     }
     P.tiles = std::max(1, (g.max_stream_frames + P.tile_len - 1) / P.tile_len);
     return P;
@@ -758,7 +770,22 @@ static RecurParams recur_params(const b200m_handle *h, const Group &g, int nband
 static size_t recur_spec_doubles(const b200m_handle *h, const Group &g, int nbands)
 {
     const RecurParams P = recur_params(h, g, nbands, 0);
-    return 5 * (size_t)g.n_streams * nbands * P.tiles;       // ss / se ping-pong + per-tile activity counts
+    return 4 * (size_t)g.n_streams * nbands * P.tiles;       // ss / se ping-pong
+}
+
+static size_t compressor_ws_bytes(const b200m_handle *h, const Group &g, int64_t F, int nbands)
+{
+    const size_t per_band = (size_t)F * 2 /*rms*/ + (size_t)F * 8 /*att*/ + (size_t)g.total_blocks * 4 /*hold*/ + 4 * 256;
+    return nbands * per_band + recur_spec_doubles(h, g, nbands) * 8 + 256;
+}
+
+// rms / hold / att for `nbands` bands starting at band_base, and the speculation scratch
+static double *take_compressor_ws(b200m_handle *h, Arena &A, const Group &g, int64_t F, int nbands, int band_base, BandPtrs &bp)
+{
+    for (int b = band_base; b < band_base + nbands; ++b) bp.rms[b] = A.take<uint16_t>(F);
+    for (int b = band_base; b < band_base + nbands; ++b) bp.att[b] = A.take<double>(F);
+    for (int b = band_base; b < band_base + nbands; ++b) bp.hold[b] = A.take<uint32_t>(g.total_blocks + 1);
+    return A.take<double>(recur_spec_doubles(h, g, nbands));
 }
 
 static int launch_compressor(b200m_handle *h, const Group &g, const BandPtrs &bp, int nbands, int band_base, int16_t *d_proc, double *d_spec)
@@ -773,23 +800,19 @@ static int launch_compressor(b200m_handle *h, const Group &g, const BandPtrs &bp
     RecurParams P0 = P;
     P0.mode = 0;
     double *ss[2] = {d_spec, d_spec + 2 * lanes}, *se[2] = {d_spec + lanes, d_spec + 3 * lanes};
-    int *tcnt = reinterpret_cast<int *>(d_spec + 4 * lanes);
     const unsigned gr = (unsigned)((lanes + 32 * RW - 1) / (32 * RW));
-    LAUNCH("k_recur_count", k_recur_count<<<(unsigned)((lanes + 127) / 128), 128, 0, h->stream>>>(g.d_streams, h->d_plans, P0, bp, tcnt));
-    LAUNCH("k_recur_tiles", k_recur_tiles<<<gr, 32 * RW, recur_smem_bytes(), h->stream>>>(g.d_streams, h->d_plans, P0, bp, tcnt, nullptr, nullptr,
-                                                                        ss[0], se[0], h->d_counters));
+    const size_t rs = recur_smem_bytes();
+    LAUNCH("k_recur_tiles", k_recur_tiles<<<gr, 32 * RW, rs, h->stream>>>(g.d_streams, h->d_plans, P0, bp, nullptr, nullptr, ss[0], se[0], h->d_counters));
     int cur = 0;
     if (P.tiles > 1) {
         RecurParams P1 = P;
         P1.mode = 1;
         for (int round = 0; round < h->recur_rounds; ++round) {      // parallel repair rounds
-            LAUNCH("k_recur_repair", k_recur_tiles<<<gr, 32 * RW, recur_smem_bytes(), h->stream>>>(g.d_streams, h->d_plans, P1, bp, tcnt, ss[cur], se[cur],
-                                                                             ss[cur ^ 1], se[cur ^ 1], h->d_counters));
+            LAUNCH("k_recur_repair", k_recur_tiles<<<gr, 32 * RW, rs, h->stream>>>(g.d_streams, h->d_plans, P1, bp, ss[cur], se[cur], ss[cur ^ 1], se[cur ^ 1], h->d_counters));
             cur ^= 1;
         }
     }
-    LAUNCH("k_recur_fix", k_recur_fix<<<(chains + 31) / 32, 32, 0, h->stream>>>(
-                              g.d_streams, h->d_plans, P, bp, ss[cur], se[cur], h->d_counters));
+    LAUNCH("k_recur_fix", k_recur_fix<<<(chains + 31) / 32, 32, 0, h->stream>>>(g.d_streams, h->d_plans, P, bp, ss[cur], se[cur], h->d_counters));
     const dim3 ga((g.max_stream_frames + 255) / 256, g.n_streams);
     if (g.ch == 2) LAUNCH("k_apply", k_apply<2><<<ga, 256, 0, h->stream>>>(g.d_streams, h->d_plans, bp, nbands, band_base, d_proc));
     else           LAUNCH("k_apply", k_apply<1><<<ga, 256, 0, h->stream>>>(g.d_streams, h->d_plans, bp, nbands, band_base, d_proc));
@@ -836,7 +859,7 @@ struct GroupPlan {
     std::vector<StreamDesc> streams;
     std::vector<TrackDesc> tracks;
     std::vector<SegDesc> csegs, ksegs;
-    int64_t F = 0, in_total = 0, zoff = 0, out_base = 0;
+    int64_t F = 0, Fp = 0, in_total = 0, zoff = 0, out_base = 0;      // F: workspace frames (aligned track starts), Fp: packed output frames
     size_t desc_bytes = 0, res_off = 0, pin_bytes = 0, need = 0;
 };
 
@@ -851,11 +874,12 @@ static void plan_group(const b200m_handle *h, GroupPlan &gp, bool in_dev, bool o
     g.ch = ch;
     g.n_tracks = t_end - t_begin;
     gp.tracks.resize(g.n_tracks);
-    int64_t F = 0, in_total = 0, zoff = 0;
+    int64_t F = 0, Fp = 0, in_total = 0, zoff = 0;
     for (int t = t_begin; t < t_end; ++t) {
         const b200m_plan &p = plans[plan_index[t]];
         TrackDesc &td = gp.tracks[t - t_begin];
-        td.off = F; td.frames = out_frames[t]; td.plan = plan_index[t];
+        F = (F + 31) & ~(int64_t)31;            // workspace rows of the compressor are moved in aligned 4-byte pieces
+        td.off = F; td.dst_off = Fp; td.frames = out_frames[t]; td.plan = plan_index[t];
         td.nblocks = p.has_lufs ? num_blocks(out_frames[t], rate) : 0;
         td.zoff = zoff; zoff += td.nblocks;
         g.max_blocks = std::max(g.max_blocks, td.nblocks);
@@ -876,6 +900,7 @@ static void plan_group(const b200m_handle *h, GroupPlan &gp, bool in_dev, bool o
             gp.streams.push_back(sd);
         }
         F += out_frames[t];
+        Fp += out_frames[t];
         in_total += in_frames[t];
     }
     g.n_streams = (int)gp.streams.size();
@@ -892,7 +917,7 @@ static void plan_group(const b200m_handle *h, GroupPlan &gp, bool in_dev, bool o
                 make_segments(gp.ksegs, (int)i, gp.tracks[i].frames, KTILE, kweight_warm_frames(plans[gp.tracks[i].plan]), ks);
         g.n_csegs = (int)gp.csegs.size(); g.n_ksegs = (int)gp.ksegs.size();
     }
-    gp.F = F; gp.in_total = in_total; gp.zoff = zoff;
+    gp.F = F; gp.Fp = Fp; gp.in_total = in_total; gp.zoff = zoff;
     gp.desc_bytes = gp.streams.size() * sizeof(StreamDesc) + gp.tracks.size() * sizeof(TrackDesc) +
                     (gp.csegs.size() + gp.ksegs.size()) * sizeof(SegDesc);
     gp.res_off = (gp.desc_bytes + 63) & ~(size_t)63;       // double2 results: 16-byte aligned slot after the descriptors
@@ -900,8 +925,8 @@ static void plan_group(const b200m_handle *h, GroupPlan &gp, bool in_dev, bool o
     size_t need = 16384 + gp.desc_bytes + (size_t)g.n_tracks * 16 + (size_t)F * ch * 2 /*proc*/ + (size_t)F * 4 /*kw*/ +
                   (size_t)zoff * 16 + 24 * 256;
     if (!in_dev) need += (size_t)in_total * ch * 2;
-    if (!out_dev) need += (size_t)F * ch * 2;
-    if (g.any_multiband) need += (size_t)F * (3 * ch * 2 + 3 * 8 + 3 * 8) + 3 * 4 * (size_t)g.total_blocks + 20 * 256 + recur_spec_doubles(h, g, 3) * 8;
+    if (!out_dev) need += (size_t)Fp * ch * 2;
+    if (g.any_multiband) need += (size_t)F * 3 * ch * 2 + 3 * 256 + compressor_ws_bytes(h, g, F, 3);
     gp.need = (need + 1023) & ~(size_t)1023;
 }
 
@@ -930,16 +955,13 @@ static int exec_group(b200m_handle *h, GroupPlan &gp, char *ws, char *pin, const
     double *d_zsel = A.take<double>(gp.zoff + 1);
     int16_t *d_in = nullptr, *d_out = nullptr;
     if (!in_dev) d_in = A.take<int16_t>((size_t)gp.in_total * ch);
-    if (!out_dev) d_out = A.take<int16_t>((size_t)F * ch);
+    if (!out_dev) d_out = A.take<int16_t>((size_t)gp.Fp * ch);
     BandPtrs bp;
     double *d_spec = nullptr;
     std::memset(&bp, 0, sizeof bp);
     if (g.any_multiband) {
         for (int b = 0; b < 3; ++b) bp.band[b] = A.take<int16_t>((size_t)F * ch);
-        for (int b = 0; b < 3; ++b) bp.matt[b] = A.take<double>(F);
-        for (int b = 0; b < 3; ++b) bp.att[b] = A.take<double>(F);
-        for (int b = 0; b < 3; ++b) bp.hold[b] = A.take<uint32_t>(g.total_blocks + 1);
-        d_spec = A.take<double>(recur_spec_doubles(h, g, 3));
+        d_spec = take_compressor_ws(h, A, g, F, 3, 0, bp);
     }
     if (A.used > gp.need) return fail(h, B200M_ERR_NOMEM, "internal: workspace estimate too small (%zu > %zu)", A.used, gp.need);
 
@@ -992,7 +1014,7 @@ static int exec_group(b200m_handle *h, GroupPlan &gp, char *ws, char *pin, const
     if (X.comp_done) { CK(cudaEventRecord(X.comp_done, X.comp)); CK(cudaStreamWaitEvent(X.out, X.comp_done, 0)); }
 
     // ---- output stream: PCM and {loudness, gain} -> host --------------------------------------
-    if (!out_dev) CK(cudaMemcpyAsync(pcm_out + gp.out_base * ch, d_out, (size_t)F * ch * 2, cudaMemcpyDeviceToHost, X.out));
+    if (!out_dev) CK(cudaMemcpyAsync(pcm_out + gp.out_base * ch, d_out, (size_t)gp.Fp * ch * 2, cudaMemcpyDeviceToHost, X.out));
     CK(cudaMemcpyAsync(pin + gp.res_off, d_loud, (size_t)g.n_tracks * 16, cudaMemcpyDeviceToHost, X.out));
     if (X.d2h_done) CK(cudaEventRecord(X.d2h_done, X.out));
     return B200M_OK;
@@ -1041,7 +1063,7 @@ extern "C" int b200m_master_batch(b200m_handle *h, const void *pcm_in, int in_on
     // ---- cut the batch into groups ---------------------------------------------------------
     // a group must fit one workspace slot; with host buffers it is also at most ~1/8 of the batch
     // (and at least ~8 M frames) so that copies and kernels of neighbouring groups overlap
-    const double per_frame = ch * 2 * 3 + 4 + 3 * (ch * 2 + 8 + 8) + 1;
+    const double per_frame = ch * 2 * 3 + 4 + 3 * (ch * 2 + 2 + 8) + 2;
     const double slot_limit = (double)h->ws_limit / slots;
     const double pipe_frames = pipelined ? std::max<double>(8e6, (double)total_frames / 8.0) : 1e300;
     std::vector<GroupPlan> gps;
@@ -1241,9 +1263,8 @@ extern "C" int b200m_multiband(b200m_handle *h, const b200m_plan *plan, const in
     Group g;
     g.ch = ch; g.n_streams = 1; g.n_tracks = 1; g.max_stream_frames = (int)nframes;
     for (int b = 0; b < 3; ++b) g.max_look = std::max(g.max_look, p.band[b].look_frames);
-    const size_t nspec = recur_spec_doubles(h, g, 3);
     g.total_blocks = (nframes + 1023) / 1024;
-    rc = ws_reserve(h, 8192 + F * ch * 2 * 5 + F * (3 * 8 + 3 * 8) + 12 * (size_t)g.total_blocks + nspec * 8 + 20 * 256);
+    rc = ws_reserve(h, 16384 + F * ch * 2 * 5 + compressor_ws_bytes(h, g, (int64_t)F, 3));
     if (rc) return rc;
     Arena A(h->ws);
     StreamDesc *d_streams = A.take<StreamDesc>(1);
@@ -1253,10 +1274,7 @@ extern "C" int b200m_multiband(b200m_handle *h, const b200m_plan *plan, const in
     BandPtrs bp;
     std::memset(&bp, 0, sizeof bp);
     for (int b = 0; b < 3; ++b) bp.band[b] = A.take<int16_t>(F * ch);
-    for (int b = 0; b < 3; ++b) bp.matt[b] = A.take<double>(F);
-    for (int b = 0; b < 3; ++b) bp.att[b] = A.take<double>(F);
-    for (int b = 0; b < 3; ++b) bp.hold[b] = A.take<uint32_t>(g.total_blocks + 1);
-    double *d_spec = A.take<double>(nspec);
+    double *d_spec = take_compressor_ws(h, A, g, (int64_t)F, 3, 0, bp);
     StreamDesc sd = {0, 0, (int32_t)nframes, (int32_t)nframes, 0, 0, 0, 0};
     CK(cudaMemcpyAsync(d_streams, &sd, sizeof sd, cudaMemcpyHostToDevice, h->stream));
     CK(cudaMemcpyAsync(d_in, pcm, F * ch * 2, cudaMemcpyHostToDevice, h->stream));
@@ -1292,9 +1310,8 @@ extern "C" int b200m_compress_dynamic_range(b200m_handle *h, const int16_t *pcm,
     Group g;
     g.ch = channels; g.n_streams = 1; g.n_tracks = 1; g.max_stream_frames = (int)nframes;
     g.max_look = band->look_frames;
-    const size_t nspec = recur_spec_doubles(h, g, 1);
     g.total_blocks = (nframes + 1023) / 1024;
-    rc = ws_reserve(h, 8192 + F * channels * 2 * 2 + F * (2 + 8 + 8) + 4 * (size_t)g.total_blocks + nspec * 8 + 10 * 256);
+    rc = ws_reserve(h, 16384 + F * channels * 2 * 2 + compressor_ws_bytes(h, g, (int64_t)F, 1));
     if (rc) return rc;
     Arena A(h->ws);
     StreamDesc *d_streams = A.take<StreamDesc>(1);
@@ -1303,11 +1320,7 @@ extern "C" int b200m_compress_dynamic_range(b200m_handle *h, const int16_t *pcm,
     BandPtrs bp;
     std::memset(&bp, 0, sizeof bp);
     bp.band[0] = d_in;
-    bp.rms[0] = A.take<uint16_t>(F);
-    bp.matt[0] = A.take<double>(F);
-    bp.att[0] = A.take<double>(F);
-    bp.hold[0] = A.take<uint32_t>(g.total_blocks + 1);
-    double *d_spec = A.take<double>(nspec);
+    double *d_spec = take_compressor_ws(h, A, g, (int64_t)F, 1, 0, bp);
     StreamDesc sd = {0, 0, (int32_t)nframes, (int32_t)nframes, 0, 0, 0, 0};
     CK(cudaMemcpyAsync(d_streams, &sd, sizeof sd, cudaMemcpyHostToDevice, h->stream));
     CK(cudaMemcpyAsync(d_in, pcm, F * channels * 2, cudaMemcpyHostToDevice, h->stream));
@@ -1334,7 +1347,7 @@ static int loudness_core(b200m_handle *h, const b200m_biquad *kw, const float *x
     p.kw[0] = kw[0]; p.kw[1] = kw[1];
     int rc = ensure_plans(h, &p, 1);
     if (rc) return rc;
-    TrackDesc td = {0, n, 0, num_blocks(n, rate), 0};
+    TrackDesc td = {0, 0, n, 0, num_blocks(n, rate), 0};
     const size_t ns = (size_t)n * channels;
     rc = ws_reserve(h, 65536 + ns * 4 + (size_t)n * 8 + (scaled_out ? ns * 8 : 0) + (size_t)(td.nblocks + 2) * 16 + (size_t)(n / KTILE + 2) * sizeof(SegDesc));
     if (rc) return rc;

@@ -42,6 +42,8 @@ struct BandDev {
     double r_attack, r_release;   // correctly rounded 1/attack_frames, 1/release_frames
     int32_t look;                 // int(attack_frames)
     int32_t div_trick;            // 1: M/A and M/R via div_const are exact for this band's curve
+    int32_t hold_max;             // curve[r] == 0 exactly for r <= hold_max (-1: no such prefix; then nothing is ever "held")
+    int32_t pad_;
 };
 
 // Compressor static curve: max attenuation M for each of the 32769 possible integer RMS
@@ -81,7 +83,8 @@ struct SegDesc {
 };
 
 struct TrackDesc {
-    int64_t off;        // first frame in the flat workspace buffers
+    int64_t off;        // first frame in the flat workspace buffers (a multiple of 32 frames)
+    int64_t dst_off;    // first frame in the group's packed output (tracks back to back)
     int64_t frames;     // out frames
     int64_t zoff;       // first block in z
     int32_t nblocks;    // pyloudnorm numBlocks

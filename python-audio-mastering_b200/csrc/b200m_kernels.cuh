@@ -5,11 +5,10 @@
 namespace b200m {
 
 struct BandPtrs {
-    int16_t *band[3];
-    double *matt[3];     // per frame: max attenuation M = (1 - 1/ratio) * dB over threshold (0 => hold)
-    double *att[3];      // per frame: attenuation trajectory
-    uint32_t *hold[3];   // bit per 32-frame block of a stream: 1 = every M in the block is 0 (state held)
-    uint16_t *rms[3];    // optional (debug / helper entry point): integer window RMS
+    int16_t *band[3];    // in: quantised crossover bands (ENG:204-206), interleaved
+    uint16_t *rms[3];    // per frame: integer window RMS (audioop.rms) -- k_detect -> k_recur_*
+    uint32_t *hold[3];   // bit per 32-frame block of a stream: 1 = rms <= threshold in the whole block (state held)
+    double *att[3];      // per frame: attenuation trajectory (pydub's `attenuation`) -- k_recur_* -> k_apply
 };
 
 // =====================================================================================
@@ -336,28 +335,26 @@ k_detect(const StreamDesc *__restrict__ streams, const PlanDev *__restrict__ pla
         run += se[k];
     }
     __syncthreads();
-    // Static curve: M is a pure function of the integer RMS (32769 values, tabulated at plan
-    // time with the host libm so it rounds like CPython's math.log).  Consecutive frames have
-    // neighbouring RMS values, so a warp's gathers touch only a few cache lines.
-    double *__restrict__ dst = bp.matt[band] + sd.out_off;
-    uint16_t *__restrict__ dbg = bp.rms[band] ? bp.rms[band] + sd.out_off : nullptr;
-    const double *__restrict__ curve = pl->curve[band];
+    // The static curve is a pure function of the integer RMS (32769 values, tabulated at plan
+    // time); it is applied inside the recurrence kernel.  Here: the RMS itself (2 bytes per frame)
+    // and one flag per 32-frame block saying that rms <= threshold throughout (M == 0: state held).
+    uint16_t *__restrict__ dst = bp.rms[band] + sd.out_off;
+    const unsigned hold_max = (unsigned)pl->band[band].hold_max;   // curve[r] == 0  <=>  r <= hold_max
     const int nvalid = min(DT, sd.out_frames - t0);
     __shared__ unsigned sbits[DT / 1024];
     if (tid < DT / 1024) sbits[tid] = 0xffffffffu;                 // blocks past the end count as held
     __syncthreads();
     for (int i = tid; i < ((nvalid + 31) & ~31); i += DNT) {      // whole warps: 32 consecutive frames each
         const int f = t0 + i;
-        double M = 0.0;
+        bool act = false;
         if (i < nvalid) {
             const unsigned long long S = P[i + H] - P[i];
             const unsigned n = (unsigned)CH * (unsigned)min(f, H);
             const unsigned r = window_rms(S, n);
-            M = curve[r];
-            dst[f] = M;
-            if (dbg) dbg[f] = (uint16_t)r;
+            dst[f] = (uint16_t)r;                                  // r <= 32768 > 65535? no: fits (max 32768)
+            act = (int)r > (int)hold_max;
         }
-        const unsigned active = __ballot_sync(FULL, M != 0.0);
+        const unsigned active = __ballot_sync(FULL, act);
         if (lane == 0 && active != 0u) atomicAnd(&sbits[i >> 10], ~(1u << ((i >> 5) & 31)));
     }
     __syncthreads();
@@ -365,31 +362,45 @@ k_detect(const StreamDesc *__restrict__ streams, const PlanDev *__restrict__ pla
 }
 
 // =====================================================================================
-// k_recur_tiles / k_recur_fix: the attenuation recurrence of pydub compress_dynamic_range,
-// state reset to 0 at every chunk (ENG:207-209 run per chunk).  With M_i the per-frame
-// maximum attenuation from k_detect (M_i != 0  <=>  rms_i > threshold):
+// k_recur_count / k_recur_tiles / k_recur_fix: pydub compress_dynamic_range after the level
+// detector (ENG:207-209 run per chunk, state reset to 0 at every chunk): static curve,
+// attenuation recurrence and gain application, fused.  With M_i = curve[rms_i] the per-frame
+// maximum attenuation (M_i != 0  <=>  rms_i > threshold):
 //   if M_i != 0 and att <= M_i:  att = min(att + M_i/A, M_i)   else  att = max(att - M_i/R, 0)
-// Every decision is an integer compare on bit patterns (att >= +0 always), both candidate
-// sums are formed in parallel, and M/A, M/R are exact constant divisions (3 instructions,
-// off the dependent chain): about 24 cycles per dependent step on B200 (45 with fmin/fmax).
+//   frame_i *= 10^(-att/20) via audioop.mul (floor of the clamped product) when att != 0
+// Every decision of the recurrence is an integer compare on bit patterns (att >= +0 always), both
+// candidate sums are formed in parallel, and M/A, M/R are exact constant divisions (3
+// instructions, off the dependent chain).
 //
 // The recurrence is not a linear scan, but two trajectories coincide for ever
 // once they are equal, and clamps (att = M, att = 0) make them equal.  So each (stream, band)
 // chain is cut into time tiles, one lane per tile:
-//   mode 0  speculate: warm up over the preceding `warm` frames from att = 0 (no stores), then
-//           run the tile, recording the assumed start state and the reached end state;
+//   mode 0  speculate: warm up over the preceding `warm` ACTIVE frames from att = 0 (no stores),
+//           then run the tile, recording the assumed start state and the reached end state;
 //   mode 1  repair round (Jacobi): every tile whose assumed start differs from its predecessor's
-//           current end state is re-run from that state until it meets its stored trajectory;
+//           current end state is re-run from that state until it meets its stored trajectory
+//           (compared at the end of every 32-frame block, bp.bend);
 // and k_recur_fix finally walks each chain's tiles in order and repairs, sequentially, whatever
 // is still inconsistent -- so the result is exact for any input and any tile length, and the
 // sequential path only runs in the worst case.
 //
-// Memory: a warp's 32 lanes walk 32 different streams, so M rows are loaded and attenuation
-// rows stored through shared memory as coalesced 32-step (256-byte) rows.
+// Data movement per 32-frame block of a warp (32 lanes = 32 different tiles): the 64-byte RMS
+// rows of the 32 tiles are brought into shared memory with cp.async
+// one block ahead; phase B expands RMS -> M row-wise (coalesced table gathers); phase C runs the
+// 32 dependent steps, one lane per tile; phase D stores the attenuation as coalesced 256-byte
+// rows.  HBM traffic per frame and band: 2 B in (plus warm-up re-reads), 8 B out.  The gain itself
+// (an fp64 exp10 per frame) is applied by k_apply at full occupancy.
 // =====================================================================================
 constexpr int RW = 4;               // warps per CTA in k_recur_tiles
 
-constexpr size_t recur_smem_bytes() { return 2 * (size_t)RW * 32 * 33 * sizeof(double); }
+struct RecurWarpSmem {
+    double m[32][33];               // M rows in (phase B), attenuation rows out (phase C -> D)
+    uint16_t rms[32][32];           // RMS rows
+    unsigned long long base_rms[32], base_curve[32], base_att[32];
+    int2 blk[32];                   // per lane: {first frame of its current block, frames to store (0 = warm-up)}
+    int2 nxt[32];                   // per lane: {first frame of its next block, frames to load (0 = held / none)}
+};
+constexpr size_t recur_smem_bytes() { return RW * sizeof(RecurWarpSmem); }
 
 struct RecurParams {
     int tile_len, warm, tiles, nbands, band_base, n_streams, mode;
@@ -416,54 +427,34 @@ __device__ __forceinline__ double recur_step(double a, double M, double inc, dou
     return p ? vu : vd;
 }
 
-// number of 32-frame blocks with any activity (M != 0) in every (chain, tile): lets the
-// speculative pass size its warm-up in ACTIVE frames (a held state survives any silence)
-__global__ void __launch_bounds__(128)
-k_recur_count(const StreamDesc *__restrict__ streams, const PlanDev *__restrict__ plans, RecurParams P,
-              BandPtrs bp, int *__restrict__ tcnt)
+// audioop.mul: floor(fbound(sample * factor)) with fbound's clip to [-32768, 32767]
+__device__ __forceinline__ int mul_floor16(int v, double g)
 {
-    const int gl = blockIdx.x * 128 + threadIdx.x;
-    const int chain = gl / P.tiles, tile = gl % P.tiles;
-    if (chain >= P.n_streams * P.nbands) return;
-    const int s = chain / P.nbands, band = P.band_base + chain % P.nbands;
-    const StreamDesc sd = streams[s];
-    int n = 0;
-    const int b0 = (tile * P.tile_len) >> 5, b1 = min(((tile + 1) * P.tile_len) >> 5, (sd.out_frames + 31) >> 5);
-    if (plans[sd.plan].multiband) {
-        const uint32_t *__restrict__ hold = bp.hold[band] + sd.blk_off;
-        for (int b = b0; b < b1;) {
-            const int span = min(32 - (b & 31), b1 - b);
-            const unsigned w = (hold[b >> 5] >> (b & 31)) & (span == 32 ? 0xffffffffu : ((1u << span) - 1u));
-            n += span - __popc(w);
-            b += span;
-        }
-    }
-    tcnt[gl] = n;
+    double val = __dmul_rn((double)v, g);
+    if (val > 32767.0) val = 32767.0;
+    else if (val < -32767.0) val = -32768.0;
+    return (int)floor(val);
 }
 
 __global__ void __launch_bounds__(32 * RW)
 k_recur_tiles(const StreamDesc *__restrict__ streams, const PlanDev *__restrict__ plans, RecurParams P,
-              BandPtrs bp, const int *__restrict__ tcnt, const double *__restrict__ ss_in,
+              BandPtrs bp, const double *__restrict__ ss_in,
               const double *__restrict__ se_in, double *__restrict__ ss_out, double *__restrict__ se_out,
               unsigned long long *__restrict__ counters)
 {
-    // M rows in, attenuation rows out (same slots); two buffers: the rows of the NEXT block are
-    // brought in with cp.async while the 32 dependent steps of the current block run.
     extern __shared__ __align__(16) unsigned char recur_smem[];
-    typedef double RowBuf[RW][32][33];
-    RowBuf *s_m = reinterpret_cast<RowBuf *>(recur_smem);           // [2]
-    __shared__ ulonglong2 s_in[RW][32], s_out[RW][32];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    RecurWarpSmem &W = reinterpret_cast<RecurWarpSmem *>(recur_smem)[warp];
     const int gl = (blockIdx.x * RW + warp) * 32 + lane;
     const int chain = gl / P.tiles, tile = gl % P.tiles;
     bool live = chain < P.n_streams * P.nbands;
     int start = 0, end = 0, wstart = 0;
-    const double *m = nullptr;
     const uint32_t *hold = nullptr;
-    double *out = nullptr;
+    const double *attp = nullptr;
     double A = 1.0, R = 1.0, rA = 1.0, rR = 1.0;
     bool exact = true;
     double a = 0.0;
+    W.base_rms[lane] = 0; W.base_curve[lane] = 0; W.base_att[lane] = 0;
     if (live) {
         const int s = chain / P.nbands, band = P.band_base + chain % P.nbands;
         const StreamDesc sd = streams[s];
@@ -472,19 +463,27 @@ k_recur_tiles(const StreamDesc *__restrict__ streams, const PlanDev *__restrict_
         live = pl->multiband && start < sd.out_frames;
         if (live) {
             end = min(start + P.tile_len, sd.out_frames);
-            m = bp.matt[band] + sd.out_off;
-            out = bp.att[band] + sd.out_off;
             hold = bp.hold[band] + sd.blk_off;
+            attp = bp.att[band] + sd.out_off;
+            W.base_rms[lane] = (unsigned long long)(bp.rms[band] + sd.out_off);
+            W.base_curve[lane] = (unsigned long long)pl->curve[band];
+            W.base_att[lane] = (unsigned long long)attp;
             const BandDev &bd = pl->band[band];
             A = bd.attack_frames; R = bd.release_frames; rA = bd.r_attack; rR = bd.r_release;
             exact = bd.div_trick != 0;
             const size_t slot = (size_t)chain * P.tiles + tile;
             if (P.mode == 0) {
-                // warm up over the preceding tiles until `warm` ACTIVE frames have been seen
-                int ws = tile, acc = 0;
-                const int *tc = tcnt + (size_t)chain * P.tiles;
-                while (ws > 0 && acc < (P.warm >> 5)) { --ws; acc += tc[ws]; }
-                wstart = ws * P.tile_len;
+                // warm up over the preceding frames until `warm` ACTIVE frames have been seen: walk the
+                // hold words (32 blocks = 1024 frames each) backwards; a held stretch carries the
+                // state unchanged, so it neither helps nor costs anything
+                int need = P.warm >> 5, wb = start >> 5;
+                while (wb > 0 && need > 0) {
+                    const int w = (wb - 1) >> 5, lo = w << 5, nbits = wb - lo;
+                    const unsigned mask = nbits == 32 ? 0xffffffffu : ((1u << nbits) - 1u);
+                    need -= nbits - __popc(hold[w] & mask);
+                    wb = lo;
+                }
+                wstart = wb << 5;
             } else {
                 wstart = start;
                 const double mine = ss_in[slot], mine_end = se_in[slot];
@@ -516,32 +515,38 @@ k_recur_tiles(const StreamDesc *__restrict__ streams, const PlanDev *__restrict_
         }
         return cb;
     };
-    // Row q of buffer `buf` <- lane q's 32 values of M for its block `cbn` (0 beyond its count and
-    // for held blocks: M = 0 is a hold, i.e. an identity step, so partial rows need no branches).
-    auto issue = [&](int buf, int cbn, bool valid) {
+    // RMS rows of every lane's block `cbn` -> W.rms (zeros beyond its count and for held blocks:
+    // r = 0 gives M = 0, a hold, i.e. an identity step, so partial rows need no branches)
+    auto issue_rms = [&](int cbn, bool valid) {
         const bool on_n = valid && cbn < eb;
         const int i0n = cbn << 5;
         const int cntn = on_n ? min(32, end - i0n) : 0;
         const bool heldn = on_n && ((hold[cbn >> 5] >> (cbn & 31)) & 1u);
-        s_in[warp][lane] = make_ulonglong2((unsigned long long)(m + i0n), (unsigned long long)(heldn ? 0 : cntn));
+        W.nxt[lane] = make_int2(i0n, heldn ? 0 : cntn);
+        const bool work_n = on_n && !heldn;      // this lane's block can change its state
         __syncwarp();
-#pragma unroll 8
-        for (int q = 0; q < 32; ++q) {
-            const ulonglong2 dsc = s_in[warp][q];
-            double *dstp = &s_m[buf][warp][q][lane];
-            if (lane < (int)dsc.y) {
+        // lane l moves frames 2l, 2l+1 of rows q = l / 16 + 2j (two rows per step)
+        const int half = lane >> 4, col = (lane & 15) * 2;
+#pragma unroll 4
+        for (int q0 = 0; q0 < 32; q0 += 2) {
+            const int q = q0 + half;
+            const int2 d = W.nxt[q];
+            uint16_t *dstp = &W.rms[q][col];
+            if (col + 1 < d.y) {
                 const unsigned sa = (unsigned)__cvta_generic_to_shared(dstp);
-                asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sa), "l"(reinterpret_cast<const double *>(dsc.x) + lane) : "memory");
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(sa), "l"(reinterpret_cast<const uint16_t *>(W.base_rms[q]) + d.x + col) : "memory");
             } else {
-                *dstp = 0.0;
+                uint16_t r0 = 0;
+                if (col < d.y) r0 = reinterpret_cast<const uint16_t *>(W.base_rms[q])[d.x + col];
+                *reinterpret_cast<unsigned *>(dstp) = (unsigned)r0;
             }
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
-        __syncwarp();
+        return work_n;
     };
+    __syncwarp();
     int cb = skip_held(wstart >> 5);
-    issue(0, cb, live);
-    int buf = 0;
+    bool work = issue_rms(cb, live);
     double a_start = a;
     bool merged = false;
     for (;;) {
@@ -553,45 +558,69 @@ k_recur_tiles(const StreamDesc *__restrict__ streams, const PlanDev *__restrict_
         if (on && cb == sb) a_start = a;
         // the value this tile stored earlier at the end of this block (repair rounds only)
         double old_last = 0.0;
-        if (P.mode == 1 && on) old_last = out[i0 + cnt - 1];
-        // ---- rows of the next block start moving now -------------------------------------------
-        const int nb = on ? skip_held(cb + 1) : cb;
-        issue(buf ^ 1, nb, on);
-        asm volatile("cp.async.wait_group 1;" ::: "memory");
+        if (P.mode == 1 && on) old_last = attp[i0 + cnt - 1];
+        W.blk[lane] = make_int2(i0, is_main ? cnt : 0);
+        const bool any_work = __any_sync(FULL, on && work);       // else every lane's block is held: att stays put
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
         __syncwarp();
-        // ---- 32 dependent steps -------------------------------------------------------------
-        if (all_exact) {            // warp-uniform: every band of this warp passed the plan-time division check
+        // ---- phase B: RMS rows -> M rows through the static curve (row-wise: consecutive frames
+        //      have neighbouring RMS values, so a row's gathers touch a few cache lines) --------
+        // (16 rows per batch: all their gathers are in flight together)
+        if (any_work) {
+#pragma unroll
+        for (int q0 = 0; q0 < 32; q0 += 16) {
+            double v[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                const double *curve = reinterpret_cast<const double *>(W.base_curve[q0 + j]);
+                const unsigned r = W.rms[q0 + j][lane];
+                v[j] = (curve != nullptr && r != 0u) ? __ldg(curve + r) : 0.0;
+            }
+#pragma unroll
+            for (int j = 0; j < 16; ++j) W.m[q0 + j][lane] = v[j];
+        }
+        }
+        __syncwarp();
+        // ---- the RMS rows of the next block start moving now -----------------------------------
+        const bool any_main = __any_sync(FULL, is_main);
+        const int nb = on ? skip_held(cb + 1) : cb;
+        work = issue_rms(nb, on);
+        // ---- phase C: 32 dependent steps, one lane per tile --------------------------------------
+        if (!any_work) {            // warp-uniform: nothing moves in this block
+            if (on) {
+#pragma unroll 8
+                for (int k = 0; k < 32; ++k) W.m[lane][k] = a;
+            }
+        } else if (all_exact) {     // warp-uniform: every band of this warp passed the plan-time division check
             if (on) {
 #pragma unroll 8
                 for (int k = 0; k < 32; ++k) {
-                    const double M = s_m[buf][warp][lane][k];
+                    const double M = W.m[lane][k];
                     const double inc = div_const(M, A, rA, true), dec = div_const(M, R, rR, true);
                     a = recur_step(a, M, inc, dec);
-                    s_m[buf][warp][lane][k] = a;
+                    W.m[lane][k] = a;
                 }
             }
         } else if (on) {
 #pragma unroll 1
             for (int k = 0; k < 32; ++k) {
-                const double M = s_m[buf][warp][lane][k];
+                const double M = W.m[lane][k];
                 const double inc = div_const(M, A, rA, exact), dec = div_const(M, R, rR, exact);
                 a = recur_step(a, M, inc, dec);
-                s_m[buf][warp][lane][k] = a;
+                W.m[lane][k] = a;
             }
         }
-        // ---- coalesced row stores of the attenuation (main part of the tile only) ---------
-        s_out[warp][lane] = make_ulonglong2((unsigned long long)(out + i0), (unsigned long long)(is_main ? cnt : 0));
-        __syncwarp();
-        if (__any_sync(FULL, is_main)) {
+        // ---- phase D: coalesced row stores of the attenuation (main part of the tile only) -------
+        if (any_main) {
+            __syncwarp();
 #pragma unroll 8
             for (int q = 0; q < 32; ++q) {
-                const ulonglong2 dsc = s_out[warp][q];
-                if (lane < (int)dsc.y) reinterpret_cast<double *>(dsc.x)[lane] = s_m[buf][warp][q][lane];
+                const int2 d = W.blk[q];
+                if (lane < d.y) reinterpret_cast<double *>(W.base_att[q])[d.x + lane] = W.m[q][lane];
             }
         }
         if (P.mode == 1 && on && __double_as_longlong(a) == __double_as_longlong(old_last)) merged = true;
         cb = nb;
-        buf ^= 1;
         __syncwarp();
     }
     asm volatile("cp.async.wait_group 0;" ::: "memory");
@@ -620,8 +649,9 @@ k_recur_fix(const StreamDesc *__restrict__ streams, const PlanDev *__restrict__ 
     const StreamDesc sd = streams[s];
     const PlanDev *__restrict__ pl = plans + sd.plan;
     if (!pl->multiband || sd.out_frames <= 0) return;
-    const double *__restrict__ m = bp.matt[band] + sd.out_off;
+    const uint16_t *__restrict__ rms = bp.rms[band] + sd.out_off;
     double *__restrict__ out = bp.att[band] + sd.out_off;
+    const double *__restrict__ curve = pl->curve[band];
     const BandDev &bd = pl->band[band];
     const double A = bd.attack_frames, R = bd.release_frames, rA = bd.r_attack, rR = bd.r_release;
     const bool exact = bd.div_trick != 0;
@@ -636,7 +666,8 @@ k_recur_fix(const StreamDesc *__restrict__ streams, const PlanDev *__restrict__ 
         bool merged = false;
         int i = i0;
         for (; i < i1; ++i) {
-            const double M = m[i];
+            const unsigned r = rms[i];
+            const double M = r ? curve[r] : 0.0;
             a = recur_step(a, M, div_const(M, A, rA, exact), div_const(M, R, rR, exact));
             if (__double_as_longlong(a) == __double_as_longlong(out[i])) { merged = true; break; }
             out[i] = a;
@@ -651,14 +682,6 @@ k_recur_fix(const StreamDesc *__restrict__ streams, const PlanDev *__restrict__ 
 // product), then low.overlay(mid).overlay(high) = two saturating int16 adds (ENG:210).
 // grid = (tiles, streams).  nbands == 1 backs the single-band helper entry point.
 // =====================================================================================
-__device__ __forceinline__ int mul_floor16(int v, double g)
-{
-    double val = __dmul_rn((double)v, g);           // audioop.mul: fbound(val * factor)
-    if (val > 32767.0) val = 32767.0;
-    else if (val < -32767.0) val = -32768.0;
-    return (int)floor(val);
-}
-
 template <int CH>
 __global__ void __launch_bounds__(256)
 k_apply(const StreamDesc *__restrict__ streams, const PlanDev *__restrict__ plans, BandPtrs bp,
@@ -1010,7 +1033,7 @@ k_final(const int16_t *__restrict__ proc, const TrackDesc *__restrict__ tracks,
     const bool has = pl->has_lufs != 0;
     const double gain = has ? loud[blockIdx.y].y : 1.0;
     const int16_t *__restrict__ src = proc + td.off * CH;
-    int16_t *__restrict__ dst = out + td.off * CH;
+    int16_t *__restrict__ dst = out + td.dst_off * CH;
     // one frame per thread: 4-byte (stereo) accesses, fully coalesced
     for (int64_t f = (int64_t)blockIdx.x * 256 + threadIdx.x; f < td.frames; f += (int64_t)gridDim.x * 256) {
         int q[CH], r[CH];

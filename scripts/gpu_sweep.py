@@ -15,9 +15,9 @@ plan = make_plan(st, rate, 2)
 offs = [i * n for i in range(ntracks)]; fr = [n] * ntracks; of = [ms_framing(n, rate)] * ntracks
 def step():
     return eng.master_raw(d_in, True, offs, fr, of, [plan], [0] * ntracks, d_out, True, want_loudness=False)
-KS = ["k_recur_count", "k_recur_tiles", "k_recur_repair", "k_recur_fix"]
-for tile, warm, rounds in [(0, 0, -1), (0, 4096, 4), (0, 2048, 4), (0, 1024, 6), (16384, 4096, 4), (8192, 4096, 4), (8192, 2048, 4),
-                           (4096, 2048, 6), (4096, 1024, 6), (2048, 1024, 8), (32768, 8192, 4)]:
+KS = ["k_recur_tiles", "k_recur_repair", "k_recur_fix"]
+for tile, warm, rounds in [(0, 0, -1), (0, 4096, 4), (0, 6144, 4), (16384, 8192, 4), (8192, 8192, 4), (8192, 4096, 4), (32768, 8192, 4), (4096, 8192, 4),
+                           (4096, 4096, 6)]:
     eng.set_recur_tiling(tile, warm, rounds)
     step(); eng.synchronize()
     eng.recur_stats(reset=True)
