@@ -42,8 +42,8 @@ enum {
 /* PCM sample formats of the staging kernels (interleaved frames). */
 enum {
     B200M_FMT_S16 = 0,  /* int16 little endian: the only width the reference handles (ENG:125) */
-    B200M_FMT_S24 = 1,  /* packed 3-byte little endian; declared extension         */
-    B200M_FMT_F32 = 2   /* float32 in [-1, 1]; declared extension                              */
+    B200M_FMT_S24 = 1,  /* packed 3-byte little endian; declared extension: b200m_stage_pcm    */
+    B200M_FMT_F32 = 2   /* float32 in [-1, 1]; declared extension: b200m_stage_pcm             */
 };
 
 typedef struct b200m_handle b200m_handle;
@@ -164,6 +164,43 @@ int b200m_master_batch(b200m_handle *h,
                        const b200m_plan *plans, int n_plans, const int32_t *plan_index,
                        void *pcm_out, int out_on_device,
                        double *loudness_out, double *gain_out);
+
+/* ---- one long track split along time over several GPUs (BASELINE config 4) ---------
+ * Slices are cut at 30-s chunk boundaries (ENG:48-54: every filter and compressor restarts
+ * there), so ENG:48-80 is local to a slice.  Only the loudness measurement (ENG:82-86,
+ * 212-222) couples slices; the host exchanges two halos of processed samples with its
+ * neighbours and SUM-all-reduces the block energies (b200master/longtrack.py, NCCL).
+ * All PCM / z buffers below are DEVICE pointers; work is issued on the handle's stream. */
+
+/* Declared extension (ENG:125 handles 16-bit only): reduce packed little-endian 24-bit PCM to
+ * the reference's 16-bit domain like pydub's set_sample_width(2) = audioop.lin2lin (keep the
+ * high-order 16 bits); float32 goes through the reference's quantiser (ENG:123-126);
+ * B200M_FMT_S16 is a copy.  n_samples = frames * channels. */
+int b200m_stage_pcm(b200m_handle *h, const void *pcm_dev, int fmt, int64_t n_samples, int16_t *out_dev);
+/* Frames of processed audio a slice starting at absolute frame abs_offset needs from the
+ * slice before it (K-weighting warm-up, aligned so the buffer starts at a filter tile
+ * boundary; 0 for the first slice) and after it (one 400 ms block; clip to the track end). */
+int b200m_slice_halo(const b200m_plan *plan, int64_t abs_offset, int64_t *halo_before, int64_t *halo_after);
+/* ENG:48-80 for one slice (a whole number of 30-s chunks, or the track's tail): exciter, EQ,
+ * width, quantise, multiband -> proc_dev (out_frames frames of interleaved int16).  in_frames /
+ * out_frames as in b200m_master_batch (pydub's ms framing applies to the last slice only). */
+int b200m_slice_chain(b200m_handle *h, const int16_t *pcm_dev, int64_t in_frames, int64_t out_frames,
+                      const b200m_plan *plan, int16_t *proc_dev);
+/* K-weighting over [halo | slice | halo] and the 400 ms block energies z_j of every block of
+ * the TRACK whose first frame lies in the slice, written to z_dev[j] (j = track block index;
+ * other entries are left untouched: start from zeros and SUM-all-reduce).  proc_ext_dev holds
+ * ext_frames frames, the slice starts at frame halo_before of it = absolute frame abs_offset. */
+int b200m_slice_energies(b200m_handle *h, const int16_t *proc_ext_dev, int64_t ext_frames, int64_t halo_before,
+                         int64_t local_frames, int64_t abs_offset, int64_t track_frames, const b200m_plan *plan,
+                         double *z_dev, int32_t *first_block_out, int32_t *n_blocks_out);
+/* pyloudnorm numBlocks for a track of track_frames frames (0 if shorter than 400 ms). */
+int b200m_track_blocks(int64_t track_frames, int rate);
+/* Gating over the assembled block energies: integrated loudness and the gain of ENG:219-220. */
+int b200m_gate(b200m_handle *h, const double *z_dev, int32_t n_blocks, const b200m_plan *plan, double *loudness_out, double *gain_out);
+/* ENG:82-89 for one slice: re-float, gain (has_gain != 0: float64 path; else the float32
+ * limiter of a job without loudness target), soft limiter, final quantise. */
+int b200m_slice_final(b200m_handle *h, const int16_t *proc_dev, int64_t frames, const b200m_plan *plan,
+                      int has_gain, double gain, int16_t *out_dev);
 
 /* ---- stage-level entry points (back the reference's helper functions and the
  *      stage parity tests).  All arrays are HOST pointers; n = frames. ----------- */

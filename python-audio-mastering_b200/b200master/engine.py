@@ -148,6 +148,39 @@ class Engine:
             pos += n
         return outs, infos
 
+    # -- time slices of one long track (device tensors; see longtrack.py) ------------------------
+    def stage_pcm(self, pcm_dev, fmt: int, n_samples: int, out_dev):
+        self._ck(self._lib.b200m_stage_pcm(self._h, C.c_void_p(_ptr(pcm_dev)), int(fmt), int(n_samples), C.c_void_p(_ptr(out_dev))))
+
+    def slice_halo(self, plan, abs_offset: int):
+        a, b = C.c_int64(), C.c_int64()
+        self._ck(self._lib.b200m_slice_halo(C.byref(plan), int(abs_offset), C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def slice_chain(self, pcm_dev, in_frames: int, out_frames: int, plan, proc_dev):
+        self._ck(self._lib.b200m_slice_chain(self._h, C.c_void_p(_ptr(pcm_dev)), int(in_frames), int(out_frames),
+                                             C.byref(plan), C.c_void_p(_ptr(proc_dev))))
+
+    def slice_energies(self, proc_ext_dev, ext_frames, halo_before, local_frames, abs_offset, track_frames, plan, z_dev):
+        j0, nb = C.c_int32(), C.c_int32()
+        self._ck(self._lib.b200m_slice_energies(self._h, C.c_void_p(_ptr(proc_ext_dev)), int(ext_frames), int(halo_before),
+                                                int(local_frames), int(abs_offset), int(track_frames), C.byref(plan),
+                                                C.c_void_p(_ptr(z_dev)), C.byref(j0), C.byref(nb)))
+        return j0.value, nb.value
+
+    def track_blocks(self, track_frames: int, rate: int) -> int:
+        return int(self._lib.b200m_track_blocks(int(track_frames), int(rate)))
+
+    def gate(self, z_dev, n_blocks: int, plan):
+        loud, gain = C.c_double(), C.c_double()
+        self._ck(self._lib.b200m_gate(self._h, C.c_void_p(_ptr(z_dev)), int(n_blocks), C.byref(plan), C.byref(loud), C.byref(gain)))
+        return loud.value, gain.value
+
+    def slice_final(self, proc_dev, frames: int, plan, gain, out_dev):
+        self._ck(self._lib.b200m_slice_final(self._h, C.c_void_p(_ptr(proc_dev)), int(frames), C.byref(plan),
+                                             int(gain is not None), float(gain if gain is not None else 1.0),
+                                             C.c_void_p(_ptr(out_dev))))
+
     # -- stage-level helpers (numpy in, numpy out) -----------------------------------------
     def pcm16_to_float(self, pcm: np.ndarray) -> np.ndarray:
         pcm = np.ascontiguousarray(pcm, dtype=np.int16)

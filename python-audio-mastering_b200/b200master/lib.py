@@ -52,6 +52,8 @@ EXPORTS = [
     "b200m_pcm16_to_float", "b200m_float_to_pcm16", "b200m_saturation", "b200m_stereo_width",
     "b200m_sosfilt", "b200m_multiband", "b200m_compress_dynamic_range", "b200m_integrated_loudness",
     "b200m_normalize_to_lufs", "b200m_soft_limiter",
+    "b200m_stage_pcm", "b200m_slice_halo", "b200m_slice_chain", "b200m_slice_energies", "b200m_track_blocks",
+    "b200m_gate", "b200m_slice_final",
 ]
 
 
@@ -98,6 +100,14 @@ def load():
     lib.b200m_normalize_to_lufs.argtypes = [vp, C.POINTER(Biquad), vp, i64, C.c_int, C.c_int, dbl, vp,
                                             C.POINTER(dbl), C.POINTER(dbl)]
     lib.b200m_soft_limiter.argtypes = [vp, vp, C.c_int, i64, dbl, vp]
+    lib.b200m_stage_pcm.argtypes = [vp, vp, C.c_int, i64, vp]
+    lib.b200m_slice_halo.argtypes = [C.POINTER(Plan), i64, C.POINTER(i64), C.POINTER(i64)]
+    lib.b200m_slice_chain.argtypes = [vp, vp, i64, i64, C.POINTER(Plan), vp]
+    lib.b200m_slice_energies.argtypes = [vp, vp, i64, i64, i64, i64, i64, C.POINTER(Plan), vp,
+                                         C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
+    lib.b200m_track_blocks.argtypes = [i64, C.c_int]
+    lib.b200m_gate.argtypes = [vp, vp, C.c_int32, C.POINTER(Plan), C.POINTER(dbl), C.POINTER(dbl)]
+    lib.b200m_slice_final.argtypes = [vp, vp, i64, C.POINTER(Plan), C.c_int, dbl, vp]
     for name in EXPORTS:
         if name not in ("b200m_destroy", "b200m_last_error", "b200m_launch_count"):
             getattr(lib, name).restype = C.c_int

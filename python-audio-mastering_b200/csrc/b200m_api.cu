@@ -755,11 +755,11 @@ static RecurParams recur_params(const b200m_handle *h, const Group &g, int nband
     if (h->recur_tile > 0) {
         P.tile_len = std::max(32, (h->recur_tile + 31) & ~31);
     } else {
-        // about half a resident wave of (chain, tile) lanes (148 SMs x 8 warps x 32); tiles of 2048 ..
+        // about three quarters of a resident wave of (chain, tile) lanes (148 SMs x 12 warps x 32); tiles of 2048 ..
         // 65536 frames: every lane also runs the warm-up (`warm` active frames), so long tiles waste
         // less work (measured: 32768-frame tiles beat 16384 by 1.28x on a 64-track batch) and short
         // tiles give a small batch enough lanes
-        const double want_tiles = 148.0 * 8 * 32 / chains;
+        const double want_tiles = 148.0 * 12 * 32 / chains;
         const double len = std::min(65536.0, std::max(2048.0, g.max_stream_frames / want_tiles));
         P.tile_len = ((int)len + 1023) & ~1023;
     }
@@ -880,6 +880,7 @@ static void plan_group(const b200m_handle *h, GroupPlan &gp, bool in_dev, bool o
         TrackDesc &td = gp.tracks[t - t_begin];
         F = (F + 31) & ~(int64_t)31;            // workspace rows of the compressor are moved in aligned 4-byte pieces
         td.off = F; td.dst_off = Fp; td.frames = out_frames[t]; td.plan = plan_index[t];
+        td.abs0 = 0; td.total_frames = out_frames[t]; td.j0 = 0; td.pad_ = 0;
         td.nblocks = p.has_lufs ? num_blocks(out_frames[t], rate) : 0;
         td.zoff = zoff; zoff += td.nblocks;
         g.max_blocks = std::max(g.max_blocks, td.nblocks);
@@ -935,9 +936,11 @@ struct ExecStreams {
     cudaEvent_t slot_free, h2d_done, comp_done, d2h_done;   // null when not pipelined
 };
 
+// ext_proc != NULL: stop after the chunk-wise part (ENG:48-80) and leave `processed_audio` there
+// (time slices of a long track: loudness is measured across slices, b200m_slice_*)
 static int exec_group(b200m_handle *h, GroupPlan &gp, char *ws, char *pin, const ExecStreams &X,
                       const int16_t *pcm_in, bool in_dev, const int64_t *in_offsets, const int64_t *in_frames,
-                      int16_t *pcm_out, bool out_dev)
+                      int16_t *pcm_out, bool out_dev, int16_t *ext_proc = nullptr)
 {
     Group &g = gp.g;
     const int ch = g.ch;
@@ -949,7 +952,7 @@ static int exec_group(b200m_handle *h, GroupPlan &gp, char *ws, char *pin, const
     SegDesc *d_csegs = A.take<SegDesc>(gp.csegs.size() + 1);
     SegDesc *d_ksegs = A.take<SegDesc>(gp.ksegs.size() + 1);
     double2 *d_loud = A.take<double2>(g.n_tracks);
-    int16_t *d_proc = A.take<int16_t>((size_t)F * ch);
+    int16_t *d_proc = ext_proc ? ext_proc : A.take<int16_t>((size_t)F * ch);
     float *d_kw = A.take<float>(F);
     double *d_z = A.take<double>(gp.zoff + 1);
     double *d_zsel = A.take<double>(gp.zoff + 1);
@@ -1005,6 +1008,7 @@ static int exec_group(b200m_handle *h, GroupPlan &gp, char *ws, char *pin, const
     CK(cudaGetLastError());
     int rc;
     if (g.any_multiband) { rc = launch_compressor(h, g, bp, 3, 0, d_proc, d_spec); if (rc) return rc; }
+    if (ext_proc) return B200M_OK;
     rc = launch_loudness(h, g, d_proc, nullptr, d_kw, d_z, d_zsel, d_loud);
     if (rc) return rc;
     const dim3 gf((unsigned)std::min<int64_t>((g.max_track_frames + 255) / 256, 8192), g.n_tracks);
@@ -1143,6 +1147,203 @@ extern "C" int b200m_master_batch(b200m_handle *h, const void *pcm_in, int in_on
             }
         }
     }
+    return B200M_OK;
+}
+
+// ------------------------------------------------------------------------------------
+// Time slices of ONE long track (BASELINE config 4: a track split along time over several
+// GPUs).  Slices are cut at 30-s chunk boundaries, so everything up to `processed_audio`
+// (ENG:48-80) is local to a slice; only the loudness measurement (ENG:82-86, 212-222) couples
+// them: the K-weighting filter state at the slice start (provided as a halo of the previous
+// slice's processed samples, joined by overlap-discard exactly like the segments inside one
+// GPU) and the 400 ms block energies (every block is computed by the slice that holds its first
+// frame, from a halo of the next slice; the per-rank z arrays are disjoint, so a SUM all-reduce
+// assembles them exactly).  The host (b200master/longtrack.py) moves the halos and the z array
+// with NCCL; these entry points do the arithmetic.  All buffers are DEVICE pointers.
+// ------------------------------------------------------------------------------------
+extern "C" int b200m_stage_pcm(b200m_handle *h, const void *pcm_dev, int fmt, int64_t n_samples, int16_t *out_dev)
+{
+    if (!h) return B200M_ERR_INVALID;
+    if (n_samples < 0 || (n_samples && (!pcm_dev || !out_dev))) return fail(h, B200M_ERR_INVALID, "stage_pcm: bad argument");
+    CK(cudaSetDevice(h->device));
+    if (n_samples == 0) return B200M_OK;
+    const int grid = (int)std::min<int64_t>((n_samples / 4 + 255) / 256 + 1, 148 * 16);
+    if (fmt == B200M_FMT_S16) CK(cudaMemcpyAsync(out_dev, pcm_dev, (size_t)n_samples * 2, cudaMemcpyDeviceToDevice, h->stream));
+    else if (fmt == B200M_FMT_S24) LAUNCH("k_stage_s24", k_stage_s24<<<grid, 256, 0, h->stream>>>((const unsigned char *)pcm_dev, n_samples, out_dev));
+    else if (fmt == B200M_FMT_F32) LAUNCH("k_stage_f32", k_stage_f32<<<grid, 256, 0, h->stream>>>((const float *)pcm_dev, n_samples, out_dev));
+    else return fail(h, B200M_ERR_INVALID, "stage_pcm: unknown format %d", fmt);
+    CK(cudaGetLastError());
+    return B200M_OK;
+}
+
+extern "C" int b200m_slice_halo(const b200m_plan *plan, int64_t abs_offset, int64_t *halo_before, int64_t *halo_after)
+{
+    if (!plan || abs_offset < 0 || plan->sample_rate <= 0) return B200M_ERR_INVALID;
+    const double wt = std::ceil(kweight_warm_frames(*plan) / KTILE);
+    if (!(wt <= 4096)) return B200M_ERR_INVALID;                 // unstable K-weighting: cannot be joined by overlap-discard
+    // the slice's buffer starts at an absolute K-weighting tile boundary, `wt` whole tiles ahead
+    // of the tile that holds the slice's first frame (the first slice starts at the track start)
+    if (halo_before) *halo_before = abs_offset == 0 ? 0 : std::min<int64_t>(abs_offset, (int64_t)wt * KTILE + abs_offset % KTILE);
+    if (halo_after) *halo_after = (int64_t)(0.4 * plan->sample_rate) + 1;     // one 400 ms block beyond the last block start
+    return B200M_OK;
+}
+
+extern "C" int b200m_slice_chain(b200m_handle *h, const int16_t *pcm_dev, int64_t in_frames, int64_t out_frames,
+                                 const b200m_plan *plan, int16_t *proc_dev)
+{
+    if (!h) return B200M_ERR_INVALID;
+    if (!plan || in_frames < 0 || out_frames < 0 || (out_frames && (!pcm_dev || !proc_dev)))
+        return fail(h, B200M_ERR_INVALID, "slice_chain: bad argument");
+    if (out_frames == 0) return B200M_OK;
+    CK(cudaSetDevice(h->device));
+    b200m_plan p = *plan;
+    p.has_lufs = 0;
+    int rc = ensure_plans(h, &p, 1);
+    if (rc) return rc;
+    const int64_t zero = 0;
+    const int32_t pi = 0;
+    GroupPlan gp;
+    plan_group(h, gp, true, true, 0, 1, &zero, &in_frames, &out_frames, &p, &pi, 0);
+    rc = ws_reserve(h, gp.need);
+    if (rc) return rc;
+    rc = pin_reserve(h, gp.pin_bytes);
+    if (rc) return rc;
+    CK(cudaStreamSynchronize(h->stream));       // pinned staging of an earlier call may still be in flight
+    ExecStreams X;
+    X.in = X.comp = X.out = h->stream;
+    X.slot_free = X.h2d_done = X.comp_done = X.d2h_done = nullptr;
+    return exec_group(h, gp, h->ws, h->pin, X, pcm_dev, true, &zero, &in_frames, proc_dev, true, proc_dev);
+}
+
+extern "C" int b200m_slice_energies(b200m_handle *h, const int16_t *proc_ext_dev, int64_t ext_frames, int64_t halo_before,
+                                    int64_t local_frames, int64_t abs_offset, int64_t track_frames, const b200m_plan *plan,
+                                    double *z_dev, int32_t *first_block_out, int32_t *n_blocks_out)
+{
+    if (!h) return B200M_ERR_INVALID;
+    if (!plan || !proc_ext_dev || !z_dev || ext_frames < 0 || halo_before < 0 || local_frames < 0 || abs_offset < halo_before ||
+        halo_before + local_frames > ext_frames || abs_offset + local_frames > track_frames)
+        return fail(h, B200M_ERR_INVALID, "slice_energies: bad argument");
+    CK(cudaSetDevice(h->device));
+    const int rate = plan->sample_rate, ch = plan->channels;
+    if ((double)track_frames < 0.4 * rate) return fail(h, B200M_ERR_TOO_SHORT, "audio must have length greater than the block size (400 ms)");
+    b200m_plan p = *plan;
+    p.has_lufs = 1;
+    int rc = ensure_plans(h, &p, 1);
+    if (rc) return rc;
+    const int64_t abs0 = abs_offset - halo_before;
+    if (abs0 % KTILE != 0) return fail(h, B200M_ERR_INVALID, "slice_energies: the buffer must start at a K-weighting tile boundary (use b200m_slice_halo)");
+    // blocks of the TRACK whose first frame lies in this slice: l_j = int(0.4 * (j * 0.25) * rate)
+    const int nb_total = num_blocks(track_frames, rate);
+    auto lj = [&](int64_t j) { return (int64_t)(0.4 * ((double)j * 0.25) * (double)rate); };
+    int64_t j0 = (int64_t)std::floor((double)abs_offset / (0.1 * rate)) - 2;
+    if (j0 < 0) j0 = 0;
+    while (j0 < nb_total && lj(j0) < abs_offset) ++j0;
+    int64_t j1 = j0;
+    while (j1 < nb_total && lj(j1) < abs_offset + local_frames) ++j1;
+    if (first_block_out) *first_block_out = (int32_t)j0;
+    if (n_blocks_out) *n_blocks_out = (int32_t)(j1 - j0);
+    if (j1 == j0) return B200M_OK;
+    // the last block must end inside the buffer (or at the track end)
+    {
+        int64_t u = (int64_t)(0.4 * ((double)(j1 - 1) * 0.25 + 1.0) * (double)rate);
+        if (u > track_frames) u = track_frames;
+        if (u - abs0 > ext_frames) return fail(h, B200M_ERR_INVALID, "slice_energies: halo after the slice is too short for its last block");
+    }
+    // K-weighting segments over the buffer: the tile holding the slice's first frame onwards
+    const int64_t begin = (halo_before / KTILE) * KTILE;
+    const double wt = std::ceil(kweight_warm_frames(p) / KTILE);
+    const int warm = (int)std::min<double>((double)begin, wt * KTILE);
+    if (abs_offset != 0 && begin < (int64_t)(wt * KTILE)) return fail(h, B200M_ERR_INVALID, "slice_energies: halo before the slice is too short (use b200m_slice_halo)");
+    std::vector<SegDesc> segs;
+    {
+        const int64_t ntiles = (ext_frames - begin + KTILE - 1) / KTILE;
+        const int64_t seg = std::max<int64_t>(std::max<int64_t>(8, 2 * (int64_t)wt), std::min<int64_t>(32, ntiles / (148 * 6)));
+        for (int64_t t = 0; t < ntiles; t += seg) {
+            const int64_t b = begin + t * KTILE, e = std::min<int64_t>(ext_frames, begin + (t + seg) * KTILE);
+            segs.push_back({b, e, 0, (int32_t)(t == 0 ? warm : (int)(wt * KTILE))});
+        }
+    }
+    TrackDesc td = {0, 0, ext_frames, j0, (int32_t)(j1 - j0), 0, abs0, track_frames, (int32_t)j0, 0};
+    rc = ws_reserve(h, 65536 + (size_t)ext_frames * 4 + segs.size() * sizeof(SegDesc));
+    if (rc) return rc;
+    rc = pin_reserve(h, sizeof td + segs.size() * sizeof(SegDesc));
+    if (rc) return rc;
+    CK(cudaStreamSynchronize(h->stream));
+    Arena A(h->ws);
+    TrackDesc *d_tracks = A.take<TrackDesc>(1);
+    SegDesc *d_segs = A.take<SegDesc>(segs.size());
+    float *d_kw = A.take<float>(ext_frames);
+    std::memcpy(h->pin, &td, sizeof td);
+    std::memcpy(h->pin + sizeof td, segs.data(), segs.size() * sizeof(SegDesc));
+    CK(cudaMemcpyAsync(d_tracks, h->pin, sizeof td, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(d_segs, h->pin + sizeof td, segs.size() * sizeof(SegDesc), cudaMemcpyHostToDevice, h->stream));
+    Group g;
+    g.ch = ch; g.n_tracks = 1; g.d_tracks = d_tracks; g.d_ksegs = d_segs; g.n_ksegs = (int)segs.size();
+    if (ch == 2) LAUNCH("k_kweight", k_kweight<2, int16_t><<<g.n_ksegs, KNT, kweight_smem_bytes(), h->stream>>>(proc_ext_dev, d_tracks, d_segs, h->d_plans, d_kw));
+    else         LAUNCH("k_kweight", k_kweight<1, int16_t><<<g.n_ksegs, KNT, kweight_smem_bytes(), h->stream>>>(proc_ext_dev, d_tracks, d_segs, h->d_plans, d_kw));
+    const dim3 gb((unsigned)(j1 - j0), 1);
+    LAUNCH("k_blocks", k_blocks<<<gb, BNT, (size_t)h->blocks_smem_floats * 4 + 16, h->stream>>>(d_kw, d_tracks, h->d_plans, z_dev));
+    CK(cudaGetLastError());
+    return B200M_OK;
+}
+
+extern "C" int b200m_track_blocks(int64_t track_frames, int rate)
+{
+    return (rate > 0 && (double)track_frames >= 0.4 * rate) ? num_blocks(track_frames, rate) : 0;
+}
+
+extern "C" int b200m_gate(b200m_handle *h, const double *z_dev, int32_t n_blocks, const b200m_plan *plan, double *loudness_out, double *gain_out)
+{
+    if (!h) return B200M_ERR_INVALID;
+    if (!plan || n_blocks < 0 || (n_blocks && !z_dev)) return fail(h, B200M_ERR_INVALID, "gate: bad argument");
+    CK(cudaSetDevice(h->device));
+    b200m_plan p = *plan;
+    p.has_lufs = 1;
+    int rc = ensure_plans(h, &p, 1);
+    if (rc) return rc;
+    rc = ws_reserve(h, 4096 + (size_t)(n_blocks + 2) * 8);
+    if (rc) return rc;
+    Arena A(h->ws);
+    TrackDesc *d_tracks = A.take<TrackDesc>(1);
+    double2 *d_loud = A.take<double2>(1);
+    double *d_zsel = A.take<double>(n_blocks + 1);
+    TrackDesc td = {0, 0, 0, 0, n_blocks, 0, 0, 0, 0, 0};
+    CK(cudaMemcpyAsync(d_tracks, &td, sizeof td, cudaMemcpyHostToDevice, h->stream));
+    LAUNCH("k_gate", k_gate<<<1, 32, 0, h->stream>>>(d_tracks, h->d_plans, z_dev, d_zsel, d_loud));
+    CK(cudaGetLastError());
+    double2 res;
+    CK(cudaMemcpyAsync(&res, d_loud, sizeof res, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    if (loudness_out) *loudness_out = res.x;
+    if (gain_out) *gain_out = res.y;
+    return B200M_OK;
+}
+
+extern "C" int b200m_slice_final(b200m_handle *h, const int16_t *proc_dev, int64_t frames, const b200m_plan *plan,
+                                 int has_gain, double gain, int16_t *out_dev)
+{
+    if (!h) return B200M_ERR_INVALID;
+    if (!plan || frames < 0 || (frames && (!proc_dev || !out_dev))) return fail(h, B200M_ERR_INVALID, "slice_final: bad argument");
+    if (frames == 0) return B200M_OK;
+    CK(cudaSetDevice(h->device));
+    b200m_plan p = *plan;
+    p.has_lufs = has_gain != 0;                 // without a loudness target the limiter runs in float32 (ENG:88 on float32 samples)
+    int rc = ensure_plans(h, &p, 1);
+    if (rc) return rc;
+    rc = ws_reserve(h, 4096);
+    if (rc) return rc;
+    Arena A(h->ws);
+    TrackDesc *d_tracks = A.take<TrackDesc>(1);
+    double2 *d_loud = A.take<double2>(1);
+    TrackDesc td = {0, 0, frames, 0, 0, 0, 0, frames, 0, 0};
+    const double2 lg = make_double2(0.0, gain);
+    CK(cudaMemcpyAsync(d_tracks, &td, sizeof td, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(d_loud, &lg, sizeof lg, cudaMemcpyHostToDevice, h->stream));
+    const dim3 gf((unsigned)std::min<int64_t>((frames + 255) / 256, 8192 * 4), 1);
+    if (p.channels == 2) LAUNCH("k_final", k_final<2><<<gf, 256, 0, h->stream>>>(proc_dev, d_tracks, h->d_plans, d_loud, out_dev));
+    else                 LAUNCH("k_final", k_final<1><<<gf, 256, 0, h->stream>>>(proc_dev, d_tracks, h->d_plans, d_loud, out_dev));
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(h->stream));       // td / lg live on this stack frame
     return B200M_OK;
 }
 
@@ -1347,7 +1548,7 @@ static int loudness_core(b200m_handle *h, const b200m_biquad *kw, const float *x
     p.kw[0] = kw[0]; p.kw[1] = kw[1];
     int rc = ensure_plans(h, &p, 1);
     if (rc) return rc;
-    TrackDesc td = {0, 0, n, 0, num_blocks(n, rate), 0};
+    TrackDesc td = {0, 0, n, 0, num_blocks(n, rate), 0, 0, n, 0, 0};
     const size_t ns = (size_t)n * channels;
     rc = ws_reserve(h, 65536 + ns * 4 + (size_t)n * 8 + (scaled_out ? ns * 8 : 0) + (size_t)(td.nblocks + 2) * 16 + (size_t)(n / KTILE + 2) * sizeof(SegDesc));
     if (rc) return rc;

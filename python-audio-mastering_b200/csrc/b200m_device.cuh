@@ -87,8 +87,13 @@ struct TrackDesc {
     int64_t dst_off;    // first frame in the group's packed output (tracks back to back)
     int64_t frames;     // out frames
     int64_t zoff;       // first block in z
-    int32_t nblocks;    // pyloudnorm numBlocks
+    int32_t nblocks;    // pyloudnorm numBlocks (of this buffer's share when the track is split along time)
     int32_t plan;
+    // A time slice of a longer track (b200m_slice_*): buffer frame 0 is absolute frame abs0 of a
+    // track of total_frames frames, and the first loudness block computed here is block j0.
+    // Whole tracks: abs0 = 0, total_frames = frames, j0 = 0.
+    int64_t abs0, total_frames;
+    int32_t j0, pad_;
 };
 
 // ------------------------------------------------------------------------------------

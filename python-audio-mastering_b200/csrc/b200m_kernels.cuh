@@ -880,21 +880,21 @@ k_blocks(const float *__restrict__ kw, const TrackDesc *__restrict__ tracks,
     extern __shared__ float bval[];              // [nleaves + ninternal]
     const TrackDesc td = tracks[blockIdx.y];
     const PlanDev *__restrict__ pl = plans + td.plan;
-    const int j = blockIdx.x, tid = threadIdx.x;
-    if (!pl->has_lufs || j >= td.nblocks) return;
+    const int jb = blockIdx.x, j = td.j0 + jb, tid = threadIdx.x;      // jb: slot in this buffer's z, j: block of the track
+    if (!pl->has_lufs || jb >= td.nblocks) return;
     const double rate = (double)pl->rate, Tg = 0.4, step = 0.25;
     int64_t l = (int64_t)__dmul_rn(__dmul_rn(Tg, __dmul_rn((double)j, step)), rate);
     int64_t u = (int64_t)__dmul_rn(__dmul_rn(Tg, __dadd_rn(__dmul_rn((double)j, step), 1.0)), rate);
-    if (u > td.frames) u = td.frames;       // numpy slicing clamps
+    if (u > td.total_frames) u = td.total_frames;       // numpy slicing clamps
     if (l > u) l = u;
-    const float *__restrict__ y = kw + td.off + l;
+    const float *__restrict__ y = kw + td.off + (l - td.abs0);
     const float scale = (float)(1.0 / (Tg * rate));
     const int64_t n = u - l;
     const int32_t *__restrict__ T = pl->ptree;
     if (T == nullptr || (int64_t)T[0] != n) {
         if (tid == 0) {
             auto get = [y](int64_t i) { const float v = y[i]; return F32(__fmul_rn(v, v)); };
-            z[td.zoff + j] = (double)__fmul_rn(scale, np_pairwise_sum<F32>(get, n).v);
+            z[td.zoff + jb] = (double)__fmul_rn(scale, np_pairwise_sum<F32>(get, n).v);
         }
         return;
     }
@@ -927,7 +927,7 @@ k_blocks(const float *__restrict__ kw, const TrackDesc *__restrict__ tracks,
         for (int i = lvl[lv] + tid; i < lvl[lv + 1]; i += BNT) bval[nleaves + i] = __fadd_rn(bval[nl[i]], bval[nr[i]]);
         __syncthreads();
     }
-    if (tid == 0) z[td.zoff + j] = (double)__fmul_rn(scale, nint ? bval[nleaves + nint - 1] : bval[0]);
+    if (tid == 0) z[td.zoff + jb] = (double)__fmul_rn(scale, nint ? bval[nleaves + nint - 1] : bval[0]);
 }
 
 // =====================================================================================
@@ -1052,6 +1052,39 @@ k_final(const int16_t *__restrict__ proc, const TrackDesc *__restrict__ tracks,
         if (CH == 2) *reinterpret_cast<short2 *>(dst + f * 2) = make_short2((short)r[0], (short)r[CH - 1]);
         else dst[f] = (int16_t)r[0];
     }
+}
+
+// =====================================================================================
+// k_stage_s24 / k_stage_f32: declared extension (the reference handles 16-bit PCM only, ENG:125).
+// Packed little-endian 24-bit PCM is reduced to the reference's 16-bit domain exactly like
+// pydub's AudioSegment.set_sample_width(2) = audioop.lin2lin (keep the high-order 16 bits);
+// float32 PCM goes through the reference's own quantiser (ENG:123-126).  Each thread converts
+// four samples: three aligned 32-bit loads for 12 bytes of 24-bit PCM, one 8-byte store.
+// =====================================================================================
+__global__ void __launch_bounds__(256)
+k_stage_s24(const unsigned char *__restrict__ in, int64_t n, int16_t *__restrict__ out)
+{
+    const bool al = ((reinterpret_cast<unsigned long long>(in) & 3ull) | (reinterpret_cast<unsigned long long>(out) & 7ull)) == 0;
+    for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g * 4 < n; g += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t i = g * 4;
+        if (al && i + 4 <= n) {
+            const unsigned w0 = reinterpret_cast<const unsigned *>(in)[3 * g], w1 = reinterpret_cast<const unsigned *>(in)[3 * g + 1],
+                           w2 = reinterpret_cast<const unsigned *>(in)[3 * g + 2];
+            // bytes b0..b11; sample k = b[3k+1] | b[3k+2] << 8
+            const unsigned s0 = (w0 >> 8) & 0xffffu, s1 = w1 & 0xffffu, s2 = (w1 >> 24) | ((w2 & 0xffu) << 8), s3 = w2 >> 16;
+            reinterpret_cast<uint2 *>(out)[g] = make_uint2(s0 | (s1 << 16), s2 | (s3 << 16));
+        } else {
+            for (int64_t k = i; k < n && k < i + 4; ++k)
+                out[k] = (int16_t)((unsigned)in[3 * k + 1] | ((unsigned)in[3 * k + 2] << 8));
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256)
+k_stage_f32(const float *__restrict__ in, int64_t n, int16_t *__restrict__ out)
+{
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        out[i] = (int16_t)quant16((double)in[i]);
 }
 
 // =====================================================================================
