@@ -131,7 +131,7 @@ int b200m_set_recur_tiling(b200m_handle *h, int tile_frames, int warm_frames, in
 int b200m_set_segment_tiles(b200m_handle *h, int chain_tiles, int kweight_tiles);
 /* Host-buffer pipeline of b200m_master_batch: with host PCM the batch is cut into groups of
  * tracks and the H2D copy of group g+1 / D2H copy of group g-1 run on side streams while the
- * kernels of group g run (two workspace slots).  on = 0 runs copy -> kernels -> copy in sequence.
+ * kernels of group g run (three workspace slots).  on = 0 runs copy -> kernels -> copy in sequence.
  * Default on.  Results do not depend on it. */
 int b200m_set_pipeline(b200m_handle *h, int on);
 /* Verification counters since the last reset: tiles repaired by the sequential pass, frames it

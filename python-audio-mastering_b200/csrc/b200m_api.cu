@@ -569,10 +569,8 @@ template <typename K> static cudaError_t allow_smem(K kernel, size_t bytes)
 
 static size_t detect_smem_bytes(int H)
 {
-    const int total = H + DT;
-    int K = (total + DNT) / DNT;
-    K |= 1;
-    return (size_t)(total + 1) * 8 + (size_t)DNT * K * 4;
+    const int R = detect_run(H);
+    return (size_t)(R * DNT + 4) * 8 + (size_t)R * DNT * 4;
 }
 
 extern "C" int b200m_abi_version(void) { return B200M_ABI_VERSION; }
@@ -813,7 +811,7 @@ static int launch_compressor(b200m_handle *h, const Group &g, const BandPtrs &bp
         }
     }
     LAUNCH("k_recur_fix", k_recur_fix<<<(chains + 31) / 32, 32, 0, h->stream>>>(g.d_streams, h->d_plans, P, bp, ss[cur], se[cur], h->d_counters));
-    const dim3 ga((g.max_stream_frames + 255) / 256, g.n_streams);
+    const dim3 ga((g.max_stream_frames + 511) / 512, g.n_streams);
     if (g.ch == 2) LAUNCH("k_apply", k_apply<2><<<ga, 256, 0, h->stream>>>(g.d_streams, h->d_plans, bp, nbands, band_base, d_proc));
     else           LAUNCH("k_apply", k_apply<1><<<ga, 256, 0, h->stream>>>(g.d_streams, h->d_plans, bp, nbands, band_base, d_proc));
     CK(cudaGetLastError());
@@ -850,7 +848,7 @@ static int num_blocks(int64_t frames, int rate)
 // (plan_group: stream / track / segment descriptors and its workspace need) and executed
 // from a workspace slot (exec_group).  With device-resident PCM there is one slot and
 // everything runs on the handle's stream.  With HOST buffers the groups are pipelined over
-// two slots and three streams: the H2D copy of group g+1 and the D2H copy of group g-1
+// three slots and three streams: the H2D copy of group g+1 and the D2H copy of group g-1
 // overlap the kernels of group g (copy engines vs SMs), ordered by events.
 // ------------------------------------------------------------------------------------
 struct GroupPlan {
@@ -1062,7 +1060,7 @@ extern "C" int b200m_master_batch(b200m_handle *h, const void *pcm_in, int in_on
     if (rc) return rc;
     const bool in_dev = in_on_device != 0, out_dev = out_on_device != 0;
     const bool pipelined = h->pipeline && (!in_dev || !out_dev) && n_tracks > 1;
-    const int slots = pipelined ? 2 : 1;
+    const int slots = pipelined ? 3 : 1;        // a slot is busy for H2D + kernels + D2H of its group: three keep all engines fed
 
     // ---- cut the batch into groups ---------------------------------------------------------
     // a group must fit one workspace slot; with host buffers it is also at most ~1/8 of the batch
@@ -1116,7 +1114,7 @@ extern "C" int b200m_master_batch(b200m_handle *h, const void *pcm_in, int in_on
         if (pipelined) {
             X.in = h->s_in; X.comp = h->stream; X.out = h->s_out;
             X.h2d_done = sync_event(h, 1 + 3 * i); X.comp_done = sync_event(h, 2 + 3 * i); X.d2h_done = sync_event(h, 3 + 3 * i);
-            X.slot_free = i >= 2 ? sync_event(h, 3 + 3 * (i - 2)) : nullptr;      // D2H of the slot's previous group
+            X.slot_free = i >= (size_t)slots ? sync_event(h, 3 + 3 * (i - slots)) : nullptr;      // D2H of the slot's previous group
         } else {
             X.in = X.comp = X.out = h->stream;
             X.slot_free = X.h2d_done = X.comp_done = X.d2h_done = nullptr;

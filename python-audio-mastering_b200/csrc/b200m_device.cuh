@@ -143,12 +143,15 @@ __device__ __forceinline__ void section_round(double (&x)[SEG], const SecTab *__
     double z0 = fma(T->Q[lane][0], m0, fma(T->Q[lane][1], m1, e0));
     double z1 = fma(T->Q[lane][2], m0, fma(T->Q[lane][3], m1, e1));
     const double b0 = T->b0, b1 = T->b1, b2 = T->b2, na1 = -T->a1, na2 = -T->a2;
+    // scipy _sosfilt (DF2T): y = b0 x + z0; z0 = b1 x - a1 y + z1; z1 = b2 x - a2 y.  The terms that do
+    // not depend on y are formed first, so the dependent chain is two FMAs per sample (y -> z0 -> y).
 #pragma unroll
     for (int n = 0; n < SEG; ++n) {
-        double xn = x[n];
-        double y = fma(b0, xn, z0);                 // scipy _sosfilt: x_n = b0*x_c + z0
-        z0 = fma(b1, xn, fma(na1, y, z1));          //   z0 = b1*x_c - a1*x_n + z1
-        z1 = fma(b2, xn, na2 * y);                  //   z1 = b2*x_c - a2*x_n
+        const double xn = x[n];
+        const double t0 = fma(b1, xn, z1), t1 = b2 * xn;
+        const double y = fma(b0, xn, z0);
+        z0 = fma(na1, y, t0);
+        z1 = fma(na2, y, t1);
         x[n] = y;
     }
 }
@@ -160,8 +163,10 @@ __device__ __forceinline__ void section_round(double (&x)[SEG], const SecTab *__
 // detected on the bit pattern.
 __device__ __forceinline__ int quant16(double y)
 {
-    int iv = max(-32768, min(32768, __double2int_rz(y * 32768.0)));
-    if (((unsigned long long)__double_as_longlong(y) << 1) > 0xffe0000000000000ull) iv = 0;
+    const int raw = __double2int_rz(y * 32768.0);
+    int iv = max(-32768, min(32768, raw));
+    // F2I yields INT_MIN for NaN (and for y <= -65536): only then look at the bit pattern
+    if (raw == (int)0x80000000 && ((unsigned long long)__double_as_longlong(y) << 1) > 0xffe0000000000000ull) iv = 0;
     return (int)(short)iv;
 }
 

@@ -265,7 +265,7 @@ constexpr size_t chain_smem_bytes()
 // grid = (tiles, streams, bands).
 // =====================================================================================
 constexpr int DT = 4096;        // frames per tile
-constexpr int DNT = 256;
+constexpr int DNT = 384;
 
 __device__ __forceinline__ unsigned window_rms(unsigned long long S, unsigned n)
 {
@@ -273,11 +273,26 @@ __device__ __forceinline__ unsigned window_rms(unsigned long long S, unsigned n)
     // largest r with r*r*n <= S  ==  (unsigned)sqrt((double)S / n): the quotient is a
     // multiple of 1/n, so it can never sit within double rounding of a perfect square
     // without being one.
-    unsigned r = (unsigned)sqrtf(__fdividef((float)S, (float)n));
+    float q;                                    // MUFU-grade estimate (off by at most one), corrected exactly below
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(q) : "f"(__fdividef((float)S, (float)n)));
+    unsigned r = (unsigned)q;
     if (r > 32768u) r = 32768u;
     while ((unsigned long long)r * r * n > S) --r;
     while ((unsigned long long)(r + 1) * (r + 1) * n <= S) ++r;
     return r;
+}
+
+__device__ __forceinline__ unsigned energy2(unsigned w)      // one stereo frame packed as two int16
+{
+    const int l = (int)(short)(w & 0xffffu), r = (int)w >> 16;
+    return (unsigned)(l * l) + (unsigned)(r * r);
+}
+
+// elements per thread in the prefix scan of the extended tile [t0 - HP, t0 + DT): a multiple of 4
+__host__ __device__ inline int detect_run(int H)
+{
+    const int HP = (H + 15) & ~15;
+    return (((HP + DT + DNT - 1) / DNT) + 3) & ~3;
 }
 
 template <int CH>
@@ -292,66 +307,92 @@ k_detect(const StreamDesc *__restrict__ streams, const PlanDev *__restrict__ pla
     const int t0 = blockIdx.x * DT;
     if (!pl->multiband || t0 >= sd.out_frames) return;
     const int H = pl->band[band].look;
-    const int total = H + DT;                       // local element k <-> frame t0 - H + k
-    int K = (total + DNT) / DNT;                    // covers k = 0..total
-    K |= 1;                                         // odd stride: conflict-free smem walks
-    unsigned long long *P = reinterpret_cast<unsigned long long *>(smem_raw);   // [total + 1]
-    unsigned *se = reinterpret_cast<unsigned *>(P + (total + 1));              // [DNT * K]
+    const int HP = (H + 15) & ~15;                  // history kept ahead of the tile (16-byte aligned loads)
+    const int ET = HP + DT;                         // extended tile: element k <-> frame t0 - HP + k
+    const int R = detect_run(H);                    // R * DNT >= ET
+    unsigned long long *P = reinterpret_cast<unsigned long long *>(smem_raw);   // [R * DNT + 4] exclusive prefix sums
+    unsigned *e = reinterpret_cast<unsigned *>(P + R * DNT + 4);               // [R * DNT] frame energies
     __shared__ unsigned long long wsum[DNT / 32];
+    __shared__ unsigned sbits[DT / 1024];
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
 
+    // ---- phase 1: frame energies, four frames per load (coalesced 16 / 8-byte pieces) -----------
     const int16_t *__restrict__ src = bp.band[band] + sd.out_off * CH;
-    for (int k = tid; k < DNT * K; k += DNT) {
-        const int f = t0 - H + k;
-        unsigned e = 0;
-        if (k < total && f >= 0 && f < sd.out_frames) {
-            if (CH == 2) {
-                const short2 q = *reinterpret_cast<const short2 *>(src + (int64_t)f * 2);
-                e = (unsigned)((int)q.x * q.x) + (unsigned)((int)q.y * q.y);
+    const bool vec = (reinterpret_cast<unsigned long long>(src) & (CH == 2 ? 15ull : 7ull)) == 0;   // chunk starts at odd rates may not be
+    for (int g = tid; g * 4 < R * DNT; g += DNT) {
+        const int k = g * 4, f = t0 - HP + k;       // f is a multiple of 4: a group never straddles frame 0
+        uint4 ev = make_uint4(0u, 0u, 0u, 0u);
+        if (k < ET && f >= 0 && f < sd.out_frames) {
+            if (!vec) {
+                unsigned t[4] = {0u, 0u, 0u, 0u};
+                for (int i = 0; i < 4 && f + i < sd.out_frames; ++i) {
+                    if (CH == 2) t[i] = energy2(*reinterpret_cast<const unsigned *>(src + (int64_t)(f + i) * 2));
+                    else { const int v = src[f + i]; t[i] = (unsigned)(v * v); }
+                }
+                ev = make_uint4(t[0], t[1], t[2], t[3]);
+            } else if (CH == 2) {
+                const uint4 q = __ldg(reinterpret_cast<const uint4 *>(src + (int64_t)f * 2));
+                ev = make_uint4(energy2(q.x), energy2(q.y), energy2(q.z), energy2(q.w));
             } else {
-                const int q = src[f];
-                e = (unsigned)(q * q);
+                const uint2 q = __ldg(reinterpret_cast<const uint2 *>(src + f));
+                const int s0 = (int)(short)(q.x & 0xffffu), s1 = (int)q.x >> 16, s2 = (int)(short)(q.y & 0xffffu), s3 = (int)q.y >> 16;
+                ev = make_uint4((unsigned)(s0 * s0), (unsigned)(s1 * s1), (unsigned)(s2 * s2), (unsigned)(s3 * s3));
+            }
+            if (f + 3 >= sd.out_frames) {           // the stream ends inside this group
+                if (f + 1 >= sd.out_frames) ev.y = 0u;
+                if (f + 2 >= sd.out_frames) ev.z = 0u;
+                ev.w = 0u;
             }
         }
-        se[k] = e;
+        reinterpret_cast<uint4 *>(e)[g] = ev;
     }
+    if (tid < DT / 1024) sbits[tid] = 0xffffffffu;                 // blocks past the end count as held
     __syncthreads();
-    unsigned long long mine = 0;
-    for (int m = 0; m < K; ++m) mine += se[tid * K + m];
-    unsigned long long inc = mine;
+
+    // ---- phase 2: exclusive prefix sums (uint64: a 960-frame window of full-scale stereo is 2^41) --
+    const uint4 *my = reinterpret_cast<const uint4 *>(e + tid * R);
+    unsigned long long run = 0;
+    for (int i = 0; i < R / 4; ++i) {
+        const uint4 v = my[i];
+        run += (unsigned long long)v.x + v.y + ((unsigned long long)v.z + v.w);
+    }
+    unsigned long long inc = run;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
-        unsigned long long t = __shfl_up_sync(FULL, inc, d);
+        const unsigned long long t = __shfl_up_sync(FULL, inc, d);
         if (lane >= d) inc += t;
     }
     if (lane == 31) wsum[wid] = inc;
     __syncthreads();
-    unsigned long long base = 0;
-    for (int w = 0; w < wid; ++w) base += wsum[w];
-    unsigned long long run = base + inc - mine;     // exclusive prefix at this thread's first element
-    for (int m = 0; m < K; ++m) {
-        const int k = tid * K + m;
-        if (k <= total) P[k] = run;
-        run += se[k];
+    unsigned long long ex = inc - run;
+    for (int w = 0; w < wid; ++w) ex += wsum[w];
+    unsigned long long *myP = P + tid * R;
+    for (int i = 0; i < R / 4; ++i) {
+        const uint4 v = my[i];
+        ulonglong2 a, b2;
+        a.x = ex; a.y = ex + v.x; ex = a.y + v.y;
+        b2.x = ex; b2.y = ex + v.z; ex = b2.y + v.w;
+        reinterpret_cast<ulonglong2 *>(myP)[2 * i] = a;
+        reinterpret_cast<ulonglong2 *>(myP)[2 * i + 1] = b2;
     }
+    if (tid == DNT - 1) P[R * DNT] = ex;
     __syncthreads();
+
+    // ---- phase 3: window sum by difference, integer RMS, hold flags ------------------------------
     // The static curve is a pure function of the integer RMS (32769 values, tabulated at plan
     // time); it is applied inside the recurrence kernel.  Here: the RMS itself (2 bytes per frame)
     // and one flag per 32-frame block saying that rms <= threshold throughout (M == 0: state held).
     uint16_t *__restrict__ dst = bp.rms[band] + sd.out_off;
     const unsigned hold_max = (unsigned)pl->band[band].hold_max;   // curve[r] == 0  <=>  r <= hold_max
     const int nvalid = min(DT, sd.out_frames - t0);
-    __shared__ unsigned sbits[DT / 1024];
-    if (tid < DT / 1024) sbits[tid] = 0xffffffffu;                 // blocks past the end count as held
-    __syncthreads();
     for (int i = tid; i < ((nvalid + 31) & ~31); i += DNT) {      // whole warps: 32 consecutive frames each
         const int f = t0 + i;
         bool act = false;
         if (i < nvalid) {
-            const unsigned long long S = P[i + H] - P[i];
-            const unsigned n = (unsigned)CH * (unsigned)min(f, H);
-            const unsigned r = window_rms(S, n);
-            dst[f] = (uint16_t)r;                                  // r <= 32768 > 65535? no: fits (max 32768)
+            const int hh = min(f, H);
+            const unsigned long long S = P[HP + i] - P[HP + i - hh];
+            const unsigned r = window_rms(S, (unsigned)CH * (unsigned)hh);
+            dst[f] = (uint16_t)r;
             act = (int)r > (int)hold_max;
         }
         const unsigned active = __ballot_sync(FULL, act);
@@ -427,13 +468,12 @@ __device__ __forceinline__ double recur_step(double a, double M, double inc, dou
     return p ? vu : vd;
 }
 
-// audioop.mul: floor(fbound(sample * factor)) with fbound's clip to [-32768, 32767]
+// audioop.mul: floor(fbound(sample * factor)), fbound clipping to [-32768, 32767] ("val < minval + 1
+// -> minval").  Clipping the floored integer instead is the same function: for val in
+// (-32768, -32767) both give -32768, above 32767 both give 32767; F2I.FLOOR saturates.
 __device__ __forceinline__ int mul_floor16(int v, double g)
 {
-    double val = __dmul_rn((double)v, g);
-    if (val > 32767.0) val = 32767.0;
-    else if (val < -32767.0) val = -32768.0;
-    return (int)floor(val);
+    return max(-32768, min(32767, __double2int_rd(__dmul_rn((double)v, g))));
 }
 
 __global__ void __launch_bounds__(32 * RW)
@@ -680,8 +720,23 @@ k_recur_fix(const StreamDesc *__restrict__ streams, const PlanDev *__restrict__ 
 // =====================================================================================
 // k_apply: gain = 10^(-att/20) per frame and band, audioop.mul (floor of the clamped
 // product), then low.overlay(mid).overlay(high) = two saturating int16 adds (ENG:210).
-// grid = (tiles, streams).  nbands == 1 backs the single-band helper entry point.
+// Two frames per thread (16-byte attenuation loads, 8-byte sample loads): six independent
+// exp10 chains in flight.  grid = (tiles of 512 frames, streams).  nbands == 1 backs the
+// single-band helper entry point.
 // =====================================================================================
+template <int CH>
+__device__ __forceinline__ void apply_frame(int &acc0, int &acc1, unsigned smp, double a, bool first)
+{
+    int v0 = (int)(short)(smp & 0xffffu), v1 = CH == 2 ? (int)smp >> 16 : 0;
+    if (a != 0.0) {                                 // pydub: `if attenuation != 0.0`
+        const double g = exp10(a * -0.05);          // db_to_float(-att) = 10 ** (-att / 20)
+        v0 = mul_floor16(v0, g);
+        if (CH == 2) v1 = mul_floor16(v1, g);
+    }
+    acc0 = first ? v0 : max(-32768, min(32767, acc0 + v0));
+    if (CH == 2) acc1 = first ? v1 : max(-32768, min(32767, acc1 + v1));
+}
+
 template <int CH>
 __global__ void __launch_bounds__(256)
 k_apply(const StreamDesc *__restrict__ streams, const PlanDev *__restrict__ plans, BandPtrs bp,
@@ -689,34 +744,45 @@ k_apply(const StreamDesc *__restrict__ streams, const PlanDev *__restrict__ plan
 {
     const StreamDesc sd = streams[blockIdx.y];
     if (!plans[sd.plan].multiband) return;
-    const int f = blockIdx.x * 256 + threadIdx.x;
+    const int f = (blockIdx.x * 256 + threadIdx.x) * 2;
     if (f >= sd.out_frames) return;
     const int64_t gi = sd.out_off + f;
-    int acc[CH];
-#pragma unroll
-    for (int k = 0; k < CH; ++k) acc[k] = 0;
-    for (int b = 0; b < nbands; ++b) {
-        const int band = band_base + b;
-        const double a = bp.att[band][gi];
-        int v[CH];
-        if (CH == 2) {
-            const short2 q = *reinterpret_cast<const short2 *>(bp.band[band] + gi * 2);
-            v[0] = q.x; v[CH - 1] = q.y;
-        } else {
-            v[0] = bp.band[band][gi];
+    const bool two = f + 1 < sd.out_frames && (gi & 1) == 0;     // aligned pair
+    int a0 = 0, a1 = 0, b0 = 0, b1 = 0;                          // frame f (L, R), frame f + 1 (L, R)
+    if (two) {
+        for (int b = 0; b < nbands; ++b) {
+            const int band = band_base + b;
+            const double2 at = *reinterpret_cast<const double2 *>(bp.att[band] + gi);
+            unsigned s0, s1;
+            if (CH == 2) {
+                const uint2 q = *reinterpret_cast<const uint2 *>(bp.band[band] + gi * 2);
+                s0 = q.x; s1 = q.y;
+            } else {
+                const unsigned q = *reinterpret_cast<const unsigned *>(bp.band[band] + gi);
+                s0 = q & 0xffffu; s1 = q >> 16;
+            }
+            apply_frame<CH>(a0, a1, s0, at.x, b == 0);
+            apply_frame<CH>(b0, b1, s1, at.y, b == 0);
         }
-        if (a != 0.0) {                             // pydub: `if attenuation != 0.0`
-            const double g = exp10(a * -0.05);      // db_to_float(-att) = 10 ** (-att / 20)
-#pragma unroll
-            for (int k = 0; k < CH; ++k) v[k] = mul_floor16(v[k], g);
+        if (CH == 2)
+            *reinterpret_cast<uint2 *>(proc + gi * 2) = make_uint2((unsigned)(a0 & 0xffff) | ((unsigned)a1 << 16),
+                                                                   (unsigned)(b0 & 0xffff) | ((unsigned)b1 << 16));
+        else
+            *reinterpret_cast<unsigned *>(proc + gi) = (unsigned)(a0 & 0xffff) | ((unsigned)b0 << 16);
+    } else {
+        for (int k = 0; k < 2 && f + k < sd.out_frames; ++k) {
+            for (int b = 0; b < nbands; ++b) {
+                const int band = band_base + b;
+                const double at = bp.att[band][gi + k];
+                unsigned s0;
+                if (CH == 2) s0 = *reinterpret_cast<const unsigned *>(bp.band[band] + (gi + k) * 2);
+                else s0 = (unsigned)(unsigned short)bp.band[band][gi + k];
+                apply_frame<CH>(a0, a1, s0, at, b == 0);
+            }
+            if (CH == 2) *reinterpret_cast<unsigned *>(proc + (gi + k) * 2) = (unsigned)(a0 & 0xffff) | ((unsigned)a1 << 16);
+            else proc[gi + k] = (int16_t)a0;
         }
-#pragma unroll
-        for (int k = 0; k < CH; ++k) acc[k] = b == 0 ? v[k] : max(-32768, min(32767, acc[k] + v[k]));
     }
-    if (CH == 2)
-        *reinterpret_cast<short2 *>(proc + gi * 2) = make_short2((short)acc[0], (short)acc[CH - 1]);
-    else
-        proc[gi] = (int16_t)acc[0];
 }
 
 // =====================================================================================

@@ -269,7 +269,7 @@ def test_time_segmentation_is_invisible(eng):
 
 def test_host_pipeline_is_invisible(eng):
     """Host-buffer batches are cut into groups whose copies overlap the kernels of their neighbours
-    (two workspace slots, three streams): same bytes as the sequential path, in the right places."""
+    (three workspace slots, three streams): same bytes as the sequential path, in the right places."""
     from b200master import synth
     rate = 48000
     tracks = [synth.make_track(80 + i, 181.0 + 7.3 * (i % 3), rate) for i in range(5)]      # ~43 M frames: several groups
