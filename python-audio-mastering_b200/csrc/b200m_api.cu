@@ -531,7 +531,10 @@ static int ensure_plans(b200m_handle *h, const b200m_plan *plans, int n)
                 std::vector<double> tab;
                 int rc = get_curve(h, bb, &d.curve[b], &tab);
                 if (rc) return rc;
-                const bool trick = div_trick_exact(tab, bb.attack_frames) && div_trick_exact(tab, bb.release_frames);
+                bool trick = div_trick_exact(tab, bb.attack_frames) && div_trick_exact(tab, bb.release_frames);
+                // the fast path of the recurrence also assumes finite values >= +0 and positive attack / release
+                for (double m : tab) if (!(m >= 0.0) || !std::isfinite(m) || std::signbit(m)) { trick = false; break; }
+                if (!(bb.attack_frames > 0) || !(bb.release_frames > 0)) trick = false;
                 // curve[r] == 0 for r <= hold_max and != 0 above it (the curve is monotone); if that
                 // does not hold for some odd parameter set, nothing is ever flagged "held"
                 int hold_max = -1;

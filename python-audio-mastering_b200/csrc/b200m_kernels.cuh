@@ -468,6 +468,21 @@ __device__ __forceinline__ double recur_step(double a, double M, double inc, dou
     return p ? vu : vd;
 }
 
+// The same step for curves whose values are all finite and >= +0 (checked at plan time; true for
+// every ratio >= 1): "M != 0" is implied -- with M == 0 the attack branch gives min(a + 0, 0) = 0
+// only when a == 0, which is what the release branch gives too -- and max(a - dec, 0) is a sign
+// test on the difference.  Six integer compares become three and a half.
+__device__ __forceinline__ double recur_step_pos(double a, double M, double inc, double dec)
+{
+    const long long ab = __double_as_longlong(a), Mb = __double_as_longlong(M);
+    const bool p = ab <= Mb;
+    const double u = __dadd_rn(a, inc), d = __dsub_rn(a, dec);
+    const bool q1 = __double_as_longlong(u) >= Mb;
+    const bool q2 = __double2hiint(d) < 0;                   // a - dec < 0 (a - dec == -0 cannot occur: a, dec >= +0 and RN)
+    const double vu = q1 ? M : u, vd = q2 ? 0.0 : d;
+    return p ? vu : vd;
+}
+
 // audioop.mul: floor(fbound(sample * factor)), fbound clipping to [-32768, 32767] ("val < minval + 1
 // -> minval").  Clipping the floored integer instead is the same function: for val in
 // (-32768, -32767) both give -32768, above 32767 both give 32767; F2I.FLOOR saturates.
@@ -637,7 +652,7 @@ k_recur_tiles(const StreamDesc *__restrict__ streams, const PlanDev *__restrict_
                 for (int k = 0; k < 32; ++k) {
                     const double M = W.m[lane][k];
                     const double inc = div_const(M, A, rA, true), dec = div_const(M, R, rR, true);
-                    a = recur_step(a, M, inc, dec);
+                    a = recur_step_pos(a, M, inc, dec);
                     W.m[lane][k] = a;
                 }
             }
