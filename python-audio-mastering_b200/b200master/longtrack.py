@@ -118,9 +118,12 @@ class DistComm:
         self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
 
     def exchange(self, sends, recvs):
-        """sends / recvs: lists of (peer_rank, tensor); tensors are contiguous."""
-        ops = [self.dist.P2POp(self.dist.isend, t, p, self.group) for p, t in sends if t.numel()]
-        ops += [self.dist.P2POp(self.dist.irecv, t, p, self.group) for p, t in recvs if t.numel()]
+        """sends / recvs: lists of (peer_rank, tensor); tensors are contiguous.  They travel as bytes
+        (NCCL has no int16 type)."""
+        def raw(t):
+            return t.view(torch.uint8) if t.dtype == torch.int16 else t
+        ops = [self.dist.P2POp(self.dist.isend, raw(t), p, self.group) for p, t in sends if t.numel()]
+        ops += [self.dist.P2POp(self.dist.irecv, raw(t), p, self.group) for p, t in recvs if t.numel()]
         if ops:
             for req in self.dist.batch_isend_irecv(ops):
                 req.wait()

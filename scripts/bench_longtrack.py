@@ -64,6 +64,7 @@ def main():
     torch.cuda.set_device(local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")     # keep NCCL's banner off stdout: rank 0 prints ONE JSON line there
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
         comm = longtrack.DistComm()
     else:
