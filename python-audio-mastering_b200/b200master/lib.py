@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(os.path.dirname(HERE), "lib", "libb200master.so")
+LIB_PATH = os.environ.get("B200M_LIB") or os.path.join(os.path.dirname(HERE), "lib", "libb200master.so")     # B200M_LIB: build experiments
 
 OK, ERR_INVALID, ERR_CUDA, ERR_TOO_SHORT, ERR_NOMEM = 0, 1, 2, 3, 4
 FMT_S16, FMT_S24, FMT_F32 = 0, 1, 2

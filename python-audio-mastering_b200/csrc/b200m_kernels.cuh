@@ -62,8 +62,11 @@ __device__ __forceinline__ void store_q16_tile(int16_t *__restrict__ dst, const 
     }
 }
 
+#ifndef B200M_CHAIN_OCC
+#define B200M_CHAIN_OCC 2
+#endif
 template <int CH>
-__global__ void __launch_bounds__(NSEG * CH, (CH == 2 ? 2 : 4))
+__global__ void __launch_bounds__(NSEG * CH, (CH == 2 ? B200M_CHAIN_OCC : 2 * B200M_CHAIN_OCC))
 k_chain(const int16_t *__restrict__ pcm_in, const StreamDesc *__restrict__ streams, const SegDesc *__restrict__ segs,
         const PlanDev *__restrict__ plans, int16_t *__restrict__ proc, BandPtrs bp)
 {
@@ -811,8 +814,11 @@ constexpr int KNT = 256;
 constexpr int KTILE = SEG * KNT;               // 4096
 constexpr int KTILE_PAD = KTILE + KNT;
 
+#ifndef B200M_KW_OCC
+#define B200M_KW_OCC 4
+#endif
 template <int CH, typename IN>
-__global__ void __launch_bounds__(KNT, 2)
+__global__ void __launch_bounds__(KNT, B200M_KW_OCC)
 k_kweight(const IN *__restrict__ src_all, const TrackDesc *__restrict__ tracks, const SegDesc *__restrict__ segs,
           const PlanDev *__restrict__ plans, float *__restrict__ kw)
 {
