@@ -813,7 +813,7 @@ static int launch_compressor(b200m_handle *h, const Group &g, const BandPtrs &bp
             cur ^= 1;
         }
     }
-    LAUNCH("k_recur_fix", k_recur_fix<<<(chains + 31) / 32, 32, 0, h->stream>>>(g.d_streams, h->d_plans, P, bp, ss[cur], se[cur], h->d_counters));
+    LAUNCH("k_recur_fix", k_recur_fix<<<(chains + 3) / 4, 128, 0, h->stream>>>(g.d_streams, h->d_plans, P, bp, ss[cur], se[cur], h->d_counters));
     const dim3 ga((g.max_stream_frames + 511) / 512, g.n_streams);
     if (g.ch == 2) LAUNCH("k_apply", k_apply<2><<<ga, 256, 0, h->stream>>>(g.d_streams, h->d_plans, bp, nbands, band_base, d_proc));
     else           LAUNCH("k_apply", k_apply<1><<<ga, 256, 0, h->stream>>>(g.d_streams, h->d_plans, bp, nbands, band_base, d_proc));

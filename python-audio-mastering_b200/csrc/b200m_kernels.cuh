@@ -696,25 +696,31 @@ k_recur_tiles(const StreamDesc *__restrict__ streams, const PlanDev *__restrict_
 
 // counters[0] = tiles repaired sequentially, counters[1] = frames re-run sequentially,
 // counters[2] = tiles repaired in the parallel rounds
-__global__ void __launch_bounds__(32)
+__global__ void __launch_bounds__(128)
 k_recur_fix(const StreamDesc *__restrict__ streams, const PlanDev *__restrict__ plans, RecurParams P,
             BandPtrs bp, const double *__restrict__ spec_start, const double *__restrict__ spec_end,
             unsigned long long *__restrict__ counters)
 {
-    const int chain = blockIdx.x * 32 + threadIdx.x;
+    // one warp per chain: all lanes check the tile joints in parallel (assumed start == predecessor's
+    // end, bit for bit); only a chain with a broken joint is walked, by lane 0, in order
+    const int chain = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (chain >= P.n_streams * P.nbands) return;
     const int s = chain / P.nbands, band = P.band_base + chain % P.nbands;
     const StreamDesc sd = streams[s];
     const PlanDev *__restrict__ pl = plans + sd.plan;
     if (!pl->multiband || sd.out_frames <= 0) return;
+    const int ntiles = (sd.out_frames + P.tile_len - 1) / P.tile_len;
+    const double *ss = spec_start + (size_t)chain * P.tiles, *se = spec_end + (size_t)chain * P.tiles;
+    bool broken = false;
+    for (int t = 1 + lane; t < ntiles; t += 32)
+        broken |= __double_as_longlong(ss[t]) != __double_as_longlong(se[t - 1]);
+    if (!__any_sync(FULL, broken) || lane != 0) return;
     const uint16_t *__restrict__ rms = bp.rms[band] + sd.out_off;
     double *__restrict__ out = bp.att[band] + sd.out_off;
     const double *__restrict__ curve = pl->curve[band];
     const BandDev &bd = pl->band[band];
     const double A = bd.attack_frames, R = bd.release_frames, rA = bd.r_attack, rR = bd.r_release;
     const bool exact = bd.div_trick != 0;
-    const int ntiles = (sd.out_frames + P.tile_len - 1) / P.tile_len;
-    const double *ss = spec_start + (size_t)chain * P.tiles, *se = spec_end + (size_t)chain * P.tiles;
     double truth = se[0];                        // tile 0 starts from att = 0 exactly
     for (int t = 1; t < ntiles; ++t) {
         if (__double_as_longlong(ss[t]) == __double_as_longlong(truth)) { truth = se[t]; continue; }
