@@ -122,6 +122,33 @@ def test_time_split_on_gpu_matches_one_gpu(rate, seconds, world):
 
 
 @pytest.mark.gpu
+def test_time_split_s24_input_on_gpu():
+    """cfg4's input format: packed 24-bit PCM is staged to the 16-bit domain per slice (declared
+    extension) and the split result equals the one-GPU result on the staged track."""
+    from b200master import Engine, get_engine
+    rate, seconds, world = 96000, 64.0, 2
+    pcm16 = synth.make_track(22, seconds, rate)
+    low = ((np.arange(pcm16.size, dtype=np.int64) * 37 + 11) & 0xff).astype(np.uint8).reshape(pcm16.shape)
+    raw = np.stack([low, (pcm16.view(np.uint16) & 0xff).astype(np.uint8), (pcm16.view(np.uint16) >> 8).astype(np.uint8)], axis=-1)   # (N, 2, 3) little endian
+    whole, winfo = get_engine(0).master([pcm16], rate, SETTINGS)
+    engines = [Engine(0) for _ in range(world)]
+
+    def fn(rank, comm):
+        me = longtrack.partition(pcm16.shape[0], rate, world)[rank]
+        local = torch.from_numpy(raw[me.abs_offset:me.abs_offset + me.in_frames].reshape(-1).copy()).cuda()
+        ops = longtrack.EngineOps(engines[rank], rate, 2, SETTINGS)
+        out, info = longtrack.master_time_split(local, pcm16.shape[0], rate, ops, comm, rank, world, fmt=1)
+        torch.cuda.synchronize()
+        return out.cpu().numpy(), info
+
+    res = longtrack.run_threaded(world, fn)
+    assert np.array_equal(np.concatenate([r[0] for r in res]), whole[0])
+    assert all(r[1]["loudness"] == winfo[0]["loudness"] for r in res)
+    for e in engines:
+        e.close()
+
+
+@pytest.mark.gpu
 def test_stage_pcm_formats():
     """Declared extension: packed s24 keeps the high-order 16 bits (pydub set_sample_width(2) =
     audioop.lin2lin), float32 goes through the reference's quantiser (ENG:123-126)."""
