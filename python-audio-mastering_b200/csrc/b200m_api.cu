@@ -593,8 +593,10 @@ extern "C" int b200m_create(int device, b200m_handle **out)
     if (e != cudaSuccess) return fail(nullptr, B200M_ERR_CUDA, "cudaSetDevice(%d): %s", device, cudaGetErrorString(e));
     h = new b200m_handle();
     h->device = device;
-    e = allow_smem(k_chain<1>, chain_smem_bytes<1>());
-    if (e == cudaSuccess) e = allow_smem(k_chain<2>, chain_smem_bytes<2>());
+    e = allow_smem(k_chain<1, true>, chain_smem_bytes<1>());
+    if (e == cudaSuccess) e = allow_smem(k_chain<2, true>, chain_smem_bytes<2>());
+    if (e == cudaSuccess) e = allow_smem(k_chain<1, false>, chain_smem_bytes<1>());
+    if (e == cudaSuccess) e = allow_smem(k_chain<2, false>, chain_smem_bytes<2>());
     if (e == cudaSuccess) e = allow_smem(k_detect<1>, detect_smem_bytes(8192));
     if (e == cudaSuccess) e = allow_smem(k_detect<2>, detect_smem_bytes(8192));
     if (e == cudaSuccess) e = allow_smem(k_recur_tiles, recur_smem_bytes());
@@ -741,6 +743,7 @@ struct Group {
     int max_look = 0;
     int64_t total_blocks = 0;        // hold-flag WORDS: sum over streams of ceil(out_frames / 1024)
     bool any_multiband = false, any_lufs = false;
+    bool chain_stable = true;        // every EQ / crossover section of every plan has its poles inside the unit circle
     const StreamDesc *d_streams = nullptr;
     const TrackDesc *d_tracks = nullptr;
     const SegDesc *d_csegs = nullptr, *d_ksegs = nullptr;   // k_chain / k_kweight segments
@@ -888,6 +891,7 @@ static void plan_group(const b200m_handle *h, GroupPlan &gp, bool in_dev, bool o
         g.max_track_frames = std::max(g.max_track_frames, td.frames);
         g.any_multiband |= p.multiband != 0;
         g.any_lufs |= p.has_lufs != 0;
+        if (!(chain_warm_frames(p) < 1e29)) g.chain_stable = false;
         if (p.multiband) for (int b = 0; b < 3; ++b) g.max_look = std::max(g.max_look, p.band[b].look_frames);
         const int64_t in_base = in_dev ? in_offsets[t] : in_total;
         for (int64_t s = 0; s < out_frames[t]; s += chunk) {
@@ -1004,8 +1008,13 @@ static int exec_group(b200m_handle *h, GroupPlan &gp, char *ws, char *pin, const
     int16_t *d_dst = out_dev ? pcm_out + gp.out_base * ch : d_out;
 
     // ---- kernels (all on the handle's stream) ------------------------------------------------
-    if (ch == 2) LAUNCH("k_chain", k_chain<2><<<g.n_csegs, NSEG * 2, chain_smem_bytes<2>(), h->stream>>>(d_src, d_streams, d_csegs, h->d_plans, d_proc, bp));
-    else         LAUNCH("k_chain", k_chain<1><<<g.n_csegs, NSEG * 1, chain_smem_bytes<1>(), h->stream>>>(d_src, d_streams, d_csegs, h->d_plans, d_proc, bp));
+    if (ch == 2) {
+        if (g.chain_stable) LAUNCH("k_chain", k_chain<2, false><<<g.n_csegs, NSEG * 2, chain_smem_bytes<2>(), h->stream>>>(d_src, d_streams, d_csegs, h->d_plans, d_proc, bp));
+        else                LAUNCH("k_chain", k_chain<2, true><<<g.n_csegs, NSEG * 2, chain_smem_bytes<2>(), h->stream>>>(d_src, d_streams, d_csegs, h->d_plans, d_proc, bp));
+    } else {
+        if (g.chain_stable) LAUNCH("k_chain", k_chain<1, false><<<g.n_csegs, NSEG * 1, chain_smem_bytes<1>(), h->stream>>>(d_src, d_streams, d_csegs, h->d_plans, d_proc, bp));
+        else                LAUNCH("k_chain", k_chain<1, true><<<g.n_csegs, NSEG * 1, chain_smem_bytes<1>(), h->stream>>>(d_src, d_streams, d_csegs, h->d_plans, d_proc, bp));
+    }
     CK(cudaGetLastError());
     int rc;
     if (g.any_multiband) { rc = launch_compressor(h, g, bp, 3, 0, d_proc, d_spec); if (rc) return rc; }
@@ -1483,8 +1492,8 @@ extern "C" int b200m_multiband(b200m_handle *h, const b200m_plan *plan, const in
     SegDesc sg = {0, (int64_t)nframes, 0, 0};
     CK(cudaMemcpyAsync(d_csegs, &sg, sizeof sg, cudaMemcpyHostToDevice, h->stream));
     g.d_streams = d_streams;
-    if (ch == 2) LAUNCH("k_chain", k_chain<2><<<1, NSEG * 2, chain_smem_bytes<2>(), h->stream>>>(d_in, d_streams, d_csegs, h->d_plans, d_proc, bp));
-    else         LAUNCH("k_chain", k_chain<1><<<1, NSEG * 1, chain_smem_bytes<1>(), h->stream>>>(d_in, d_streams, d_csegs, h->d_plans, d_proc, bp));
+    if (ch == 2) LAUNCH("k_chain", k_chain<2, true><<<1, NSEG * 2, chain_smem_bytes<2>(), h->stream>>>(d_in, d_streams, d_csegs, h->d_plans, d_proc, bp));
+    else         LAUNCH("k_chain", k_chain<1, true><<<1, NSEG * 1, chain_smem_bytes<1>(), h->stream>>>(d_in, d_streams, d_csegs, h->d_plans, d_proc, bp));
     CK(cudaGetLastError());
     rc = launch_compressor(h, g, bp, 3, 0, d_proc, d_spec);
     if (rc) return rc;

@@ -161,12 +161,14 @@ __device__ __forceinline__ void section_round(double (&x)[SEG], const SecTab *__
 // the clip is done on the integer (ALU pipe, not the fp64 pipe).  NaN must cast to 0 (x86
 // cvttsd2si gives 0x80000000, whose low 16 bits are 0); F2I.F64 has no NaN-to-zero mode, so NaN is
 // detected on the bit pattern.
+template <bool NANCHK = true>
 __device__ __forceinline__ int quant16(double y)
 {
     const int raw = __double2int_rz(y * 32768.0);
     int iv = max(-32768, min(32768, raw));
-    // F2I yields INT_MIN for NaN (and for y <= -65536): only then look at the bit pattern
-    if (raw == (int)0x80000000 && ((unsigned long long)__double_as_longlong(y) << 1) > 0xffe0000000000000ull) iv = 0;
+    // F2I yields INT_MIN for NaN.  Where NaN cannot occur (k_chain with stable filters: finite input
+    // stays finite) the test is compiled out.
+    if (NANCHK && ((unsigned long long)__double_as_longlong(y) << 1) > 0xffe0000000000000ull) iv = 0;
     return (int)(short)iv;
 }
 
