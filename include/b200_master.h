@@ -134,6 +134,11 @@ int b200m_set_segment_tiles(b200m_handle *h, int chain_tiles, int kweight_tiles)
  * kernels of group g run (three workspace slots).  on = 0 runs copy -> kernels -> copy in sequence.
  * Default on.  Results do not depend on it. */
 int b200m_set_pipeline(b200m_handle *h, int on);
+/* Shape of that pipeline: the batch is cut into about `groups` groups of whole tracks (0 = default 8)
+ * and their kernels run on `compute_streams` streams (1 or 2; 0 = default 1; with 2, neighbouring
+ * groups alternate, which measured slower on B200: 68.7 vs 65.0 ms per 64-track step).  Results do
+ * not depend on it. */
+int b200m_set_pipeline_shape(b200m_handle *h, int groups, int compute_streams);
 /* Verification counters since the last reset: tiles repaired by the sequential pass, frames it
  * re-ran, and tiles repaired in the parallel rounds. */
 int b200m_recur_stats(b200m_handle *h, int64_t *wrong_tiles, int64_t *rerun_frames, int64_t *round_repairs, int reset);

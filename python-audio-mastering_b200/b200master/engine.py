@@ -87,6 +87,9 @@ class Engine:
     def set_pipeline(self, on: bool = True):
         self._ck(self._lib.b200m_set_pipeline(self._h, int(on)))
 
+    def set_pipeline_shape(self, groups: int = 0, compute_streams: int = 0):
+        self._ck(self._lib.b200m_set_pipeline_shape(self._h, int(groups), int(compute_streams)))
+
     def recur_stats(self, reset: bool = False):
         a, b, c = C.c_int64(), C.c_int64(), C.c_int64()
         self._ck(self._lib.b200m_recur_stats(self._h, C.byref(a), C.byref(b), C.byref(c), int(reset)))

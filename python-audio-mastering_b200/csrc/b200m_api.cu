@@ -37,6 +37,7 @@ struct b200m_handle {
     std::map<std::tuple<double, double>, double *> curves;
     std::map<int, std::pair<int32_t *, int>> pw_trees;      // block length -> (device table, smem floats)
     int blocks_smem_floats = 0;                              // max over the current plans
+    int hops_smem_floats = 0;                                // the same for the hop trees (0: no plan shares hops)
     // pinned staging for descriptors / small results
     char *pin = nullptr;
     size_t pin_cap = 0;
@@ -54,7 +55,8 @@ struct b200m_handle {
     unsigned long long *d_counters = nullptr;
     // host-buffer pipeline: side streams for H2D / D2H and the events that order the groups
     bool pipeline = true;
-    cudaStream_t s_in = nullptr, s_out = nullptr;
+    int pipe_groups = 8, pipe_streams = 1;      // groups per batch; compute streams the groups alternate over
+    cudaStream_t s_in = nullptr, s_out = nullptr, s_comp2 = nullptr;
     std::vector<cudaEvent_t> sync_events;
 };
 
@@ -502,6 +504,7 @@ static int ensure_plans(b200m_handle *h, const b200m_plan *plans, int n)
     CK(cudaStreamSynchronize(h->stream));   // previous launches may still read d_plans
     h->plans_host.assign(n, PlanDev());
     h->blocks_smem_floats = 0;
+    h->hops_smem_floats = 0;
     for (int i = 0; i < n; ++i) {
         const b200m_plan &p = plans[i];
         PlanDev &d = h->plans_host[i];
@@ -521,6 +524,15 @@ static int ensure_plans(b200m_handle *h, const b200m_plan *plans, int n)
             int rc = get_pw_tree(h, (int)(int64_t)(0.4 * (0.0 * 0.25 + 1.0) * (double)p.sample_rate), &d.ptree, &fl);
             if (rc) return rc;
             h->blocks_smem_floats = std::max(h->blocks_smem_floats, fl);
+            // numpy's tree over n elements splits at n2 = n/2 - (n/2) % 8: when n is a multiple of 32 the
+            // first two levels cut at n/2 and n/4, i.e. a block is four hop trees (k_hops)
+            const int nblk = (int)(int64_t)(0.4 * (0.0 * 0.25 + 1.0) * (double)p.sample_rate);
+            if (d.ptree && nblk % 32 == 0 && nblk > 512) {
+                int hf = 0;
+                rc = get_pw_tree(h, nblk / 4, &d.htree, &hf);
+                if (rc) return rc;
+                if (d.htree) { d.hop = nblk / 4; h->hops_smem_floats = std::max(h->hops_smem_floats, hf); }
+            }
         }
         if (p.multiband) {
             for (int s = 0; s < 2; ++s) { build_sectab(p.lp[s], d.lp[s]); build_sectab(p.hp[s], d.hp[s]); }
@@ -610,8 +622,8 @@ extern "C" int b200m_create(int device, b200m_handle **out)
         delete h;
         return B200M_ERR_CUDA;
     }
-    if (cudaMalloc(&h->d_counters, 4 * sizeof(unsigned long long)) != cudaSuccess ||
-        cudaMemset(h->d_counters, 0, 4 * sizeof(unsigned long long)) != cudaSuccess) {
+    if (cudaMalloc(&h->d_counters, 16 * sizeof(unsigned long long)) != cudaSuccess ||
+        cudaMemset(h->d_counters, 0, 16 * sizeof(unsigned long long)) != cudaSuccess) {
         fail(nullptr, B200M_ERR_CUDA, "counter allocation failed");
         delete h;
         return B200M_ERR_CUDA;
@@ -636,6 +648,7 @@ extern "C" void b200m_destroy(b200m_handle *h)
     for (auto e : h->sync_events) cudaEventDestroy(e);
     if (h->s_in) cudaStreamDestroy(h->s_in);
     if (h->s_out) cudaStreamDestroy(h->s_out);
+    if (h->s_comp2) cudaStreamDestroy(h->s_comp2);
     delete h;
 }
 
@@ -709,6 +722,16 @@ extern "C" int b200m_set_pipeline(b200m_handle *h, int on)
     return B200M_OK;
 }
 
+extern "C" int b200m_set_pipeline_shape(b200m_handle *h, int groups, int compute_streams)
+{
+    if (!h) return B200M_ERR_INVALID;
+    if (groups < 0 || groups > 4096 || compute_streams < 0 || compute_streams > 2)
+        return fail(h, B200M_ERR_INVALID, "b200m_set_pipeline_shape: groups 0..4096, compute_streams 0..2");
+    h->pipe_groups = groups == 0 ? 8 : groups;
+    h->pipe_streams = compute_streams == 0 ? 1 : compute_streams;
+    return B200M_OK;
+}
+
 extern "C" int b200m_recur_stats(b200m_handle *h, int64_t *wrong_tiles, int64_t *rerun_frames, int64_t *round_repairs, int reset)
 {
     if (!h) return B200M_ERR_INVALID;
@@ -720,6 +743,17 @@ extern "C" int b200m_recur_stats(b200m_handle *h, int64_t *wrong_tiles, int64_t 
     if (rerun_frames) *rerun_frames = (int64_t)c[1];
     if (round_repairs) *round_repairs = (int64_t)c[2];
     if (reset) CK(cudaMemset(h->d_counters, 0, sizeof c));
+    return B200M_OK;
+}
+
+// build experiments (-DB200M_RECUR_TIMING): the raw counter block, counters[8 ..] = per-phase cycles
+extern "C" int b200m_debug_counters(b200m_handle *h, unsigned long long *out16, int reset)
+{
+    if (!h || !out16) return B200M_ERR_INVALID;
+    CK(cudaSetDevice(h->device));
+    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaMemcpy(out16, h->d_counters, 16 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    if (reset) CK(cudaMemset(h->d_counters, 0, 16 * sizeof(unsigned long long)));
     return B200M_OK;
 }
 
@@ -832,7 +866,11 @@ static int launch_loudness(b200m_handle *h, const Group &g, const int16_t *d_pro
         else if (g.ch == 2) LAUNCH("k_kweight", k_kweight<2, int16_t><<<g.n_ksegs, KNT, kweight_smem_bytes(), h->stream>>>(d_proc, g.d_tracks, g.d_ksegs, h->d_plans, d_kw));
         else                LAUNCH("k_kweight", k_kweight<1, int16_t><<<g.n_ksegs, KNT, kweight_smem_bytes(), h->stream>>>(d_proc, g.d_tracks, g.d_ksegs, h->d_plans, d_kw));
         const dim3 gb(g.max_blocks, g.n_tracks);
-        if (g.max_blocks > 0) LAUNCH("k_blocks", k_blocks<<<gb, BNT, (size_t)h->blocks_smem_floats * 4 + 16, h->stream>>>(d_kw, g.d_tracks, h->d_plans, d_z));
+        // hop sums go to d_zsel (k_gate's scratch, free until then): nblocks + 3 floats in nblocks doubles per track
+        const bool hops = h->hops_smem_floats > 0 && g.max_blocks >= 3;
+        const dim3 gh(g.max_blocks + 3, g.n_tracks);
+        if (hops) LAUNCH("k_hops", k_hops<<<gh, BNT, (size_t)h->hops_smem_floats * 4 + 16, h->stream>>>(d_kw, g.d_tracks, h->d_plans, d_zsel));
+        if (g.max_blocks > 0) LAUNCH("k_blocks", k_blocks<<<gb, BNT, (size_t)h->blocks_smem_floats * 4 + 16, h->stream>>>(d_kw, g.d_tracks, h->d_plans, hops ? d_zsel : nullptr, d_z));
     }
     LAUNCH("k_gate", k_gate<<<g.n_tracks, 32, 0, h->stream>>>(g.d_tracks, h->d_plans, d_z, d_zsel, d_loud));
     CK(cudaGetLastError());
@@ -1021,7 +1059,7 @@ static int exec_group(b200m_handle *h, GroupPlan &gp, char *ws, char *pin, const
     if (ext_proc) return B200M_OK;
     rc = launch_loudness(h, g, d_proc, nullptr, d_kw, d_z, d_zsel, d_loud);
     if (rc) return rc;
-    const dim3 gf((unsigned)std::min<int64_t>((g.max_track_frames + 255) / 256, 8192), g.n_tracks);
+    const dim3 gf((unsigned)std::min<int64_t>((g.max_track_frames + 1023) / 1024, 8192), g.n_tracks);   // four frames per thread
     if (ch == 2) LAUNCH("k_final", k_final<2><<<gf, 256, 0, h->stream>>>(d_proc, d_tracks, h->d_plans, d_loud, d_dst));
     else         LAUNCH("k_final", k_final<1><<<gf, 256, 0, h->stream>>>(d_proc, d_tracks, h->d_plans, d_loud, d_dst));
     CK(cudaGetLastError());
@@ -1079,7 +1117,7 @@ extern "C" int b200m_master_batch(b200m_handle *h, const void *pcm_in, int in_on
     // (and at least ~8 M frames) so that copies and kernels of neighbouring groups overlap
     const double per_frame = ch * 2 * 3 + 4 + 3 * (ch * 2 + 2 + 8) + 2;
     const double slot_limit = (double)h->ws_limit / slots;
-    const double pipe_frames = pipelined ? std::max<double>(8e6, (double)total_frames / 8.0) : 1e300;
+    const double pipe_frames = pipelined ? std::max<double>(8e6, (double)total_frames / (double)h->pipe_groups) : 1e300;
     std::vector<GroupPlan> gps;
     {
         int t0 = 0;
@@ -1109,6 +1147,7 @@ extern "C" int b200m_master_batch(b200m_handle *h, const void *pcm_in, int in_on
     if (pipelined && !h->s_in) {
         CK(cudaStreamCreateWithFlags(&h->s_in, cudaStreamNonBlocking));
         CK(cudaStreamCreateWithFlags(&h->s_out, cudaStreamNonBlocking));
+        CK(cudaStreamCreateWithFlags(&h->s_comp2, cudaStreamNonBlocking));
     }
     cudaEvent_t start_ev = nullptr;
     if (pipelined) {                            // the side streams start after whatever the caller queued on the handle's stream
@@ -1116,6 +1155,7 @@ extern "C" int b200m_master_batch(b200m_handle *h, const void *pcm_in, int in_on
         CK(cudaEventRecord(start_ev, h->stream));
         CK(cudaStreamWaitEvent(h->s_in, start_ev, 0));
         CK(cudaStreamWaitEvent(h->s_out, start_ev, 0));
+        CK(cudaStreamWaitEvent(h->s_comp2, start_ev, 0));
     }
     size_t pin_off = 0;
     std::vector<size_t> pin_offs(gps.size());
@@ -1123,6 +1163,11 @@ extern "C" int b200m_master_batch(b200m_handle *h, const void *pcm_in, int in_on
         GroupPlan &gp = gps[i];
         pin_offs[i] = pin_off;
         ExecStreams X;
+        // Neighbouring groups alternate between two compute streams: the latency-bound kernels of one
+        // group (k_recur_*, the tails of k_chain) share the SMs with the next group's throughput kernels,
+        // which a small group cannot fill on its own.  Every launch of exec_group goes to h->stream.
+        cudaStream_t const own = h->stream;
+        if (pipelined && h->pipe_streams > 1 && (i & 1)) h->stream = h->s_comp2;
         if (pipelined) {
             X.in = h->s_in; X.comp = h->stream; X.out = h->s_out;
             X.h2d_done = sync_event(h, 1 + 3 * i); X.comp_done = sync_event(h, 2 + 3 * i); X.d2h_done = sync_event(h, 3 + 3 * i);
@@ -1133,6 +1178,7 @@ extern "C" int b200m_master_batch(b200m_handle *h, const void *pcm_in, int in_on
         }
         rc = exec_group(h, gp, h->ws + (i % slots) * max_need, h->pin + pin_off, X, (const int16_t *)pcm_in, in_dev, in_offsets,
                         in_frames, (int16_t *)pcm_out, out_dev);
+        h->stream = own;
         if (rc) break;
         pin_off += gp.pin_bytes;
     }
@@ -1143,6 +1189,9 @@ extern "C" int b200m_master_batch(b200m_handle *h, const void *pcm_in, int in_on
         cudaEvent_t done_in = sync_event(h, 2 + 3 * gps.size());
         cudaEventRecord(done_in, h->s_in);
         cudaStreamWaitEvent(h->stream, done_in, 0);
+        cudaEvent_t done_c2 = sync_event(h, 3 + 3 * gps.size());
+        cudaEventRecord(done_c2, h->s_comp2);
+        cudaStreamWaitEvent(h->stream, done_c2, 0);
     }
     if (rc) { cudaStreamSynchronize(h->stream); return rc; }
     if (loudness_out || gain_out || !out_dev) {
@@ -1274,7 +1323,7 @@ extern "C" int b200m_slice_energies(b200m_handle *h, const int16_t *proc_ext_dev
         }
     }
     TrackDesc td = {0, 0, ext_frames, j0, (int32_t)(j1 - j0), 0, abs0, track_frames, (int32_t)j0, 0};
-    rc = ws_reserve(h, 65536 + (size_t)ext_frames * 4 + segs.size() * sizeof(SegDesc));
+    rc = ws_reserve(h, 65536 + (size_t)ext_frames * 4 + segs.size() * sizeof(SegDesc) + (size_t)(j1 + 4) * 8);
     if (rc) return rc;
     rc = pin_reserve(h, sizeof td + segs.size() * sizeof(SegDesc));
     if (rc) return rc;
@@ -1283,6 +1332,7 @@ extern "C" int b200m_slice_energies(b200m_handle *h, const int16_t *proc_ext_dev
     TrackDesc *d_tracks = A.take<TrackDesc>(1);
     SegDesc *d_segs = A.take<SegDesc>(segs.size());
     float *d_kw = A.take<float>(ext_frames);
+    double *d_hops = A.take<double>(j1 + 4);         // indexed like z_dev (td.zoff = j0): hop sums of blocks j0 .. j1 + 2
     std::memcpy(h->pin, &td, sizeof td);
     std::memcpy(h->pin + sizeof td, segs.data(), segs.size() * sizeof(SegDesc));
     CK(cudaMemcpyAsync(d_tracks, h->pin, sizeof td, cudaMemcpyHostToDevice, h->stream));
@@ -1292,7 +1342,9 @@ extern "C" int b200m_slice_energies(b200m_handle *h, const int16_t *proc_ext_dev
     if (ch == 2) LAUNCH("k_kweight", k_kweight<2, int16_t><<<g.n_ksegs, KNT, kweight_smem_bytes(), h->stream>>>(proc_ext_dev, d_tracks, d_segs, h->d_plans, d_kw));
     else         LAUNCH("k_kweight", k_kweight<1, int16_t><<<g.n_ksegs, KNT, kweight_smem_bytes(), h->stream>>>(proc_ext_dev, d_tracks, d_segs, h->d_plans, d_kw));
     const dim3 gb((unsigned)(j1 - j0), 1);
-    LAUNCH("k_blocks", k_blocks<<<gb, BNT, (size_t)h->blocks_smem_floats * 4 + 16, h->stream>>>(d_kw, d_tracks, h->d_plans, z_dev));
+    const bool hops = h->hops_smem_floats > 0 && j1 - j0 >= 3;
+    if (hops) LAUNCH("k_hops", k_hops<<<dim3((unsigned)(j1 - j0 + 3), 1), BNT, (size_t)h->hops_smem_floats * 4 + 16, h->stream>>>(d_kw, d_tracks, h->d_plans, d_hops));
+    LAUNCH("k_blocks", k_blocks<<<gb, BNT, (size_t)h->blocks_smem_floats * 4 + 16, h->stream>>>(d_kw, d_tracks, h->d_plans, hops ? d_hops : nullptr, z_dev));
     CK(cudaGetLastError());
     return B200M_OK;
 }
@@ -1349,7 +1401,7 @@ extern "C" int b200m_slice_final(b200m_handle *h, const int16_t *proc_dev, int64
     const double2 lg = make_double2(0.0, gain);
     CK(cudaMemcpyAsync(d_tracks, &td, sizeof td, cudaMemcpyHostToDevice, h->stream));
     CK(cudaMemcpyAsync(d_loud, &lg, sizeof lg, cudaMemcpyHostToDevice, h->stream));
-    const dim3 gf((unsigned)std::min<int64_t>((frames + 255) / 256, 8192 * 4), 1);
+    const dim3 gf((unsigned)std::min<int64_t>((frames + 1023) / 1024, 8192 * 4), 1);
     if (p.channels == 2) LAUNCH("k_final", k_final<2><<<gf, 256, 0, h->stream>>>(proc_dev, d_tracks, h->d_plans, d_loud, out_dev));
     else                 LAUNCH("k_final", k_final<1><<<gf, 256, 0, h->stream>>>(proc_dev, d_tracks, h->d_plans, d_loud, out_dev));
     CK(cudaGetLastError());

@@ -57,6 +57,8 @@ struct PlanDev {
     BandDev band[3];
     const double *curve[3];       // device pointers, CURVE_N doubles each (NULL if !multiband)
     const int32_t *ptree;         // numpy pairwise-sum tree of a full 400 ms block (k_blocks), or NULL
+    const int32_t *htree;         // the same for one 100 ms hop when the block tree is four hop trees (k_hops), or NULL
+    int32_t hop, pad2_;           // hop length in samples (0: no hop sharing at this rate)
     SecTab eq[4], lp[2], hp[2], kw[2];
 };
 

@@ -272,18 +272,32 @@ constexpr size_t chain_smem_bytes()
 constexpr int DT = 4096;        // frames per tile
 constexpr int DNT = 384;
 
+__device__ __forceinline__ unsigned window_rms_rn(unsigned long long S, unsigned n, float rn);
 __device__ __forceinline__ unsigned window_rms(unsigned long long S, unsigned n)
 {
     if (n == 0) return 0u;
     // largest r with r*r*n <= S  ==  (unsigned)sqrt((double)S / n): the quotient is a
     // multiple of 1/n, so it can never sit within double rounding of a perfect square
     // without being one.
-    float q;                                    // MUFU-grade estimate (off by at most one), corrected exactly below
-    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(q) : "f"(__fdividef((float)S, (float)n)));
-    unsigned r = (unsigned)q;
-    if (r > 32768u) r = 32768u;
-    while ((unsigned long long)r * r * n > S) --r;
-    while ((unsigned long long)(r + 1) * (r + 1) * n <= S) ++r;
+    // MUFU-grade estimate: (float)S, rcp.approx, the product and sqrt.approx carry at most
+    // 2^-24 + 2^-23 + 2^-24 + 2^-23 < 4e-7 of relative error between them (half of the first three
+    // survives the root), i.e. < 0.01 absolute at r <= 32768, so its floor is off by at most ONE.
+    // One exact, branch-free correction settles it: lo = r^2 n <= S < (r + 1)^2 n = lo + (2r + 1) n.
+    // (n <= 2 * 8192 frames of look-back: (2r + 1) n < 2^31; r^2 <= 2^30; S <= n 2^30 < 2^45.)
+    float rn;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rn) : "f"((float)n));
+    return window_rms_rn(S, n, rn);
+}
+
+// the same with rn = rcp.approx(n) supplied (n > 0): n is the same for every frame past the look-back
+__device__ __forceinline__ unsigned window_rms_rn(unsigned long long S, unsigned n, float rn)
+{
+    float q;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(q) : "f"(__fmul_rn((float)S, rn)));
+    unsigned r = min((unsigned)q, 32768u);
+    const unsigned long long lo = (unsigned long long)(r * r) * n;
+    const unsigned long long hi = lo + (unsigned long long)((2u * r + 1u) * n);
+    r += (unsigned)(S >= hi) - (unsigned)(S < lo);
     return r;
 }
 
@@ -387,21 +401,49 @@ k_detect(const StreamDesc *__restrict__ streams, const PlanDev *__restrict__ pla
     // The static curve is a pure function of the integer RMS (32769 values, tabulated at plan
     // time); it is applied inside the recurrence kernel.  Here: the RMS itself (2 bytes per frame)
     // and one flag per 32-frame block saying that rms <= threshold throughout (M == 0: state held).
+    // Four consecutive frames per thread: two 16-byte reads of the leading prefix sums, one 8-byte
+    // store of the four RMS values, and one ballot per 128 frames for the four hold bits.
     uint16_t *__restrict__ dst = bp.rms[band] + sd.out_off;
-    const unsigned hold_max = (unsigned)pl->band[band].hold_max;   // curve[r] == 0  <=>  r <= hold_max
+    const int hold_max = pl->band[band].hold_max;                  // curve[r] == 0  <=>  r <= hold_max
     const int nvalid = min(DT, sd.out_frames - t0);
-    for (int i = tid; i < ((nvalid + 31) & ~31); i += DNT) {      // whole warps: 32 consecutive frames each
-        const int f = t0 + i;
+    const bool al8 = ((reinterpret_cast<unsigned long long>(dst + t0)) & 7ull) == 0;
+    const unsigned nH = (unsigned)CH * (unsigned)H;
+    float rnH = 0.0f;
+    if (nH) asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rnH) : "f"((float)nH));
+    for (int i4 = tid * 4; i4 < ((nvalid + 127) & ~127); i4 += DNT * 4) {      // whole warps: 128 consecutive frames each
         bool act = false;
-        if (i < nvalid) {
-            const int hh = min(f, H);
-            const unsigned long long S = P[HP + i] - P[HP + i - hh];
-            const unsigned r = window_rms(S, (unsigned)CH * (unsigned)hh);
-            dst[f] = (uint16_t)r;
-            act = (int)r > (int)hold_max;
+        if (i4 < nvalid) {
+            const int f0 = t0 + i4;
+            const ulonglong2 p01 = *reinterpret_cast<const ulonglong2 *>(P + HP + i4);
+            const ulonglong2 p23 = *reinterpret_cast<const ulonglong2 *>(P + HP + i4 + 2);
+            const unsigned long long top[4] = {p01.x, p01.y, p23.x, p23.y};
+            unsigned r[4];
+            if (f0 >= H) {                          // the whole look-back lies inside the stream: n = CH * H for all four
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    r[k] = nH ? window_rms_rn(top[k] - P[HP + i4 + k - H], nH, rnH) : 0u;
+            } else {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const int hh = min(f0 + k, H);
+                    r[k] = window_rms(top[k] - P[HP + i4 + k - hh], (unsigned)CH * (unsigned)hh);
+                }
+            }
+            if (al8 && i4 + 3 < nvalid) {
+                *reinterpret_cast<uint2 *>(dst + f0) = make_uint2(r[0] | (r[1] << 16), r[2] | (r[3] << 16));
+                act = (int)max(max(r[0], r[1]), max(r[2], r[3])) > hold_max;
+            } else {
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    if (i4 + k < nvalid) { dst[f0 + k] = (uint16_t)r[k]; act |= (int)r[k] > hold_max; }
+            }
         }
-        const unsigned active = __ballot_sync(FULL, act);
-        if (lane == 0 && active != 0u) atomicAnd(&sbits[i >> 10], ~(1u << ((i >> 5) & 31)));
+        const unsigned active = __ballot_sync(FULL, act);          // lanes 8b .. 8b+7 hold block (i4 >> 5) + b
+        if (lane == 0 && active != 0u) {
+            const unsigned m4 = (active & 0xffu ? 1u : 0u) | (active & 0xff00u ? 2u : 0u) | (active & 0xff0000u ? 4u : 0u) |
+                                (active & 0xff000000u ? 8u : 0u);
+            atomicAnd(&sbits[i4 >> 10], ~(m4 << ((i4 >> 5) & 31)));
+        }
     }
     __syncthreads();
     if (tid < DT / 1024 && tid * 1024 < nvalid) bp.hold[band][sd.blk_off + (t0 >> 10) + tid] = sbits[tid];
@@ -438,13 +480,22 @@ k_detect(const StreamDesc *__restrict__ streams, const PlanDev *__restrict__ pla
 // (an fp64 exp10 per frame) is applied by k_apply at full occupancy.
 // =====================================================================================
 constexpr int RW = 4;               // warps per CTA in k_recur_tiles
+#ifndef B200M_RECUR_GB
+#define B200M_RECUR_GB 32           // rows of curve gathers in flight per batch (phase B): 32 beats 16 by 1.4 ms per 64-track step
+#endif
+// -DB200M_RECUR_TIMING: lane 0 of every warp adds the cycles it spent per phase to counters[8 ..]
+// (build experiment only; scripts/gpu_recur_phases.py)
+#ifdef B200M_RECUR_TIMING
+#define RT_MARK(slot) do { const long long t_ = clock64(); rt_acc[slot] += t_ - rt_t; rt_t = t_; } while (0)
+#else
+#define RT_MARK(slot) do { } while (0)
+#endif
 
 struct RecurWarpSmem {
     double m[32][33];               // M rows in (phase B), attenuation rows out (phase C -> D)
     uint16_t rms[32][32];           // RMS rows
-    unsigned long long base_rms[32], base_curve[32], base_att[32];
+    unsigned long long base_curve[32], base_att[32];
     int2 blk[32];                   // per lane: {first frame of its current block, frames to store (0 = warm-up)}
-    int2 nxt[32];                   // per lane: {first frame of its next block, frames to load (0 = held / none)}
 };
 constexpr size_t recur_smem_bytes() { return RW * sizeof(RecurWarpSmem); }
 
@@ -514,7 +565,8 @@ k_recur_tiles(const StreamDesc *__restrict__ streams, const PlanDev *__restrict_
     double A = 1.0, R = 1.0, rA = 1.0, rR = 1.0;
     bool exact = true;
     double a = 0.0;
-    W.base_rms[lane] = 0; W.base_curve[lane] = 0; W.base_att[lane] = 0;
+    W.base_curve[lane] = 0; W.base_att[lane] = 0;
+    const uint16_t *my_rms = nullptr;
     if (live) {
         const int s = chain / P.nbands, band = P.band_base + chain % P.nbands;
         const StreamDesc sd = streams[s];
@@ -525,7 +577,7 @@ k_recur_tiles(const StreamDesc *__restrict__ streams, const PlanDev *__restrict_
             end = min(start + P.tile_len, sd.out_frames);
             hold = bp.hold[band] + sd.blk_off;
             attp = bp.att[band] + sd.out_off;
-            W.base_rms[lane] = (unsigned long long)(bp.rms[band] + sd.out_off);
+            my_rms = bp.rms[band] + sd.out_off;
             W.base_curve[lane] = (unsigned long long)pl->curve[band];
             W.base_att[lane] = (unsigned long long)attp;
             const BandDev &bd = pl->band[band];
@@ -564,10 +616,13 @@ k_recur_tiles(const StreamDesc *__restrict__ streams, const PlanDev *__restrict_
     // warm-up are skipped outright (the state cannot change there), so the warp iterates
     // max-over-lanes of the blocks that need work, not the span.
     const int sb = start >> 5, eb = (end + 31) >> 5;
+    int hw_idx = -1;
+    unsigned hw_val = 0u;
+#define HOLD_WORD(w) (((w) != hw_idx) ? (hw_idx = (w), hw_val = hold[(w)]) : hw_val)   /* the hold word of blocks 32w .. 32w+31, kept while the cursor stays inside it */
     auto skip_held = [&](int cb) {               // first block >= cb that needs work (warm-up part only)
         if (live) {
             while (cb < sb) {
-                const unsigned wv = hold[cb >> 5] >> (cb & 31);
+                const unsigned wv = HOLD_WORD(cb >> 5) >> (cb & 31);
                 if (!(wv & 1u)) break;
                 const int run = (~wv) ? __ffs(~wv) - 1 : 32;     // run of held blocks (shifted-in zeros end it)
                 cb = min(cb + run, sb);
@@ -575,30 +630,35 @@ k_recur_tiles(const StreamDesc *__restrict__ streams, const PlanDev *__restrict_
         }
         return cb;
     };
-    // RMS rows of every lane's block `cbn` -> W.rms (zeros beyond its count and for held blocks:
-    // r = 0 gives M = 0, a hold, i.e. an identity step, so partial rows need no branches)
+    // The RMS rows of every lane's block `cbn` -> W.rms: 64 bytes per row, moved as 16-byte cp.async
+    // pieces, eight rows per instruction (lane l: row q0 + l / 4, piece l % 4, so every 32-byte sector is
+    // asked for once and the shared-memory side is one contiguous 512-byte span).  The source address
+    // of a row travels by shuffle from the lane that owns it.  Rows of held blocks, of lanes without
+    // work and the ragged last block of a stream are written by their owner: zeros (r = 0 gives
+    // M = 0, a hold, i.e. an identity step, so partial rows need no branches later) plus whatever
+    // valid elements there are.
+    const bool rms16 = (reinterpret_cast<unsigned long long>(my_rms) & 15ull) == 0;    // chunk starts at odd rates may not be
     auto issue_rms = [&](int cbn, bool valid) {
         const bool on_n = valid && cbn < eb;
         const int i0n = cbn << 5;
         const int cntn = on_n ? min(32, end - i0n) : 0;
-        const bool heldn = on_n && ((hold[cbn >> 5] >> (cbn & 31)) & 1u);
-        W.nxt[lane] = make_int2(i0n, heldn ? 0 : cntn);
+        const bool heldn = on_n && ((HOLD_WORD(cbn >> 5) >> (cbn & 31)) & 1u);
         const bool work_n = on_n && !heldn;      // this lane's block can change its state
-        __syncwarp();
-        // lane l moves frames 2l, 2l+1 of rows q = l / 16 + 2j (two rows per step)
-        const int half = lane >> 4, col = (lane & 15) * 2;
-#pragma unroll 4
-        for (int q0 = 0; q0 < 32; q0 += 2) {
-            const int q = q0 + half;
-            const int2 d = W.nxt[q];
-            uint16_t *dstp = &W.rms[q][col];
-            if (col + 1 < d.y) {
-                const unsigned sa = (unsigned)__cvta_generic_to_shared(dstp);
-                asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(sa), "l"(reinterpret_cast<const uint16_t *>(W.base_rms[q]) + d.x + col) : "memory");
-            } else {
-                uint16_t r0 = 0;
-                if (col < d.y) r0 = reinterpret_cast<const uint16_t *>(W.base_rms[q])[d.x + col];
-                *reinterpret_cast<unsigned *>(dstp) = (unsigned)r0;
+        const uint16_t *srcp = (work_n && cntn == 32 && rms16) ? my_rms + i0n : nullptr;
+        if (srcp == nullptr) {
+            uint16_t *row = &W.rms[lane][0];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) reinterpret_cast<uint4 *>(row)[j] = make_uint4(0u, 0u, 0u, 0u);
+            if (work_n)
+                for (int k = 0; k < cntn; ++k) row[k] = my_rms[i0n + k];
+        }
+        const int sub = lane >> 2, piece = lane & 3;
+#pragma unroll
+        for (int q0 = 0; q0 < 32; q0 += 8) {
+            const unsigned long long p = __shfl_sync(FULL, (unsigned long long)srcp, q0 + sub);
+            if (p != 0ull) {
+                const unsigned sa = (unsigned)__cvta_generic_to_shared(&W.rms[q0 + sub][piece * 8]);
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(p + 16ull * piece) : "memory");
             }
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
@@ -609,9 +669,17 @@ k_recur_tiles(const StreamDesc *__restrict__ streams, const PlanDev *__restrict_
     bool work = issue_rms(cb, live);
     double a_start = a;
     bool merged = false;
+#ifdef B200M_RECUR_TIMING
+    long long rt_acc[6] = {0, 0, 0, 0, 0, 0}, rt_t = clock64();
+    const long long rt_begin = rt_t;
+    long long rt_blocks = 0;
+#endif
     for (;;) {
         const bool on = live && !merged && cb < eb;
         if (!__any_sync(FULL, on)) break;
+#ifdef B200M_RECUR_TIMING
+        ++rt_blocks;
+#endif
         const int i0 = cb << 5;
         const int cnt = on ? min(32, end - i0) : 0;
         const bool is_main = on && cb >= sb;
@@ -623,28 +691,31 @@ k_recur_tiles(const StreamDesc *__restrict__ streams, const PlanDev *__restrict_
         const bool any_work = __any_sync(FULL, on && work);       // else every lane's block is held: att stays put
         asm volatile("cp.async.wait_group 0;" ::: "memory");
         __syncwarp();
+        RT_MARK(0);
         // ---- phase B: RMS rows -> M rows through the static curve (row-wise: consecutive frames
         //      have neighbouring RMS values, so a row's gathers touch a few cache lines) --------
-        // (16 rows per batch: all their gathers are in flight together)
+        // (B200M_RECUR_GB rows per batch: all their gathers are in flight together)
         if (any_work) {
 #pragma unroll
-        for (int q0 = 0; q0 < 32; q0 += 16) {
-            double v[16];
+        for (int q0 = 0; q0 < 32; q0 += B200M_RECUR_GB) {
+            double v[B200M_RECUR_GB];
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
+            for (int j = 0; j < B200M_RECUR_GB; ++j) {
                 const double *curve = reinterpret_cast<const double *>(W.base_curve[q0 + j]);
                 const unsigned r = W.rms[q0 + j][lane];
                 v[j] = (curve != nullptr && r != 0u) ? __ldg(curve + r) : 0.0;
             }
 #pragma unroll
-            for (int j = 0; j < 16; ++j) W.m[q0 + j][lane] = v[j];
+            for (int j = 0; j < B200M_RECUR_GB; ++j) W.m[q0 + j][lane] = v[j];
         }
         }
         __syncwarp();
+        RT_MARK(1);
         // ---- the RMS rows of the next block start moving now -----------------------------------
         const bool any_main = __any_sync(FULL, is_main);
         const int nb = on ? skip_held(cb + 1) : cb;
         work = issue_rms(nb, on);
+        RT_MARK(2);
         // ---- phase C: 32 dependent steps, one lane per tile --------------------------------------
         if (!any_work) {            // warp-uniform: nothing moves in this block
             if (on) {
@@ -670,6 +741,7 @@ k_recur_tiles(const StreamDesc *__restrict__ streams, const PlanDev *__restrict_
                 W.m[lane][k] = a;
             }
         }
+        RT_MARK(3);
         // ---- phase D: coalesced row stores of the attenuation (main part of the tile only) -------
         if (any_main) {
             __syncwarp();
@@ -682,8 +754,17 @@ k_recur_tiles(const StreamDesc *__restrict__ streams, const PlanDev *__restrict_
         if (P.mode == 1 && on && __double_as_longlong(a) == __double_as_longlong(old_last)) merged = true;
         cb = nb;
         __syncwarp();
+        RT_MARK(4);
     }
     asm volatile("cp.async.wait_group 0;" ::: "memory");
+#ifdef B200M_RECUR_TIMING
+    if (lane == 0 && P.mode == 0) {
+        for (int k = 0; k < 5; ++k) atomicAdd(&counters[8 + k], (unsigned long long)rt_acc[k]);
+        atomicAdd(&counters[13], (unsigned long long)(clock64() - rt_begin));
+        atomicAdd(&counters[14], (unsigned long long)rt_blocks);
+        atomicAdd(&counters[15], 1ull);
+    }
+#endif
     if (live) {
         const size_t slot = (size_t)chain * P.tiles + tile;
         if (P.mode == 0) {
@@ -750,12 +831,43 @@ k_recur_fix(const StreamDesc *__restrict__ streams, const PlanDev *__restrict__ 
 // exp10 chains in flight.  grid = (tiles of 512 frames, streams).  nbands == 1 backs the
 // single-band helper entry point.
 // =====================================================================================
+// 10^x for the gain of an attenuation: x = -att / 20 <= 0 and far from underflow (att is at most
+// slope * 20 log10(32768 / thresh_rms) dB; the caller falls back to the library routine beyond
+// 10^-300).  x log2(10) is split as n + f with the 1.5 * 2^52 trick, r = x - n log10(2) (two-piece
+// constant, |r| <= 0.1506), 10^r by its degree-13 Taylor polynomial (next term < 5e-18) in Horner
+// form with the coefficients as constant-bank operands (the library routine spends 28 uniform-
+// register moves per call on its immediates), and 2^n goes straight into the exponent field.
+// Max error measured against 60-digit arithmetic: 1.05 ulp, the class of the library's exp10
+// (1 ulp) -- both far inside what floor(sample * gain) can see.
+__constant__ double c_exp10[18] = {
+    0x1.0000000000000p+0, 0x1.26bb1bbb55516p+1, 0x1.53524c73cea69p+1, 0x1.0470591de2ca4p+1,
+    0x1.2bd7609fd98c4p+0, 0x1.1429ffd1d4d76p-1, 0x1.a7ed70847c8b6p-3, 0x1.16e4dfc333a87p-4,
+    0x1.4116b05fdaa5dp-6, 0x1.4897c45d93d42p-8, 0x1.2ea52b2d182afp-10, 0x1.facfd5d909d64p-13,
+    0x1.84fe12df80be4p-15, 0x1.1398ad2c41708p-17,
+    0x1.a934f0979a371p+1,       // [14] log2(10)
+    -0x1.34413509f79ffp-2,      // [15] -log10(2), high part
+    0x1.9dc1da994fd21p-59,      // [16] -log10(2), low part
+    6755399441055744.0};        // [17] 1.5 * 2^52
+__device__ __noinline__ double exp10_far(double x) { return exp10(x); }
+__device__ __forceinline__ double exp10_gain(double x)
+{
+    if (!(x > -300.0)) return exp10_far(x);
+    const double t = fma(x, c_exp10[14], c_exp10[17]);
+    const double nf = __dsub_rn(t, c_exp10[17]);
+    double r = fma(nf, c_exp10[15], x);
+    r = fma(nf, c_exp10[16], r);
+    double p = c_exp10[13];
+#pragma unroll
+    for (int k = 12; k >= 0; --k) p = fma(p, r, c_exp10[k]);
+    return __hiloint2double(__double2hiint(p) + (__double2loint(t) << 20), __double2loint(p));
+}
+
 template <int CH>
 __device__ __forceinline__ void apply_frame(int &acc0, int &acc1, unsigned smp, double a, bool first)
 {
     int v0 = (int)(short)(smp & 0xffffu), v1 = CH == 2 ? (int)smp >> 16 : 0;
     if (a != 0.0) {                                 // pydub: `if attenuation != 0.0`
-        const double g = exp10(a * -0.05);          // db_to_float(-att) = 10 ** (-att / 20)
+        const double g = exp10_gain(a * -0.05);     // db_to_float(-att) = 10 ** (-att / 20)
         v0 = mul_floor16(v0, g);
         if (CH == 2) v1 = mul_floor16(v1, g);
     }
@@ -968,31 +1080,10 @@ __device__ T np_pairwise_sum(Get get, int64_t n)
 // =====================================================================================
 constexpr int BNT = 256;
 
-__global__ void __launch_bounds__(BNT)
-k_blocks(const float *__restrict__ kw, const TrackDesc *__restrict__ tracks,
-         const PlanDev *__restrict__ plans, double *__restrict__ z)
+// Parallel evaluation of one tabulated pairwise tree over y[0 .. T[0]): returns the root (valid in
+// every thread).  bval: [nleaves + ninternal] floats of shared memory.  Ends with a barrier.
+__device__ __forceinline__ float pw_tree_eval(const float *__restrict__ y, const int32_t *__restrict__ T, float *bval, int tid)
 {
-    extern __shared__ float bval[];              // [nleaves + ninternal]
-    const TrackDesc td = tracks[blockIdx.y];
-    const PlanDev *__restrict__ pl = plans + td.plan;
-    const int jb = blockIdx.x, j = td.j0 + jb, tid = threadIdx.x;      // jb: slot in this buffer's z, j: block of the track
-    if (!pl->has_lufs || jb >= td.nblocks) return;
-    const double rate = (double)pl->rate, Tg = 0.4, step = 0.25;
-    int64_t l = (int64_t)__dmul_rn(__dmul_rn(Tg, __dmul_rn((double)j, step)), rate);
-    int64_t u = (int64_t)__dmul_rn(__dmul_rn(Tg, __dadd_rn(__dmul_rn((double)j, step), 1.0)), rate);
-    if (u > td.total_frames) u = td.total_frames;       // numpy slicing clamps
-    if (l > u) l = u;
-    const float *__restrict__ y = kw + td.off + (l - td.abs0);
-    const float scale = (float)(1.0 / (Tg * rate));
-    const int64_t n = u - l;
-    const int32_t *__restrict__ T = pl->ptree;
-    if (T == nullptr || (int64_t)T[0] != n) {
-        if (tid == 0) {
-            auto get = [y](int64_t i) { const float v = y[i]; return F32(__fmul_rn(v, v)); };
-            z[td.zoff + jb] = (double)__fmul_rn(scale, np_pairwise_sum<F32>(get, n).v);
-        }
-        return;
-    }
     const int nleaves = T[1], nint = T[2], nlev = T[3];
     const int32_t *lvl = T + 4, *loff = lvl + nlev + 1, *ln = loff + nleaves, *nl = ln + nleaves, *nr = nl + nint;
     const int sub = tid >> 3, k = tid & 7;
@@ -1022,7 +1113,66 @@ k_blocks(const float *__restrict__ kw, const TrackDesc *__restrict__ tracks,
         for (int i = lvl[lv] + tid; i < lvl[lv + 1]; i += BNT) bval[nleaves + i] = __fadd_rn(bval[nl[i]], bval[nr[i]]);
         __syncthreads();
     }
-    if (tid == 0) z[td.zoff + jb] = (double)__fmul_rn(scale, nint ? bval[nleaves + nint - 1] : bval[0]);
+    return nint ? bval[nleaves + nint - 1] : bval[0];
+}
+
+// k_hops: blocks overlap by 75 %, and at rates whose block length n is a multiple of 32 (48 kHz,
+// 96 kHz, ...) numpy's tree over a block splits exactly at n/2 and n/4: sum(block j) =
+// (h_j + h_{j+1}) + (h_{j+2} + h_{j+3}) with h the pairwise sum of one 100 ms hop.  The hop sums
+// are computed once (one CTA each) into `hops` (floats; slot = hop index - first block of the
+// buffer); k_blocks adds four of them whenever pyloudnorm's float bounds of the block are the
+// hop multiples (checked per block), and walks the block itself otherwise.
+__global__ void __launch_bounds__(BNT)
+k_hops(const float *__restrict__ kw, const TrackDesc *__restrict__ tracks, const PlanDev *__restrict__ plans,
+       double *__restrict__ hops)
+{
+    extern __shared__ float bval[];
+    const TrackDesc td = tracks[blockIdx.y];
+    const PlanDev *__restrict__ pl = plans + td.plan;
+    const int hs = blockIdx.x;
+    if (!pl->has_lufs || pl->hop <= 0 || td.nblocks < 3 || hs >= td.nblocks + 3) return;
+    const int64_t b = (int64_t)(td.j0 + hs) * pl->hop, e = b + pl->hop;
+    if (b < td.abs0 || e > td.total_frames || e - td.abs0 > td.frames) return;     // not (entirely) in this buffer: no block will ask for it
+    const float v = pw_tree_eval(kw + td.off + (b - td.abs0), pl->htree, bval, threadIdx.x);
+    if (threadIdx.x == 0) reinterpret_cast<float *>(hops + td.zoff)[hs] = v;
+}
+
+__global__ void __launch_bounds__(BNT)
+k_blocks(const float *__restrict__ kw, const TrackDesc *__restrict__ tracks,
+         const PlanDev *__restrict__ plans, const double *__restrict__ hops, double *__restrict__ z)
+{
+    extern __shared__ float bval[];              // [nleaves + ninternal]
+    const TrackDesc td = tracks[blockIdx.y];
+    const PlanDev *__restrict__ pl = plans + td.plan;
+    const int jb = blockIdx.x, j = td.j0 + jb, tid = threadIdx.x;      // jb: slot in this buffer's z, j: block of the track
+    if (!pl->has_lufs || jb >= td.nblocks) return;
+    const double rate = (double)pl->rate, Tg = 0.4, step = 0.25;
+    int64_t l = (int64_t)__dmul_rn(__dmul_rn(Tg, __dmul_rn((double)j, step)), rate);
+    int64_t u = (int64_t)__dmul_rn(__dmul_rn(Tg, __dadd_rn(__dmul_rn((double)j, step), 1.0)), rate);
+    const float scale = (float)(1.0 / (Tg * rate));
+    const int hop = pl->hop;
+    if (hops != nullptr && hop > 0 && td.nblocks >= 3 && l == (int64_t)j * hop && u == l + 4 * (int64_t)hop &&
+        u <= td.total_frames && l >= td.abs0 && u - td.abs0 <= td.frames) {
+        if (tid == 0) {
+            const float *H = reinterpret_cast<const float *>(hops + td.zoff) + jb;
+            z[td.zoff + jb] = (double)__fmul_rn(scale, __fadd_rn(__fadd_rn(H[0], H[1]), __fadd_rn(H[2], H[3])));
+        }
+        return;
+    }
+    if (u > td.total_frames) u = td.total_frames;       // numpy slicing clamps
+    if (l > u) l = u;
+    const float *__restrict__ y = kw + td.off + (l - td.abs0);
+    const int64_t n = u - l;
+    const int32_t *__restrict__ T = pl->ptree;
+    if (T == nullptr || (int64_t)T[0] != n) {
+        if (tid == 0) {
+            auto get = [y](int64_t i) { const float v = y[i]; return F32(__fmul_rn(v, v)); };
+            z[td.zoff + jb] = (double)__fmul_rn(scale, np_pairwise_sum<F32>(get, n).v);
+        }
+        return;
+    }
+    const float root = pw_tree_eval(y, T, bval, tid);
+    if (tid == 0) z[td.zoff + jb] = (double)__fmul_rn(scale, root);
 }
 
 // =====================================================================================
@@ -1117,6 +1267,25 @@ __device__ __forceinline__ float limiter32(float x, float thr)
     return x;
 }
 
+// One sample of ENG:82-89.  v = q / 2^15 is exact in float32 and scaling by a power of two commutes
+// with rounding, so fl(v * gain) * 2^15 == fl(q * gain): below the limiter threshold the whole
+// re-float / gain / quantise sequence is one multiply and one truncation, and the limiter test
+// |fl(v * gain)| > 0.98 is |fl(q * gain)| > 0.98 * 2^15 exactly.  Anything else (limited samples,
+// NaN from 0 * inf on silent input) takes the reference's formula step by step.
+__device__ __forceinline__ int final_sample(int q, bool has, double gain)
+{
+    if (has) {
+        const double p = __dmul_rn((double)q, gain);
+        if (fabs(p) <= 0.98 * 32768.0) return __double2int_rz(p);
+        const float v = (float)q * (1.0f / 32768.0f);
+        return quant16(limiter64(__dmul_rn((double)v, gain), 0.98));
+    }
+    // float32 limiter (no loudness target): |q / 2^15| > 0.98f  <=>  |q| >= 32113, and below it the
+    // quantiser returns q itself
+    if (abs(q) <= 32112) return q;
+    return quant16((double)limiter32((float)q * (1.0f / 32768.0f), 0.98f));
+}
+
 template <int CH>
 __global__ void __launch_bounds__(256)
 k_final(const int16_t *__restrict__ proc, const TrackDesc *__restrict__ tracks,
@@ -1129,24 +1298,25 @@ k_final(const int16_t *__restrict__ proc, const TrackDesc *__restrict__ tracks,
     const double gain = has ? loud[blockIdx.y].y : 1.0;
     const int16_t *__restrict__ src = proc + td.off * CH;
     int16_t *__restrict__ dst = out + td.dst_off * CH;
-    // one frame per thread: 4-byte (stereo) accesses, fully coalesced
-    for (int64_t f = (int64_t)blockIdx.x * 256 + threadIdx.x; f < td.frames; f += (int64_t)gridDim.x * 256) {
-        int q[CH], r[CH];
-        if (CH == 2) {
-            const short2 s = *reinterpret_cast<const short2 *>(src + f * 2);
-            q[0] = s.x; q[CH - 1] = s.y;
-        } else {
-            q[0] = src[f];
-        }
+    const int64_t nsamp = td.frames * CH;
+    // eight samples per thread and step (16-byte accesses) where both ends are aligned; workspace track
+    // starts always are, packed output starts are when the preceding tracks have multiples of 8 / CH frames
+    const bool vec = ((reinterpret_cast<unsigned long long>(src) | reinterpret_cast<unsigned long long>(dst)) & 15ull) == 0;
+    const int64_t nvec = vec ? nsamp / 8 : 0;
+    for (int64_t g = (int64_t)blockIdx.x * 256 + threadIdx.x; g < nvec; g += (int64_t)gridDim.x * 256) {
+        const uint4 w = __ldg(reinterpret_cast<const uint4 *>(src) + g);
+        const unsigned in[4] = {w.x, w.y, w.z, w.w};
+        unsigned o[4];
 #pragma unroll
-        for (int k = 0; k < CH; ++k) {
-            const float v = (float)q[k] * (1.0f / 32768.0f);
-            if (has) r[k] = quant16(limiter64(__dmul_rn((double)v, gain), 0.98));
-            else     r[k] = quant16((double)limiter32(v, 0.98f));
+        for (int k = 0; k < 4; ++k) {
+            const int r0 = final_sample((int)(short)(in[k] & 0xffffu), has, gain);
+            const int r1 = final_sample((int)in[k] >> 16, has, gain);
+            o[k] = (unsigned)(r0 & 0xffff) | ((unsigned)r1 << 16);
         }
-        if (CH == 2) *reinterpret_cast<short2 *>(dst + f * 2) = make_short2((short)r[0], (short)r[CH - 1]);
-        else dst[f] = (int16_t)r[0];
+        reinterpret_cast<uint4 *>(dst)[g] = make_uint4(o[0], o[1], o[2], o[3]);
     }
+    for (int64_t i = nvec * 8 + (int64_t)blockIdx.x * 256 + threadIdx.x; i < nsamp; i += (int64_t)gridDim.x * 256)
+        dst[i] = (int16_t)final_sample((int)src[i], has, gain);
 }
 
 // =====================================================================================
