@@ -87,6 +87,9 @@ class Engine:
     def set_pipeline(self, on: bool = True):
         self._ck(self._lib.b200m_set_pipeline(self._h, int(on)))
 
+    def set_chain_kernel(self, mode: int = 0):
+        self._ck(self._lib.b200m_set_chain_kernel(self._h, int(mode)))
+
     def set_pipeline_shape(self, groups: int = 0, compute_streams: int = 0):
         self._ck(self._lib.b200m_set_pipeline_shape(self._h, int(groups), int(compute_streams)))
 

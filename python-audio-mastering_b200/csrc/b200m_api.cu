@@ -7,6 +7,7 @@
 #include <complex>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <string>
@@ -52,6 +53,7 @@ struct b200m_handle {
     int recur_tile = 0, recur_warm = 8192, recur_rounds = 4;
     // time segmentation of k_chain / k_kweight: 0 = automatic, < 0 = off, > 0 = tiles per segment
     int seg_chain = 0, seg_kweight = 0;
+    int chain_kernel = 0;            // 0 = automatic, 1 = k_chain (a CTA per segment), 2 = k_chainw (a warp per segment)
     unsigned long long *d_counters = nullptr;
     // host-buffer pipeline: side streams for H2D / D2H and the events that order the groups
     bool pipeline = true;
@@ -350,6 +352,28 @@ static void make_segments(std::vector<SegDesc> &out, int owner, int64_t frames, 
     }
 }
 
+// Warp segments of k_chainw: the stream is cut into a multiple of CW_WARPS equal runs of about `seg_tiles`
+// warp tiles (never shorter than twice the warm-up), so that the eight warps of a CTA share one stream
+// (one plan, one set of tables) and carry the same load; what cannot be filled is padded with empty segments.
+static void make_segments_w(std::vector<SegDesc> &out, int owner, int64_t frames, int tile, double warm_frames, int seg_tiles)
+{
+    const size_t first = out.size();
+    if (frames > 0) {
+        const int64_t ntiles = (frames + tile - 1) / tile;
+        const int64_t warm_tiles = (int64_t)std::ceil(warm_frames / tile);
+        const int64_t min_seg = std::max<int64_t>(1, 2 * warm_tiles);
+        int64_t nseg = std::max<int64_t>(CW_WARPS, ((ntiles / std::max(1, seg_tiles) + CW_WARPS / 2) / CW_WARPS) * CW_WARPS);
+        while (nseg > CW_WARPS && (ntiles + nseg - 1) / nseg < min_seg) nseg -= CW_WARPS;
+        const int64_t seg = std::max(min_seg, (ntiles + nseg - 1) / nseg);
+        const int warm = (int)(warm_tiles * tile);
+        for (int64_t t = 0; t < ntiles; t += seg) {
+            const int64_t b = t * tile, e = std::min<int64_t>(frames, (t + seg) * tile);
+            out.push_back({b, e, owner, b == 0 ? 0 : warm});
+        }
+    }
+    while ((out.size() - first) % CW_WARPS != 0 || out.size() == first) out.push_back({0, 0, owner, 0});
+}
+
 static int auto_seg_tiles(int64_t total_tiles, int lo, int hi)
 {
     return (int)std::max<int64_t>(lo, std::min<int64_t>(hi, total_tiles / (148 * 6)));
@@ -605,10 +629,15 @@ extern "C" int b200m_create(int device, b200m_handle **out)
     if (e != cudaSuccess) return fail(nullptr, B200M_ERR_CUDA, "cudaSetDevice(%d): %s", device, cudaGetErrorString(e));
     h = new b200m_handle();
     h->device = device;
+    if (const char *ck = std::getenv("B200M_CHAIN_KERNEL")) h->chain_kernel = std::max(0, std::min(2, std::atoi(ck)));   // test / experiment override
     e = allow_smem(k_chain<1, true>, chain_smem_bytes<1>());
     if (e == cudaSuccess) e = allow_smem(k_chain<2, true>, chain_smem_bytes<2>());
     if (e == cudaSuccess) e = allow_smem(k_chain<1, false>, chain_smem_bytes<1>());
     if (e == cudaSuccess) e = allow_smem(k_chain<2, false>, chain_smem_bytes<2>());
+    if (e == cudaSuccess) e = allow_smem(k_chainw<1, true>, ChainW<1>::SMEM);
+    if (e == cudaSuccess) e = allow_smem(k_chainw<1, false>, ChainW<1>::SMEM);
+    if (e == cudaSuccess) e = allow_smem(k_chainw<2, true>, ChainW<2>::SMEM);
+    if (e == cudaSuccess) e = allow_smem(k_chainw<2, false>, ChainW<2>::SMEM);
     if (e == cudaSuccess) e = allow_smem(k_detect<1>, detect_smem_bytes(8192));
     if (e == cudaSuccess) e = allow_smem(k_detect<2>, detect_smem_bytes(8192));
     if (e == cudaSuccess) e = allow_smem(k_recur_tiles, recur_smem_bytes());
@@ -722,6 +751,13 @@ extern "C" int b200m_set_pipeline(b200m_handle *h, int on)
     return B200M_OK;
 }
 
+extern "C" int b200m_set_chain_kernel(b200m_handle *h, int mode)
+{
+    if (!h || mode < 0 || mode > 2) return B200M_ERR_INVALID;
+    h->chain_kernel = mode;
+    return B200M_OK;
+}
+
 extern "C" int b200m_set_pipeline_shape(b200m_handle *h, int groups, int compute_streams)
 {
     if (!h) return B200M_ERR_INVALID;
@@ -782,6 +818,7 @@ struct Group {
     const TrackDesc *d_tracks = nullptr;
     const SegDesc *d_csegs = nullptr, *d_ksegs = nullptr;   // k_chain / k_kweight segments
     int n_csegs = 0, n_ksegs = 0;
+    bool chain_warps = false;        // csegs are warp segments (k_chainw), padded to eight per CTA
 };
 
 static RecurParams recur_params(const b200m_handle *h, const Group &g, int nbands, int band_base)
@@ -852,8 +889,15 @@ static int launch_compressor(b200m_handle *h, const Group &g, const BandPtrs &bp
     }
     LAUNCH("k_recur_fix", k_recur_fix<<<(chains + 3) / 4, 128, 0, h->stream>>>(g.d_streams, h->d_plans, P, bp, ss[cur], se[cur], h->d_counters));
     const dim3 ga((g.max_stream_frames + 511) / 512, g.n_streams);
-    if (g.ch == 2) LAUNCH("k_apply", k_apply<2><<<ga, 256, 0, h->stream>>>(g.d_streams, h->d_plans, bp, nbands, band_base, d_proc));
-    else           LAUNCH("k_apply", k_apply<1><<<ga, 256, 0, h->stream>>>(g.d_streams, h->d_plans, bp, nbands, band_base, d_proc));
+    if (nbands == 3 && band_base == 0) {
+        if (g.ch == 2) LAUNCH("k_apply", k_apply<2, 3><<<ga, 256, 0, h->stream>>>(g.d_streams, h->d_plans, bp, 0, d_proc));
+        else           LAUNCH("k_apply", k_apply<1, 3><<<ga, 256, 0, h->stream>>>(g.d_streams, h->d_plans, bp, 0, d_proc));
+    } else if (nbands == 1) {
+        if (g.ch == 2) LAUNCH("k_apply", k_apply<2, 1><<<ga, 256, 0, h->stream>>>(g.d_streams, h->d_plans, bp, band_base, d_proc));
+        else           LAUNCH("k_apply", k_apply<1, 1><<<ga, 256, 0, h->stream>>>(g.d_streams, h->d_plans, bp, band_base, d_proc));
+    } else {
+        return fail(h, B200M_ERR_INVALID, "internal: compressor runs on one band or on all three");
+    }
     CK(cudaGetLastError());
     return B200M_OK;
 }
@@ -954,8 +998,32 @@ static void plan_group(const b200m_handle *h, GroupPlan &gp, bool in_dev, bool o
         for (auto &td : gp.tracks) ktiles += (td.frames + KTILE - 1) / KTILE;
         const int cs = h->seg_chain == 0 ? auto_seg_tiles(ctiles, 8, 48) : h->seg_chain;
         const int ks = h->seg_kweight == 0 ? auto_seg_tiles(ktiles, 8, 32) : h->seg_kweight;
-        for (size_t i = 0; i < gp.streams.size(); ++i)
-            make_segments(gp.csegs, (int)i, gp.streams[i].out_frames, TILE, chain_warm_frames(plans[gp.streams[i].plan]), cs);
+        // k_chainw needs eight times as many independent segments as k_chain.  It runs w = 4, 3, 2 or 1
+        // resident waves of warps (148 SMs x 16), the most for which a warp's run is still >= 4 warm-ups
+        // (warm-up share <= 20 %; measured on B200: 13.0 vs 13.9 ms on 64 tracks, 1.82 vs 1.98 ms on 8);
+        // smaller groups stay with k_chain, whose eight warps share one warm-up.
+        double max_warm = 0;
+        bool bounded = true;
+        for (auto &sd : gp.streams) {
+            const double w = chain_warm_frames(plans[sd.plan]);
+            if (!(w < 1e6)) bounded = false;
+            max_warm = std::max(max_warm, w);
+        }
+        const int wt = ch == 2 ? ChainW<2>::WT : ChainW<1>::WT;
+        const double frames_total = (double)ctiles * TILE;
+        double run = 0;
+        for (int w = 4; w >= 1 && run == 0; --w)
+            if (frames_total / (148.0 * 16 * w) >= 4.0 * std::max(max_warm, 256.0)) run = frames_total / (148.0 * 16 * w);
+        g.chain_warps = bounded && h->seg_chain >= 0 && (h->chain_kernel == 2 || (h->chain_kernel == 0 && run > 0));
+        if (run == 0) run = 4.0 * std::max(max_warm, 256.0);
+        if (g.chain_warps) {
+            const int wseg = (int)std::min<double>(1 << 20, std::max(8.0, std::ceil(run / wt)));
+            for (size_t i = 0; i < gp.streams.size(); ++i)
+                make_segments_w(gp.csegs, (int)i, gp.streams[i].out_frames, wt, chain_warm_frames(plans[gp.streams[i].plan]), h->seg_chain > 0 ? h->seg_chain * (TILE / wt) : wseg);
+        } else {
+            for (size_t i = 0; i < gp.streams.size(); ++i)
+                make_segments(gp.csegs, (int)i, gp.streams[i].out_frames, TILE, chain_warm_frames(plans[gp.streams[i].plan]), cs);
+        }
         for (size_t i = 0; i < gp.tracks.size(); ++i)
             if (plans[gp.tracks[i].plan].has_lufs)
                 make_segments(gp.ksegs, (int)i, gp.tracks[i].frames, KTILE, kweight_warm_frames(plans[gp.tracks[i].plan]), ks);
@@ -1046,7 +1114,16 @@ static int exec_group(b200m_handle *h, GroupPlan &gp, char *ws, char *pin, const
     int16_t *d_dst = out_dev ? pcm_out + gp.out_base * ch : d_out;
 
     // ---- kernels (all on the handle's stream) ------------------------------------------------
-    if (ch == 2) {
+    if (g.chain_warps) {
+        const int nb = g.n_csegs / CW_WARPS;
+        if (ch == 2) {
+            if (g.chain_stable) LAUNCH("k_chain", k_chainw<2, false><<<nb, 32 * CW_WARPS, ChainW<2>::SMEM, h->stream>>>(d_src, d_streams, d_csegs, g.n_csegs, h->d_plans, d_proc, bp));
+            else                LAUNCH("k_chain", k_chainw<2, true><<<nb, 32 * CW_WARPS, ChainW<2>::SMEM, h->stream>>>(d_src, d_streams, d_csegs, g.n_csegs, h->d_plans, d_proc, bp));
+        } else {
+            if (g.chain_stable) LAUNCH("k_chain", k_chainw<1, false><<<nb, 32 * CW_WARPS, ChainW<1>::SMEM, h->stream>>>(d_src, d_streams, d_csegs, g.n_csegs, h->d_plans, d_proc, bp));
+            else                LAUNCH("k_chain", k_chainw<1, true><<<nb, 32 * CW_WARPS, ChainW<1>::SMEM, h->stream>>>(d_src, d_streams, d_csegs, g.n_csegs, h->d_plans, d_proc, bp));
+        }
+    } else if (ch == 2) {
         if (g.chain_stable) LAUNCH("k_chain", k_chain<2, false><<<g.n_csegs, NSEG * 2, chain_smem_bytes<2>(), h->stream>>>(d_src, d_streams, d_csegs, h->d_plans, d_proc, bp));
         else                LAUNCH("k_chain", k_chain<2, true><<<g.n_csegs, NSEG * 2, chain_smem_bytes<2>(), h->stream>>>(d_src, d_streams, d_csegs, h->d_plans, d_proc, bp));
     } else {

@@ -263,6 +263,296 @@ constexpr size_t chain_smem_bytes()
 }
 
 // =====================================================================================
+// k_chainw: the same chain (ENG:117-206) with every WARP on its own: a warp walks one time segment
+// of a stream in tiles of 256 frames (stereo: lanes 0-15 own 16 consecutive samples of L, lanes 16-31
+// the same frames of R) or 512 frames (mono), so
+//   * the blocked scan of a biquad is a 16- (32-) lane shuffle scan and the tile-to-tile carry is the
+//     DF2T state the last lane ends its segment with -- no cross-warp chain, no __syncthreads;
+//   * the M/S width exchange is one shuffle (xor 16) per sample instead of a trip through shared memory;
+//   * raw PCM comes in as 16-byte cp.async pieces straight into the layout the lanes read back as
+//     128-bit words, and the quantised bands leave as 16-byte stores after a shuffle interleave.
+// Warps of a CTA never wait for each other after the section tables are staged, so their fp64-heavy
+// and integer-heavy phases overlap freely.  Segments are joined by overlap-discard exactly like
+// k_chain's; since eight times as many independent segments are needed, the host picks this kernel
+// for batches large enough to keep the warm-up share small (b200m_set_chain_kernel).
+// The eight segments of a CTA belong to one stream (the host pads with empty segments).
+// =====================================================================================
+constexpr int CW_WARPS = 8;
+template <int CH> struct ChainW {
+    static constexpr int NL = 32 / CH;                      // lanes per channel
+    static constexpr int WT = NL * SEG;                     // frames per warp tile
+    static constexpr int RSTRIDE = CH == 2 ? 20 : 12;       // 32-bit words per 16-frame raw segment (16 / 8 used): conflict-free LDS.128
+    static constexpr int RAW_WORDS = NL * RSTRIDE;
+    static constexpr int USTRIDE = 20;                      // floats per lane in the re-floated stash
+    static constexpr size_t WARP_BYTES = (size_t)RAW_WORDS * 4 + 32 * USTRIDE * 4 + 8 * CH * 2 * 8;
+    static constexpr size_t SMEM = 8 * sizeof(SecTab) + CW_WARPS * WARP_BYTES;
+};
+
+// One biquad over the warp's tile.  j = lane within the channel group of NL lanes; carry (shared
+// memory, 2 doubles per section and channel) = the section state at the tile start, replaced by the
+// state after the tile's last sample.
+template <int NL>
+__device__ __forceinline__ void section_round_w(double (&x)[SEG], const SecTab *__restrict__ T, double *carry, int j)
+{
+    double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+    for (int n = 0; n < SEG; ++n) {
+        s0 = fma(T->g[n][0], x[n], s0);
+        s1 = fma(T->g[n][1], x[n], s1);
+    }
+#pragma unroll
+    for (int k = 0; (1 << k) < NL; ++k) {
+        const double t0 = __shfl_up_sync(FULL, s0, 1 << k, NL);
+        const double t1 = __shfl_up_sync(FULL, s1, 1 << k, NL);
+        if (j >= (1 << k)) {
+            s0 = fma(T->P[k][0], t0, fma(T->P[k][1], t1, s0));
+            s1 = fma(T->P[k][2], t0, fma(T->P[k][3], t1, s1));
+        }
+    }
+    double e0 = __shfl_up_sync(FULL, s0, 1, NL);
+    double e1 = __shfl_up_sync(FULL, s1, 1, NL);
+    if (j == 0) { e0 = 0.0; e1 = 0.0; }
+    const double c0 = carry[0], c1 = carry[1];
+    double z0 = fma(T->Q[j][0], c0, fma(T->Q[j][1], c1, e0));
+    double z1 = fma(T->Q[j][2], c0, fma(T->Q[j][3], c1, e1));
+    const double b0 = T->b0, b1 = T->b1, b2 = T->b2, na1 = -T->a1, na2 = -T->a2;
+#pragma unroll
+    for (int n = 0; n < SEG; ++n) {
+        const double xn = x[n];
+        const double t0 = fma(b1, xn, z1), t1 = b2 * xn;
+        const double y = fma(b0, xn, z0);
+        z0 = fma(na1, y, t0);
+        z1 = fma(na2, y, t1);
+        x[n] = y;
+    }
+    __syncwarp();                                   // every lane has read the carry
+    if (j == NL - 1) { carry[0] = z0; carry[1] = z1; }
+}
+
+// 16 quantised samples per lane -> interleaved int16 in global memory.  Stereo: lane j (L) and lane
+// j + 16 (R) hold the two channels of frames 16j .. 16j+15; they swap halves by shuffle, the L lane
+// writes frames 0..7 and the R lane frames 8..15 of the segment (32 contiguous bytes each).
+template <int CH>
+__device__ __forceinline__ void store_q16_w(int16_t *__restrict__ dst, const int (&q)[SEG], int j, int c, int nvalid, bool al16)
+{
+    unsigned pk[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) pk[i] = (unsigned)(q[2 * i] & 0xffff) | ((unsigned)q[2 * i + 1] << 16);
+    if (CH == 2) {
+        unsigned o[8];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const unsigned snd = c ? pk[i] : pk[4 + i];
+            const unsigned rcv = __shfl_xor_sync(FULL, snd, 16);
+            const unsigned Lw = c ? rcv : pk[i], Rw = c ? pk[4 + i] : rcv;
+            o[2 * i] = __byte_perm(Lw, Rw, 0x5410);
+            o[2 * i + 1] = __byte_perm(Lw, Rw, 0x7632);
+        }
+        const int f0 = 16 * j + 8 * c;
+        unsigned *g = reinterpret_cast<unsigned *>(dst) + f0;
+        if (al16 && f0 + 8 <= nvalid) {
+            reinterpret_cast<uint4 *>(g)[0] = make_uint4(o[0], o[1], o[2], o[3]);
+            reinterpret_cast<uint4 *>(g)[1] = make_uint4(o[4], o[5], o[6], o[7]);
+        } else {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) if (f0 + k < nvalid) g[k] = o[k];
+        }
+    } else {
+        const int f0 = 16 * j;
+        if (al16 && f0 + 16 <= nvalid) {
+            reinterpret_cast<uint4 *>(dst + f0)[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            reinterpret_cast<uint4 *>(dst + f0)[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+        } else {
+#pragma unroll
+            for (int k = 0; k < 16; ++k) if (f0 + k < nvalid) dst[f0 + k] = (int16_t)q[k];
+        }
+    }
+}
+
+template <int CH, bool NANCHK>
+__global__ void __launch_bounds__(32 * CW_WARPS, 2)
+k_chainw(const int16_t *__restrict__ pcm_in, const StreamDesc *__restrict__ streams, const SegDesc *__restrict__ segs, int n_segs,
+         const PlanDev *__restrict__ plans, int16_t *__restrict__ proc, BandPtrs bp)
+{
+    using W = ChainW<CH>;
+    constexpr int NL = W::NL, WT = W::WT;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    SecTab *tabs = reinterpret_cast<SecTab *>(smem_raw);                 // eq[4] lp[2] hp[2] of the CTA's plan
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    unsigned char *wbase = smem_raw + 8 * sizeof(SecTab) + (size_t)warp * W::WARP_BYTES;
+    unsigned *raw = reinterpret_cast<unsigned *>(wbase);                 // [NL][RSTRIDE] raw PCM of the tile being fetched
+    float *su = reinterpret_cast<float *>(wbase + (size_t)W::RAW_WORDS * 4) + lane * W::USTRIDE;   // this lane's 16 re-floated samples
+    double *carry = reinterpret_cast<double *>(wbase + (size_t)W::RAW_WORDS * 4 + 32 * W::USTRIDE * 4);   // [8][CH][2]
+
+    const int sidx = blockIdx.x * CW_WARPS + warp;
+    const SegDesc sg0 = segs[blockIdx.x * CW_WARPS];                     // the CTA's first segment names the stream (and so the plan)
+    const PlanDev *__restrict__ pl = plans + streams[sg0.owner].plan;
+    {
+        const double *src = reinterpret_cast<const double *>(pl->eq);
+        double *dst = reinterpret_cast<double *>(tabs);
+        for (int i = threadIdx.x; i < 8 * (int)(sizeof(SecTab) / 8); i += 32 * CW_WARPS) dst[i] = src[i];
+    }
+    if (lane < 8 * CH * 2) carry[lane] = 0.0;
+    __syncthreads();                                                     // the only CTA-wide barrier
+    if (sidx >= n_segs) return;
+    const SegDesc sg = segs[sidx];
+    if (sg.begin >= sg.end) return;
+    const StreamDesc sd = streams[sg.owner];
+    const int sat_on = pl->sat_on, n_eq = pl->n_eq, width_on = pl->width_on, multiband = pl->multiband;
+    const float s_clean = pl->sat_clean, s_mix = pl->sat_mix, s_drive = pl->sat_drive;
+    const double width = pl->width;
+    const float widthf = (float)width;
+    const int c = CH == 2 ? lane >> 4 : 0, j = CH == 2 ? lane & 15 : lane;
+
+    const int16_t *__restrict__ in = pcm_in + sd.in_off * CH;
+    const bool in16 = (reinterpret_cast<unsigned long long>(in) & 15ull) == 0;
+    // every output buffer of the stream starts at the same frame offset: one alignment test serves all
+    const bool out16 = ((reinterpret_cast<unsigned long long>(proc + sd.out_off * CH) | reinterpret_cast<unsigned long long>(bp.band[0] + sd.out_off * CH) |
+                         reinterpret_cast<unsigned long long>(bp.band[1] + sd.out_off * CH) | reinterpret_cast<unsigned long long>(bp.band[2] + sd.out_off * CH)) & 15ull) == 0;
+
+    // raw PCM of tile t0 -> raw[]: 64 pieces of 16 bytes, two per lane (zeros past the end of the input)
+    auto fetch = [&](int t0) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int p = lane + 32 * h;
+            if (CH == 2) {
+                const int gf = t0 + 4 * p;
+                unsigned *d = raw + W::RSTRIDE * (p >> 2) + 4 * (p & 3);
+                if (in16 && gf + 4 <= sd.in_frames) {
+                    const unsigned sa = (unsigned)__cvta_generic_to_shared(d);
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(reinterpret_cast<const unsigned *>(in) + gf) : "memory");
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) d[k] = gf + k < sd.in_frames ? reinterpret_cast<const unsigned *>(in)[gf + k] : 0u;
+                }
+            } else {
+                const int gf = t0 + 8 * p;
+                unsigned *d = raw + W::RSTRIDE * (p >> 1) + 4 * (p & 1);
+                if (in16 && gf + 8 <= sd.in_frames) {
+                    const unsigned sa = (unsigned)__cvta_generic_to_shared(d);
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(in + gf) : "memory");
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const unsigned lo = gf + 2 * k < sd.in_frames ? (unsigned)(unsigned short)in[gf + 2 * k] : 0u;
+                        const unsigned hi = gf + 2 * k + 1 < sd.in_frames ? (unsigned)(unsigned short)in[gf + 2 * k + 1] : 0u;
+                        d[k] = lo | (hi << 16);
+                    }
+                }
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+
+    const int seg_begin = (int)sg.begin, seg_end = (int)sg.end;
+    const int t_first = max(0, seg_begin - sg.warm);
+    fetch(t_first);
+    for (int t0 = t_first; t0 < seg_end; t0 += WT) {
+        const bool store = t0 >= seg_begin;          // warm-up tiles only advance the filter states
+        const int nvalid = store ? min(WT, seg_end - t0) : 0;
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncwarp();
+        // ---- int16 -> float32 (+ exciter), ENG:117-134: this lane's 16 samples of its channel ----------
+        double x[SEG];
+        {
+            float v[SEG];
+            if (CH == 2) {
+                const uint4 *rp = reinterpret_cast<const uint4 *>(raw + W::RSTRIDE * j);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const uint4 w = rp[i];
+                    const unsigned ww[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        v[4 * i + k] = (float)(c ? (int)ww[k] >> 16 : (int)(short)(ww[k] & 0xffffu)) * (1.0f / 32768.0f);
+                }
+            } else {
+                const uint4 *rp = reinterpret_cast<const uint4 *>(raw + W::RSTRIDE * j);
+#pragma unroll
+                for (int i = 0; i < 2; ++i) {
+                    const uint4 w = rp[i];
+                    const unsigned ww[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        v[8 * i + 2 * k] = (float)(int)(short)(ww[k] & 0xffffu) * (1.0f / 32768.0f);
+                        v[8 * i + 2 * k + 1] = (float)((int)ww[k] >> 16) * (1.0f / 32768.0f);
+                    }
+                }
+            }
+            if (sat_on) {
+#pragma unroll
+                for (int n = 0; n < SEG; ++n) v[n] = exciter(v[n], s_clean, s_mix, s_drive);
+            }
+#pragma unroll
+            for (int n = 0; n < SEG; ++n) x[n] = (double)v[n];
+        }
+        __syncwarp();                                // raw[] is free again
+        if (t0 + WT < seg_end) fetch(t0 + WT);
+
+        // ---- EQ (bypassed sections were dropped at plan time, ENG:171,186) ---------------------------
+#pragma unroll
+        for (int s = 0; s < 4; ++s)
+            if (s < n_eq) section_round_w<NL>(x, &tabs[s], carry + (s * CH + c) * 2, j);
+
+        // ---- M/S width: the other channel of the same frames lives 16 lanes away ----------------------
+        if (CH == 2 && width_on) {
+            if (n_eq > 0) {     // float64 arithmetic (EQ output is float64)
+#pragma unroll
+                for (int n = 0; n < SEG; ++n) {
+                    const double o = __shfl_xor_sync(FULL, x[n], 16);
+                    const double mid = __dmul_rn(__dadd_rn(x[n], o), 0.5);
+                    const double side = __dmul_rn(__dmul_rn(__dsub_rn(x[n], o), 0.5), width);
+                    x[n] = __dadd_rn(mid, side);
+                }
+            } else {            // EQ fully bypassed: the reference stays in float32
+#pragma unroll
+                for (int n = 0; n < SEG; ++n) {
+                    const float me = (float)x[n], o = __shfl_xor_sync(FULL, me, 16);
+                    const float mid = __fmul_rn(__fadd_rn(me, o), 0.5f);
+                    const float side = __fmul_rn(__fmul_rn(__fsub_rn(me, o), 0.5f), widthf);
+                    x[n] = (double)__fadd_rn(mid, side);
+                }
+            }
+        }
+
+        int q[SEG];
+        const int64_t o0 = (sd.out_off + t0) * CH;
+        if (!multiband) {
+#pragma unroll
+            for (int n = 0; n < SEG; ++n) q[n] = quant16<NANCHK>(x[n]);
+            store_q16_w<CH>(proc + o0, q, j, c, nvalid, out16);
+        } else {
+            // ---- quantise #1, re-float (ENG:199), crossover ------------------------------
+#pragma unroll
+            for (int n = 0; n < SEG; ++n) {
+                const float u = (float)quant16<NANCHK>(x[n]) * (1.0f / 32768.0f);
+                su[n] = u;
+                x[n] = (double)u;
+            }
+            section_round_w<NL>(x, &tabs[4], carry + (4 * CH + c) * 2, j);
+            section_round_w<NL>(x, &tabs[5], carry + (5 * CH + c) * 2, j);
+            double rest[SEG];
+#pragma unroll
+            for (int n = 0; n < SEG; ++n) {
+                const double u = (double)su[n];
+                q[n] = quant16<NANCHK>(x[n]);
+                rest[n] = __dsub_rn(u, x[n]);
+                x[n] = u;
+            }
+            store_q16_w<CH>(bp.band[0] + o0, q, j, c, nvalid, out16);
+            section_round_w<NL>(x, &tabs[6], carry + (6 * CH + c) * 2, j);
+            section_round_w<NL>(x, &tabs[7], carry + (7 * CH + c) * 2, j);
+#pragma unroll
+            for (int n = 0; n < SEG; ++n) q[n] = quant16<NANCHK>(__dsub_rn(rest[n], x[n]));
+            store_q16_w<CH>(bp.band[1] + o0, q, j, c, nvalid, out16);
+#pragma unroll
+            for (int n = 0; n < SEG; ++n) q[n] = quant16<NANCHK>(x[n]);
+            store_q16_w<CH>(bp.band[2] + o0, q, j, c, nvalid, out16);
+        }
+    }
+}
+
+// =====================================================================================
 // k_detect: audioop.rms over the look-back window [i-look, i) of both channels, for every
 // frame of every band (pydub rms_at, called from compress_dynamic_range; ENG:207-209).
 // Exact integer arithmetic: per-tile prefix sums of frame energies in uint64, window sum
@@ -828,8 +1118,8 @@ k_recur_fix(const StreamDesc *__restrict__ streams, const PlanDev *__restrict__ 
 // k_apply: gain = 10^(-att/20) per frame and band, audioop.mul (floor of the clamped
 // product), then low.overlay(mid).overlay(high) = two saturating int16 adds (ENG:210).
 // Two frames per thread (16-byte attenuation loads, 8-byte sample loads): six independent
-// exp10 chains in flight.  grid = (tiles of 512 frames, streams).  nbands == 1 backs the
-// single-band helper entry point.
+// exp10 chains in flight.  grid = (tiles of 512 frames, streams).  NB == 1 backs the
+// single-band helper entry point (band `band_base`); NB == 3 is the crossover (bands 0..2).
 // =====================================================================================
 // 10^x for the gain of an attenuation: x = -att / 20 <= 0 and far from underflow (att is at most
 // slope * 20 log10(32768 / thresh_rms) dB; the caller falls back to the library routine beyond
@@ -875,10 +1165,10 @@ __device__ __forceinline__ void apply_frame(int &acc0, int &acc1, unsigned smp, 
     if (CH == 2) acc1 = first ? v1 : max(-32768, min(32767, acc1 + v1));
 }
 
-template <int CH>
+template <int CH, int NB>
 __global__ void __launch_bounds__(256)
 k_apply(const StreamDesc *__restrict__ streams, const PlanDev *__restrict__ plans, BandPtrs bp,
-        int nbands, int band_base, int16_t *__restrict__ proc)
+        int band_base, int16_t *__restrict__ proc)
 {
     const StreamDesc sd = streams[blockIdx.y];
     if (!plans[sd.plan].multiband) return;
@@ -887,20 +1177,33 @@ k_apply(const StreamDesc *__restrict__ streams, const PlanDev *__restrict__ plan
     const int64_t gi = sd.out_off + f;
     const bool two = f + 1 < sd.out_frames && (gi & 1) == 0;     // aligned pair
     int a0 = 0, a1 = 0, b0 = 0, b1 = 0;                          // frame f (L, R), frame f + 1 (L, R)
+    const double *attp[NB];
+    const int16_t *smpp[NB];
+#pragma unroll
+    for (int b = 0; b < NB; ++b) {                               // NB == 3: all bands, band_base == 0 (constant indices: no local copy of bp)
+        attp[b] = NB == 3 ? bp.att[b] : bp.att[band_base];
+        smpp[b] = NB == 3 ? bp.band[b] : bp.band[band_base];
+    }
     if (two) {
-        for (int b = 0; b < nbands; ++b) {
-            const int band = band_base + b;
-            const double2 at = *reinterpret_cast<const double2 *>(bp.att[band] + gi);
-            unsigned s0, s1;
+        // every load of the thread is issued before the first gain is computed: the kernel runs at
+        // the speed its 40 bytes per frame arrive
+        double2 at[NB];
+        unsigned s0[NB], s1[NB];
+#pragma unroll
+        for (int b = 0; b < NB; ++b) {
+            at[b] = *reinterpret_cast<const double2 *>(attp[b] + gi);
             if (CH == 2) {
-                const uint2 q = *reinterpret_cast<const uint2 *>(bp.band[band] + gi * 2);
-                s0 = q.x; s1 = q.y;
+                const uint2 q = *reinterpret_cast<const uint2 *>(smpp[b] + gi * 2);
+                s0[b] = q.x; s1[b] = q.y;
             } else {
-                const unsigned q = *reinterpret_cast<const unsigned *>(bp.band[band] + gi);
-                s0 = q & 0xffffu; s1 = q >> 16;
+                const unsigned q = *reinterpret_cast<const unsigned *>(smpp[b] + gi);
+                s0[b] = q & 0xffffu; s1[b] = q >> 16;
             }
-            apply_frame<CH>(a0, a1, s0, at.x, b == 0);
-            apply_frame<CH>(b0, b1, s1, at.y, b == 0);
+        }
+#pragma unroll
+        for (int b = 0; b < NB; ++b) {
+            apply_frame<CH>(a0, a1, s0[b], at[b].x, b == 0);
+            apply_frame<CH>(b0, b1, s1[b], at[b].y, b == 0);
         }
         if (CH == 2)
             *reinterpret_cast<uint2 *>(proc + gi * 2) = make_uint2((unsigned)(a0 & 0xffff) | ((unsigned)a1 << 16),
@@ -909,12 +1212,12 @@ k_apply(const StreamDesc *__restrict__ streams, const PlanDev *__restrict__ plan
             *reinterpret_cast<unsigned *>(proc + gi) = (unsigned)(a0 & 0xffff) | ((unsigned)b0 << 16);
     } else {
         for (int k = 0; k < 2 && f + k < sd.out_frames; ++k) {
-            for (int b = 0; b < nbands; ++b) {
-                const int band = band_base + b;
-                const double at = bp.att[band][gi + k];
+#pragma unroll
+            for (int b = 0; b < NB; ++b) {
+                const double at = attp[b][gi + k];
                 unsigned s0;
-                if (CH == 2) s0 = *reinterpret_cast<const unsigned *>(bp.band[band] + (gi + k) * 2);
-                else s0 = (unsigned)(unsigned short)bp.band[band][gi + k];
+                if (CH == 2) s0 = *reinterpret_cast<const unsigned *>(smpp[b] + (gi + k) * 2);
+                else s0 = (unsigned)(unsigned short)smpp[b][gi + k];
                 apply_frame<CH>(a0, a1, s0, at, b == 0);
             }
             if (CH == 2) *reinterpret_cast<unsigned *>(proc + (gi + k) * 2) = (unsigned)(a0 & 0xffff) | ((unsigned)a1 << 16);
