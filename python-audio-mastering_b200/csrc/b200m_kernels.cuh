@@ -294,12 +294,18 @@ template <int CH> struct ChainW {
 template <int NL>
 __device__ __forceinline__ void section_round_w(double (&x)[SEG], const SecTab *__restrict__ T, double *carry, int j)
 {
-    double s0 = 0.0, s1 = 0.0;
+    // zero-state end state of the segment: even and odd samples accumulate separately (two chains
+    // per component instead of one: half the dependent latency)
+    double s0 = 0.0, s1 = 0.0, r0 = 0.0, r1 = 0.0;
 #pragma unroll
-    for (int n = 0; n < SEG; ++n) {
+    for (int n = 0; n < SEG; n += 2) {
         s0 = fma(T->g[n][0], x[n], s0);
         s1 = fma(T->g[n][1], x[n], s1);
+        r0 = fma(T->g[n + 1][0], x[n + 1], r0);
+        r1 = fma(T->g[n + 1][1], x[n + 1], r1);
     }
+    s0 = __dadd_rn(s0, r0);
+    s1 = __dadd_rn(s1, r1);
 #pragma unroll
     for (int k = 0; (1 << k) < NL; ++k) {
         const double t0 = __shfl_up_sync(FULL, s0, 1 << k, NL);
@@ -327,6 +333,59 @@ __device__ __forceinline__ void section_round_w(double (&x)[SEG], const SecTab *
     }
     __syncwarp();                                   // every lane has read the carry
     if (j == NL - 1) { carry[0] = z0; carry[1] = z1; }
+}
+
+// Two INDEPENDENT biquads over the same tile side by side (the low-pass and the high-pass branch of
+// the crossover, ENG:200-201): the same arithmetic as two section_round_w calls, written so that the
+// two dependent chains interleave (twice the instruction-level parallelism of one).
+template <int NL>
+__device__ __forceinline__ void section_round_w2(double (&xa)[SEG], double (&xb)[SEG], const SecTab *__restrict__ Ta,
+                                                 const SecTab *__restrict__ Tb, double *carry_a, double *carry_b, int j)
+{
+    double a0 = 0.0, a1 = 0.0, b0s = 0.0, b1s = 0.0;
+#pragma unroll
+    for (int n = 0; n < SEG; ++n) {
+        a0 = fma(Ta->g[n][0], xa[n], a0);
+        a1 = fma(Ta->g[n][1], xa[n], a1);
+        b0s = fma(Tb->g[n][0], xb[n], b0s);
+        b1s = fma(Tb->g[n][1], xb[n], b1s);
+    }
+#pragma unroll
+    for (int k = 0; (1 << k) < NL; ++k) {
+        const double ta0 = __shfl_up_sync(FULL, a0, 1 << k, NL), ta1 = __shfl_up_sync(FULL, a1, 1 << k, NL);
+        const double tb0 = __shfl_up_sync(FULL, b0s, 1 << k, NL), tb1 = __shfl_up_sync(FULL, b1s, 1 << k, NL);
+        if (j >= (1 << k)) {
+            a0 = fma(Ta->P[k][0], ta0, fma(Ta->P[k][1], ta1, a0));
+            a1 = fma(Ta->P[k][2], ta0, fma(Ta->P[k][3], ta1, a1));
+            b0s = fma(Tb->P[k][0], tb0, fma(Tb->P[k][1], tb1, b0s));
+            b1s = fma(Tb->P[k][2], tb0, fma(Tb->P[k][3], tb1, b1s));
+        }
+    }
+    double ea0 = __shfl_up_sync(FULL, a0, 1, NL), ea1 = __shfl_up_sync(FULL, a1, 1, NL);
+    double eb0 = __shfl_up_sync(FULL, b0s, 1, NL), eb1 = __shfl_up_sync(FULL, b1s, 1, NL);
+    if (j == 0) { ea0 = 0.0; ea1 = 0.0; eb0 = 0.0; eb1 = 0.0; }
+    const double ca0 = carry_a[0], ca1 = carry_a[1], cb0 = carry_b[0], cb1 = carry_b[1];
+    double za0 = fma(Ta->Q[j][0], ca0, fma(Ta->Q[j][1], ca1, ea0));
+    double za1 = fma(Ta->Q[j][2], ca0, fma(Ta->Q[j][3], ca1, ea1));
+    double zb0 = fma(Tb->Q[j][0], cb0, fma(Tb->Q[j][1], cb1, eb0));
+    double zb1 = fma(Tb->Q[j][2], cb0, fma(Tb->Q[j][3], cb1, eb1));
+    const double ab0 = Ta->b0, ab1 = Ta->b1, ab2 = Ta->b2, ana1 = -Ta->a1, ana2 = -Ta->a2;
+    const double bb0 = Tb->b0, bb1 = Tb->b1, bb2 = Tb->b2, bna1 = -Tb->a1, bna2 = -Tb->a2;
+#pragma unroll
+    for (int n = 0; n < SEG; ++n) {
+        const double xan = xa[n], xbn = xb[n];
+        const double ta0 = fma(ab1, xan, za1), ta1 = ab2 * xan;
+        const double tb0 = fma(bb1, xbn, zb1), tb1 = bb2 * xbn;
+        const double ya = fma(ab0, xan, za0), yb = fma(bb0, xbn, zb0);
+        za0 = fma(ana1, ya, ta0);
+        zb0 = fma(bna1, yb, tb0);
+        za1 = fma(ana2, ya, ta1);
+        zb1 = fma(bna2, yb, tb1);
+        xa[n] = ya;
+        xb[n] = yb;
+    }
+    __syncwarp();
+    if (j == NL - 1) { carry_a[0] = za0; carry_a[1] = za1; carry_b[0] = zb0; carry_b[1] = zb1; }
 }
 
 // 16 quantised samples per lane -> interleaved int16 in global memory.  Stereo: lane j (L) and lane
@@ -529,24 +588,21 @@ k_chainw(const int16_t *__restrict__ pcm_in, const StreamDesc *__restrict__ stre
                 su[n] = u;
                 x[n] = (double)u;
             }
-            section_round_w<NL>(x, &tabs[4], carry + (4 * CH + c) * 2, j);
-            section_round_w<NL>(x, &tabs[5], carry + (5 * CH + c) * 2, j);
-            double rest[SEG];
+            // low-pass and high-pass branches side by side (both start from u)
+            double xh[SEG];
 #pragma unroll
-            for (int n = 0; n < SEG; ++n) {
-                const double u = (double)su[n];
-                q[n] = quant16<NANCHK>(x[n]);
-                rest[n] = __dsub_rn(u, x[n]);
-                x[n] = u;
-            }
-            store_q16_w<CH>(bp.band[0] + o0, q, j, c, nvalid, out16);
-            section_round_w<NL>(x, &tabs[6], carry + (6 * CH + c) * 2, j);
-            section_round_w<NL>(x, &tabs[7], carry + (7 * CH + c) * 2, j);
-#pragma unroll
-            for (int n = 0; n < SEG; ++n) q[n] = quant16<NANCHK>(__dsub_rn(rest[n], x[n]));
-            store_q16_w<CH>(bp.band[1] + o0, q, j, c, nvalid, out16);
+            for (int n = 0; n < SEG; ++n) xh[n] = x[n];
+            section_round_w2<NL>(x, xh, &tabs[4], &tabs[6], carry + (4 * CH + c) * 2, carry + (6 * CH + c) * 2, j);
+            section_round_w2<NL>(x, xh, &tabs[5], &tabs[7], carry + (5 * CH + c) * 2, carry + (7 * CH + c) * 2, j);
+            // ---- low band; mid = x - low - high (ENG:202), same order of subtractions -----------------
 #pragma unroll
             for (int n = 0; n < SEG; ++n) q[n] = quant16<NANCHK>(x[n]);
+            store_q16_w<CH>(bp.band[0] + o0, q, j, c, nvalid, out16);
+#pragma unroll
+            for (int n = 0; n < SEG; ++n) q[n] = quant16<NANCHK>(__dsub_rn(__dsub_rn((double)su[n], x[n]), xh[n]));
+            store_q16_w<CH>(bp.band[1] + o0, q, j, c, nvalid, out16);
+#pragma unroll
+            for (int n = 0; n < SEG; ++n) q[n] = quant16<NANCHK>(xh[n]);
             store_q16_w<CH>(bp.band[2] + o0, q, j, c, nvalid, out16);
         }
     }

@@ -284,3 +284,28 @@ def test_host_pipeline_is_invisible(eng):
     for a, b, ia, ib in zip(base, out, binfo, info):
         assert np.array_equal(a, b)
         assert ia["loudness"] == ib["loudness"] and ia["gain"] == ib["gain"]
+
+
+@pytest.mark.parametrize("rate,channels", [(44101, 1), (44101, 2), (48001, 2)])
+def test_ragged_unaligned_batch(eng, rate, channels):
+    """Tracks of odd lengths at odd sample rates in one batch (30-s chunks of an odd rate start at frames
+    that are not multiples of four): chunk and track starts fall on addresses that are
+    not 8 / 16-byte aligned, so every kernel takes its element-wise load / store path (k_chain tile
+    stores, k_detect RMS quads, the recurrence's RMS rows, k_final's vector path).  Bit-exact against the
+    oracle (saturation 0), with both chain kernels."""
+    from b200master import synth
+    from oracle import port
+    st = dict(bass_boost=3.0, mid_cut=2.0, presence_boost=1.5, treble_boost=2.0, width=1.15, multiband=True, lufs=-16.0)
+    lens = [31.013, 2.507, 30.0, 0.731]
+    tracks = [synth.make_track(80 + i, s, rate, channels) for i, s in enumerate(lens)]
+    tracks = [t[: t.shape[0] - (i % 3)] for i, t in enumerate(tracks)]          # odd frame counts
+    refs = [port.master(t, rate, st) for t in tracks]
+    try:
+        for mode in (1, 2):
+            eng.set_chain_kernel(mode)
+            outs, infos = eng.master(tracks, rate, st)
+            for o, (r, info), i in zip(outs, refs, infos):
+                assert np.array_equal(o, r), f"chain kernel {mode}"
+                assert abs(i["loudness"] - info["loudness"]) <= 1e-12
+    finally:
+        eng.set_chain_kernel(0)
