@@ -174,6 +174,18 @@ __device__ __forceinline__ int quant16(double y)
     return (int)(short)iv;
 }
 
+// The same quantiser for a value that is already scaled by 2^15 (k_chainw runs the crossover on
+// 2^15 u: the filters are linear and scaling by a power of two commutes with every rounding, so
+// fl(2^15 y) is what y * 32768.0 would have produced).
+template <bool NANCHK = true>
+__device__ __forceinline__ int quant16s(double ys)
+{
+    const int raw = __double2int_rz(ys);
+    int iv = max(-32768, min(32768, raw));
+    if (NANCHK && ((unsigned long long)__double_as_longlong(ys) << 1) > 0xffe0000000000000ull) iv = 0;
+    return (int)(short)iv;
+}
+
 // ENG:128-134 in float32 with every product / sum separately rounded (numpy semantics).
 __device__ __forceinline__ float exciter(float x, float clean, float mix, float drive)
 {

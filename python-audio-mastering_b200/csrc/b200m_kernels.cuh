@@ -581,28 +581,30 @@ k_chainw(const int16_t *__restrict__ pcm_in, const StreamDesc *__restrict__ stre
             for (int n = 0; n < SEG; ++n) q[n] = quant16<NANCHK>(x[n]);
             store_q16_w<CH>(proc + o0, q, j, c, nvalid, out16);
         } else {
-            // ---- quantise #1, re-float (ENG:199), crossover ------------------------------
-#pragma unroll
-            for (int n = 0; n < SEG; ++n) {
-                const float u = (float)quant16<NANCHK>(x[n]) * (1.0f / 32768.0f);
-                su[n] = u;
-                x[n] = (double)u;
-            }
-            // low-pass and high-pass branches side by side (both start from u)
+            // ---- quantise #1, re-float (ENG:199), crossover: run on 2^15 u, i.e. on the integer itself ----
+            // (linear filters, power-of-two scale: every rounding is that of the reference's u = q / 2^15
+            // path, and the three band quantisers lose their multiply)
+            int *sq = reinterpret_cast<int *>(su);
             double xh[SEG];
 #pragma unroll
-            for (int n = 0; n < SEG; ++n) xh[n] = x[n];
+            for (int n = 0; n < SEG; ++n) {
+                const int q1 = quant16<NANCHK>(x[n]);
+                sq[n] = q1;
+                x[n] = (double)q1;
+                xh[n] = x[n];
+            }
+            // low-pass and high-pass branches side by side (both start from u)
             section_round_w2<NL>(x, xh, &tabs[4], &tabs[6], carry + (4 * CH + c) * 2, carry + (6 * CH + c) * 2, j);
             section_round_w2<NL>(x, xh, &tabs[5], &tabs[7], carry + (5 * CH + c) * 2, carry + (7 * CH + c) * 2, j);
             // ---- low band; mid = x - low - high (ENG:202), same order of subtractions -----------------
 #pragma unroll
-            for (int n = 0; n < SEG; ++n) q[n] = quant16<NANCHK>(x[n]);
+            for (int n = 0; n < SEG; ++n) q[n] = quant16s<NANCHK>(x[n]);
             store_q16_w<CH>(bp.band[0] + o0, q, j, c, nvalid, out16);
 #pragma unroll
-            for (int n = 0; n < SEG; ++n) q[n] = quant16<NANCHK>(__dsub_rn(__dsub_rn((double)su[n], x[n]), xh[n]));
+            for (int n = 0; n < SEG; ++n) q[n] = quant16s<NANCHK>(__dsub_rn(__dsub_rn((double)sq[n], x[n]), xh[n]));
             store_q16_w<CH>(bp.band[1] + o0, q, j, c, nvalid, out16);
 #pragma unroll
-            for (int n = 0; n < SEG; ++n) q[n] = quant16<NANCHK>(xh[n]);
+            for (int n = 0; n < SEG; ++n) q[n] = quant16s<NANCHK>(xh[n]);
             store_q16_w<CH>(bp.band[2] + o0, q, j, c, nvalid, out16);
         }
     }
@@ -1212,11 +1214,11 @@ template <int CH>
 __device__ __forceinline__ void apply_frame(int &acc0, int &acc1, unsigned smp, double a, bool first)
 {
     int v0 = (int)(short)(smp & 0xffffu), v1 = CH == 2 ? (int)smp >> 16 : 0;
-    if (a != 0.0) {                                 // pydub: `if attenuation != 0.0`
-        const double g = exp10_gain(a * -0.05);     // db_to_float(-att) = 10 ** (-att / 20)
-        v0 = mul_floor16(v0, g);
-        if (CH == 2) v1 = mul_floor16(v1, g);
-    }
+    // pydub multiplies only `if attenuation != 0.0`; exp10_gain(0) is exactly 1.0 (the polynomial at
+    // r = 0 is its constant term) and floor(v * 1.0) == v, so the test needs no branch
+    const double g = exp10_gain(a * -0.05);         // db_to_float(-att) = 10 ** (-att / 20)
+    v0 = mul_floor16(v0, g);
+    if (CH == 2) v1 = mul_floor16(v1, g);
     acc0 = first ? v0 : max(-32768, min(32767, acc0 + v0));
     if (CH == 2) acc1 = first ? v1 : max(-32768, min(32767, acc1 + v1));
 }
