@@ -12,7 +12,7 @@ for nt in [int(a) for a in sys.argv[1:]] or [64, 8]:
     d_in = synth.make_tracks_torch(0, nt, seconds, rate, "cuda"); n = d_in.shape[1]
     outs = {}
     offs = [i * n for i in range(nt)]; fr = [n] * nt; of = [ms_framing(n, rate)] * nt
-    for mode, segt in [(1, 0), (2, 0), (2, 8), (2, 16), (2, 32), (2, 64)]:
+    for mode, segt in [(1, 0), (2, 0), (0, 0)]:
         eng.set_chain_kernel(mode); eng.set_segment_tiles(segt, 0)
         d_out = torch.empty_like(d_in)
         def step():
@@ -23,10 +23,11 @@ for nt in [int(a) for a in sys.argv[1:]] or [64, 8]:
         for _ in range(K): step()
         eng.synchronize()
         ms = eng.kernel_time_ms("k_chain")[0] / K
+        msk = eng.kernel_time_ms("k_kweight")[0] / K
         eng.set_profiling(False)
-        key = "ref" if mode == 1 else f"w{segt}"
+        key = "ref" if mode == 1 else f"w{mode}{segt}"
         outs[key] = d_out
         same = bool(torch.equal(d_out, outs["ref"]))
-        print(f"tracks {nt:3d} mode {mode} seg_tiles(2048) {segt:3d}: k_chain {ms:8.3f} ms/step   identical to k_chain: {same}", flush=True)
+        print(f"tracks {nt:3d} mode {mode} seg_tiles(2048) {segt:3d}: k_chain {ms:8.3f} k_kweight {msk:7.3f} ms/step   identical to k_chain: {same}", flush=True)
     del outs, d_in
     eng.set_chain_kernel(0); eng.set_segment_tiles(0, 0)
