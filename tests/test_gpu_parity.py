@@ -140,6 +140,10 @@ def test_recurrence_tiling_is_exact_for_any_tile_length(eng):
                 go, ga, _ = eng.compress_dynamic_range(b, make_band(rate, thr, ratio, att, rel), debug=True)
                 assert np.array_equal(ra, ga), f"attenuation differs with tile={tile} warm={warm} rounds={rounds}"
                 assert np.array_equal(ro, go)
+                # a threshold that is only crossed now and then: long held stretches between short active ones
+                ro3 = port.compress_band(b, rate, thr + 14.0, ratio, att, rel)
+                g3 = eng.compress_dynamic_range(b, make_band(rate, thr + 14.0, ratio, att, rel))
+                assert np.array_equal(ro3, g3), f"sparse activity: output differs with tile={tile} warm={warm} rounds={rounds}"
             st = eng.recur_stats()
             if tile == 32:
                 assert st["wrong_tiles"] + st["round_repairs"] > 0, "a 32-frame warm-up cannot always guess right: a repair path must have run"
