@@ -175,6 +175,23 @@ int b200m_master_batch(b200m_handle *h,
                        void *pcm_out, int out_on_device,
                        double *loudness_out, double *gain_out);
 
+/* The same batch for SEVERAL loudness targets at once (a preset x loudness sweep shares
+ * everything ahead of ENG:84): ENG:46-82 and the loudness measurement (ENG:212-218) run once per track,
+ * gain, limiter and final cast (ENG:219-227, ENG:89) once per target.  Bit-identical to n_targets calls of
+ * b200m_master_batch with plan.lufs = targets[k].
+ *   targets      [n_targets] LUFS (1..64); every track's plan must have has_lufs, its own lufs is ignored  (host)
+ *   pcm_out      n_targets copies of the packed batch output, target-major: copy k starts
+ *                k * sum(out_frames) frames after copy 0; device or host
+ *   loudness_out [n_tracks], gain_out [n_targets * n_tracks] (gain_out[k * n_tracks + t]); may be NULL     (host) */
+int b200m_master_batch_targets(b200m_handle *h,
+                               const void *pcm_in, int in_on_device, int fmt,
+                               int n_tracks, const int64_t *in_offsets, const int64_t *in_frames,
+                               const int64_t *out_frames,
+                               const b200m_plan *plans, int n_plans, const int32_t *plan_index,
+                               const double *targets, int n_targets,
+                               void *pcm_out, int out_on_device,
+                               double *loudness_out, double *gain_out);
+
 /* ---- one long track split along time over several GPUs (BASELINE config 4) ---------
  * Slices are cut at 30-s chunk boundaries (ENG:48-54: every filter and compressor restarts
  * there), so ENG:48-80 is local to a slice.  Only the loudness measurement (ENG:82-86,

@@ -100,9 +100,11 @@ class Engine:
 
     # -- the whole path ------------------------------------------------------------------
     def master_raw(self, pcm_in, in_on_device, in_offsets, in_frames, out_frames, plans, plan_index,
-                   pcm_out, out_on_device, want_loudness=True):
-        """Thin wrapper over ``b200m_master_batch``.  pcm_in / pcm_out: numpy int16 arrays or
-        torch tensors; offsets / frames / plan_index: sequences."""
+                   pcm_out, out_on_device, want_loudness=True, targets=None):
+        """Thin wrapper over ``b200m_master_batch`` (``b200m_master_batch_targets`` when ``targets`` is
+        given: pcm_out then holds ``len(targets)`` copies of the batch output, target-major, and the
+        returned gains have shape (len(targets), n)).  pcm_in / pcm_out: numpy int16 arrays or torch
+        tensors; offsets / frames / plan_index: sequences."""
         n = len(in_frames)
         off = np.ascontiguousarray(in_offsets, dtype=np.int64)
         inf = np.ascontiguousarray(in_frames, dtype=np.int64)
@@ -110,6 +112,17 @@ class Engine:
         pidx = np.ascontiguousarray(plan_index, dtype=np.int32)
         parr = (L.Plan * len(plans))(*plans)
         loud = np.empty(n, dtype=np.float64) if want_loudness else None
+        if targets is not None:
+            tg = np.ascontiguousarray(targets, dtype=np.float64)
+            gain = np.empty((len(tg), n), dtype=np.float64) if want_loudness else None
+            self._ck(self._lib.b200m_master_batch_targets(
+                self._h, C.c_void_p(_ptr(pcm_in)), int(in_on_device), L.FMT_S16, n,
+                C.c_void_p(off.ctypes.data), C.c_void_p(inf.ctypes.data), C.c_void_p(outf.ctypes.data),
+                parr, len(plans), C.c_void_p(pidx.ctypes.data), C.c_void_p(tg.ctypes.data), len(tg),
+                C.c_void_p(_ptr(pcm_out)), int(out_on_device),
+                C.c_void_p(loud.ctypes.data) if want_loudness else None,
+                C.c_void_p(gain.ctypes.data) if want_loudness else None))
+            return loud, gain
         gain = np.empty(n, dtype=np.float64) if want_loudness else None
         self._ck(self._lib.b200m_master_batch(
             self._h, C.c_void_p(_ptr(pcm_in)), int(in_on_device), L.FMT_S16, n,
@@ -152,6 +165,57 @@ class Engine:
             infos.append({"loudness": float(loud[i]) if plans[index[i]].has_lufs else None,
                           "gain": float(gain[i]) if plans[index[i]].has_lufs else None})
             pos += n
+        return outs, infos
+
+    def master_targets(self, tracks, rate: int, settings, targets):
+        """``master`` for several loudness targets at once (a preset x loudness sweep): the chain and
+        the loudness measurement run once per track, gain / limiter / final cast once per target.
+        ``settings["lufs"]`` is ignored.  Returns (outs[target][track], infos[track]) with
+        ``infos[t]["gain"]`` a list over targets."""
+        tracks = list(tracks)
+        targets = [float(t) for t in targets]
+        if not targets:
+            raise ValueError("master_targets: at least one loudness target")
+        if not tracks:
+            return [[] for _ in targets], []
+        ch = 1 if tracks[0].ndim == 1 else tracks[0].shape[1]
+        sets = [settings] * len(tracks) if isinstance(settings, dict) else list(settings)
+        plans, index, keys = [], [], {}
+        for s in sets:
+            s = dict(s or {}, lufs=targets[0])
+            k = repr(sorted(s.items(), key=lambda kv: kv[0]))
+            if k not in keys:
+                keys[k] = len(plans)
+                plans.append(make_plan(s, rate, ch))
+            index.append(keys[k])
+        n = len(tracks)
+        in_frames = [int(t.shape[0]) for t in tracks]
+        out_frames = [ms_framing(f, rate) for f in in_frames]
+        flat = np.ascontiguousarray(np.concatenate([np.ascontiguousarray(t, dtype=np.int16).reshape(-1) for t in tracks]))
+        off = np.ascontiguousarray(np.concatenate([[0], np.cumsum(in_frames)[:-1]]), dtype=np.int64)
+        inf = np.ascontiguousarray(in_frames, dtype=np.int64)
+        outf = np.ascontiguousarray(out_frames, dtype=np.int64)
+        pidx = np.ascontiguousarray(index, dtype=np.int32)
+        tg = np.ascontiguousarray(targets, dtype=np.float64)
+        total = int(sum(out_frames))
+        out = np.empty(len(targets) * total * ch, dtype=np.int16)
+        loud = np.empty(n, dtype=np.float64)
+        gain = np.empty(len(targets) * n, dtype=np.float64)
+        parr = (L.Plan * len(plans))(*plans)
+        self._ck(self._lib.b200m_master_batch_targets(
+            self._h, C.c_void_p(flat.ctypes.data), 0, L.FMT_S16, n, C.c_void_p(off.ctypes.data), C.c_void_p(inf.ctypes.data),
+            C.c_void_p(outf.ctypes.data), parr, len(plans), C.c_void_p(pidx.ctypes.data),
+            C.c_void_p(tg.ctypes.data), len(targets), C.c_void_p(out.ctypes.data), 0,
+            C.c_void_p(loud.ctypes.data), C.c_void_p(gain.ctypes.data)))
+        outs = []
+        for k in range(len(targets)):
+            pos, row = k * total, []
+            for f in out_frames:
+                o = out[pos * ch:(pos + f) * ch]
+                row.append(o.reshape(-1, ch) if ch > 1 else o)
+                pos += f
+            outs.append(row)
+        infos = [{"loudness": float(loud[t]), "gain": [float(gain[k * n + t]) for k in range(len(targets))]} for t in range(n)]
         return outs, infos
 
     # -- time slices of one long track (device tensors; see longtrack.py) ------------------------

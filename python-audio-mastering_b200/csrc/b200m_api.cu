@@ -947,12 +947,15 @@ struct GroupPlan {
     std::vector<SegDesc> csegs, ksegs;
     int64_t F = 0, Fp = 0, in_total = 0, zoff = 0, out_base = 0;      // F: workspace frames (aligned track starts), Fp: packed output frames
     size_t desc_bytes = 0, res_off = 0, pin_bytes = 0, need = 0;
+    int n_targets = 0;               // > 0: loudness sweep (b200m_master_batch_targets): that many outputs per track
 };
 
 static void plan_group(const b200m_handle *h, GroupPlan &gp, bool in_dev, bool out_dev, int t_begin, int t_end,
                        const int64_t *in_offsets, const int64_t *in_frames, const int64_t *out_frames,
-                       const b200m_plan *plans, const int32_t *plan_index, int64_t out_base)
+                       const b200m_plan *plans, const int32_t *plan_index, int64_t out_base, int n_targets = 0)
 {
+    gp.n_targets = n_targets;
+    const size_t outs = (size_t)std::max(1, n_targets);
     const int ch = plans[0].channels, rate = plans[0].sample_rate;
     const int64_t chunk = 30LL * rate;          // ENG:48: 30 000 ms -> int(ms * rate / 1000) frames
     Group &g = gp.g;
@@ -1033,11 +1036,11 @@ static void plan_group(const b200m_handle *h, GroupPlan &gp, bool in_dev, bool o
     gp.desc_bytes = gp.streams.size() * sizeof(StreamDesc) + gp.tracks.size() * sizeof(TrackDesc) +
                     (gp.csegs.size() + gp.ksegs.size()) * sizeof(SegDesc);
     gp.res_off = (gp.desc_bytes + 63) & ~(size_t)63;       // double2 results: 16-byte aligned slot after the descriptors
-    gp.pin_bytes = (gp.res_off + (size_t)g.n_tracks * 16 + 255) & ~(size_t)255;
-    size_t need = 16384 + gp.desc_bytes + (size_t)g.n_tracks * 16 + (size_t)F * ch * 2 /*proc*/ + (size_t)F * 4 /*kw*/ +
-                  (size_t)zoff * 16 + 24 * 256;
+    gp.pin_bytes = (gp.res_off + (size_t)g.n_tracks * 16 * (1 + (size_t)n_targets) + 255) & ~(size_t)255;
+    size_t need = 16384 + gp.desc_bytes + (size_t)g.n_tracks * 16 * (1 + (size_t)n_targets) + (size_t)F * ch * 2 /*proc*/ + (size_t)F * 4 /*kw*/ +
+                  (size_t)zoff * 16 + 25 * 256;
     if (!in_dev) need += (size_t)in_total * ch * 2;
-    if (!out_dev) need += (size_t)Fp * ch * 2;
+    if (!out_dev) need += (size_t)Fp * ch * 2 * outs + 256 * outs;
     if (g.any_multiband) need += (size_t)F * 3 * ch * 2 + 3 * 256 + compressor_ws_bytes(h, g, F, 3);
     gp.need = (need + 1023) & ~(size_t)1023;
 }
@@ -1051,8 +1054,12 @@ struct ExecStreams {
 // (time slices of a long track: loudness is measured across slices, b200m_slice_*)
 static int exec_group(b200m_handle *h, GroupPlan &gp, char *ws, char *pin, const ExecStreams &X,
                       const int16_t *pcm_in, bool in_dev, const int64_t *in_offsets, const int64_t *in_frames,
-                      int16_t *pcm_out, bool out_dev, int16_t *ext_proc = nullptr)
+                      int16_t *pcm_out, bool out_dev, int16_t *ext_proc = nullptr,
+                      const double *targets = nullptr, int64_t out_total = 0)
 {
+    // targets != NULL (gp.n_targets of them): k_final runs once per target; output copy k of the whole batch
+    // starts out_total frames after copy k - 1
+    const int n_out = targets ? gp.n_targets : 1;
     Group &g = gp.g;
     const int ch = g.ch;
     const int64_t F = gp.F;
@@ -1062,14 +1069,15 @@ static int exec_group(b200m_handle *h, GroupPlan &gp, char *ws, char *pin, const
     TrackDesc *d_tracks = A.take<TrackDesc>(gp.tracks.size());
     SegDesc *d_csegs = A.take<SegDesc>(gp.csegs.size() + 1);
     SegDesc *d_ksegs = A.take<SegDesc>(gp.ksegs.size() + 1);
-    double2 *d_loud = A.take<double2>(g.n_tracks);
+    double2 *d_loud = A.take<double2>((size_t)g.n_tracks * (1 + (size_t)gp.n_targets));     // [0]: k_gate's, [1 + k]: target k
     int16_t *d_proc = ext_proc ? ext_proc : A.take<int16_t>((size_t)F * ch);
     float *d_kw = A.take<float>(F);
     double *d_z = A.take<double>(gp.zoff + 1);
     double *d_zsel = A.take<double>(gp.zoff + 1);
     int16_t *d_in = nullptr, *d_out = nullptr;
     if (!in_dev) d_in = A.take<int16_t>((size_t)gp.in_total * ch);
-    if (!out_dev) d_out = A.take<int16_t>((size_t)gp.Fp * ch);
+    const size_t out_stride = ((size_t)gp.Fp * ch + 127) & ~(size_t)127;                    // samples between the staged copies (256-byte aligned)
+    if (!out_dev) d_out = A.take<int16_t>(out_stride * n_out);
     BandPtrs bp;
     double *d_spec = nullptr;
     std::memset(&bp, 0, sizeof bp);
@@ -1137,14 +1145,27 @@ static int exec_group(b200m_handle *h, GroupPlan &gp, char *ws, char *pin, const
     rc = launch_loudness(h, g, d_proc, nullptr, d_kw, d_z, d_zsel, d_loud);
     if (rc) return rc;
     const dim3 gf((unsigned)std::min<int64_t>((g.max_track_frames + 1023) / 1024, 8192), g.n_tracks);   // four frames per thread
-    if (ch == 2) LAUNCH("k_final", k_final<2><<<gf, 256, 0, h->stream>>>(d_proc, d_tracks, h->d_plans, d_loud, d_dst));
-    else         LAUNCH("k_final", k_final<1><<<gf, 256, 0, h->stream>>>(d_proc, d_tracks, h->d_plans, d_loud, d_dst));
+    for (int k = 0; k < n_out; ++k) {
+        const double2 *loud_k = d_loud;
+        int16_t *dst_k = d_dst;
+        if (targets) {
+            double2 *lk = d_loud + (size_t)(1 + k) * g.n_tracks;
+            LAUNCH("k_regain", k_regain<<<(g.n_tracks + 127) / 128, 128, 0, h->stream>>>(d_loud, g.n_tracks, targets[k], lk));
+            loud_k = lk;
+            dst_k = out_dev ? pcm_out + ((int64_t)k * out_total + gp.out_base) * ch : d_out + (size_t)k * out_stride;
+        }
+        if (ch == 2) LAUNCH("k_final", k_final<2><<<gf, 256, 0, h->stream>>>(d_proc, d_tracks, h->d_plans, loud_k, dst_k));
+        else         LAUNCH("k_final", k_final<1><<<gf, 256, 0, h->stream>>>(d_proc, d_tracks, h->d_plans, loud_k, dst_k));
+    }
     CK(cudaGetLastError());
     if (X.comp_done) { CK(cudaEventRecord(X.comp_done, X.comp)); CK(cudaStreamWaitEvent(X.out, X.comp_done, 0)); }
 
     // ---- output stream: PCM and {loudness, gain} -> host --------------------------------------
-    if (!out_dev) CK(cudaMemcpyAsync(pcm_out + gp.out_base * ch, d_out, (size_t)gp.Fp * ch * 2, cudaMemcpyDeviceToHost, X.out));
-    CK(cudaMemcpyAsync(pin + gp.res_off, d_loud, (size_t)g.n_tracks * 16, cudaMemcpyDeviceToHost, X.out));
+    if (!out_dev)
+        for (int k = 0; k < n_out; ++k)
+            CK(cudaMemcpyAsync(pcm_out + ((int64_t)k * out_total + gp.out_base) * ch, d_out + (size_t)k * out_stride, (size_t)gp.Fp * ch * 2,
+                               cudaMemcpyDeviceToHost, X.out));
+    CK(cudaMemcpyAsync(pin + gp.res_off, d_loud, (size_t)g.n_tracks * 16 * (1 + (size_t)gp.n_targets), cudaMemcpyDeviceToHost, X.out));
     if (X.d2h_done) CK(cudaEventRecord(X.d2h_done, X.out));
     return B200M_OK;
 }
@@ -1159,10 +1180,11 @@ static cudaEvent_t sync_event(b200m_handle *h, size_t i)
     return h->sync_events[i];
 }
 
-extern "C" int b200m_master_batch(b200m_handle *h, const void *pcm_in, int in_on_device, int fmt, int n_tracks,
-                                  const int64_t *in_offsets, const int64_t *in_frames, const int64_t *out_frames,
-                                  const b200m_plan *plans, int n_plans, const int32_t *plan_index,
-                                  void *pcm_out, int out_on_device, double *loudness_out, double *gain_out)
+static int master_batch_impl(b200m_handle *h, const void *pcm_in, int in_on_device, int fmt, int n_tracks,
+                             const int64_t *in_offsets, const int64_t *in_frames, const int64_t *out_frames,
+                             const b200m_plan *plans, int n_plans, const int32_t *plan_index,
+                             const double *targets, int n_targets,
+                             void *pcm_out, int out_on_device, double *loudness_out, double *gain_out)
 {
     if (!h) return B200M_ERR_INVALID;
     if (!pcm_in || !pcm_out || n_tracks <= 0 || !in_offsets || !in_frames || !out_frames || !plans || n_plans <= 0 || !plan_index)
@@ -1182,7 +1204,11 @@ extern "C" int b200m_master_batch(b200m_handle *h, const void *pcm_in, int in_on
         if (plans[plan_index[t]].has_lufs && (double)out_frames[t] < 0.4 * rate)
             return fail(h, B200M_ERR_TOO_SHORT, "track %d: audio must have length greater than the block size (400 ms)", t);
         total_frames += std::max(out_frames[t], in_frames[t]);
+        if (targets && !plans[plan_index[t]].has_lufs)
+            return fail(h, B200M_ERR_INVALID, "track %d: a loudness sweep needs a plan with a loudness target (has_lufs)", t);
     }
+    int64_t out_total = 0;                      // frames of one packed copy of the batch output
+    for (int t = 0; t < n_tracks; ++t) out_total += out_frames[t];
     int rc = ensure_plans(h, plans, n_plans);
     if (rc) return rc;
     const bool in_dev = in_on_device != 0, out_dev = out_on_device != 0;
@@ -1192,7 +1218,7 @@ extern "C" int b200m_master_batch(b200m_handle *h, const void *pcm_in, int in_on
     // ---- cut the batch into groups ---------------------------------------------------------
     // a group must fit one workspace slot; with host buffers it is also at most ~1/8 of the batch
     // (and at least ~8 M frames) so that copies and kernels of neighbouring groups overlap
-    const double per_frame = ch * 2 * 3 + 4 + 3 * (ch * 2 + 2 + 8) + 2;
+    const double per_frame = ch * 2 * (2 + std::max(1, n_targets)) + 4 + 3 * (ch * 2 + 2 + 8) + 2;
     const double slot_limit = (double)h->ws_limit / slots;
     const double pipe_frames = pipelined ? std::max<double>(8e6, (double)total_frames / (double)h->pipe_groups) : 1e300;
     std::vector<GroupPlan> gps;
@@ -1209,7 +1235,7 @@ extern "C" int b200m_master_batch(b200m_handle *h, const void *pcm_in, int in_on
                 bytes += per_frame * f; fr += f; frames += out_frames[t1]; ++t1;
             }
             gps.emplace_back();
-            plan_group(h, gps.back(), in_dev, out_dev, t0, t1, in_offsets, in_frames, out_frames, plans, plan_index, out_base);
+            plan_group(h, gps.back(), in_dev, out_dev, t0, t1, in_offsets, in_frames, out_frames, plans, plan_index, out_base, targets ? n_targets : 0);
             out_base += frames;
             t0 = t1;
         }
@@ -1254,7 +1280,7 @@ extern "C" int b200m_master_batch(b200m_handle *h, const void *pcm_in, int in_on
             X.slot_free = X.h2d_done = X.comp_done = X.d2h_done = nullptr;
         }
         rc = exec_group(h, gp, h->ws + (i % slots) * max_need, h->pin + pin_off, X, (const int16_t *)pcm_in, in_dev, in_offsets,
-                        in_frames, (int16_t *)pcm_out, out_dev);
+                        in_frames, (int16_t *)pcm_out, out_dev, nullptr, targets, out_total);
         h->stream = own;
         if (rc) break;
         pin_off += gp.pin_bytes;
@@ -1279,11 +1305,35 @@ extern "C" int b200m_master_batch(b200m_handle *h, const void *pcm_in, int in_on
             for (int t = gp.t_begin; t < gp.t_end; ++t) {
                 const bool has = gp.F > 0;
                 if (loudness_out) loudness_out[t] = has ? hl[t - gp.t_begin].x : NAN;
-                if (gain_out) gain_out[t] = has ? hl[t - gp.t_begin].y : 1.0;
+                if (gain_out && !targets) gain_out[t] = has ? hl[t - gp.t_begin].y : 1.0;
+                if (gain_out && targets)
+                    for (int k = 0; k < n_targets; ++k)
+                        gain_out[(size_t)k * n_tracks + t] = has ? hl[(size_t)(1 + k) * gp.g.n_tracks + (t - gp.t_begin)].y : 1.0;
             }
         }
     }
     return B200M_OK;
+}
+
+extern "C" int b200m_master_batch(b200m_handle *h, const void *pcm_in, int in_on_device, int fmt, int n_tracks,
+                                  const int64_t *in_offsets, const int64_t *in_frames, const int64_t *out_frames,
+                                  const b200m_plan *plans, int n_plans, const int32_t *plan_index,
+                                  void *pcm_out, int out_on_device, double *loudness_out, double *gain_out)
+{
+    return master_batch_impl(h, pcm_in, in_on_device, fmt, n_tracks, in_offsets, in_frames, out_frames, plans, n_plans, plan_index,
+                             nullptr, 0, pcm_out, out_on_device, loudness_out, gain_out);
+}
+
+extern "C" int b200m_master_batch_targets(b200m_handle *h, const void *pcm_in, int in_on_device, int fmt, int n_tracks,
+                                          const int64_t *in_offsets, const int64_t *in_frames, const int64_t *out_frames,
+                                          const b200m_plan *plans, int n_plans, const int32_t *plan_index,
+                                          const double *targets, int n_targets,
+                                          void *pcm_out, int out_on_device, double *loudness_out, double *gain_out)
+{
+    if (!h) return B200M_ERR_INVALID;
+    if (!targets || n_targets <= 0 || n_targets > 64) return fail(h, B200M_ERR_INVALID, "b200m_master_batch_targets: 1..64 loudness targets");
+    return master_batch_impl(h, pcm_in, in_on_device, fmt, n_tracks, in_offsets, in_frames, out_frames, plans, n_plans, plan_index,
+                             targets, n_targets, pcm_out, out_on_device, loudness_out, gain_out);
 }
 
 // ------------------------------------------------------------------------------------

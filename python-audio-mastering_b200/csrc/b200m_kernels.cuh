@@ -1596,6 +1596,18 @@ k_gate(const TrackDesc *__restrict__ tracks, const PlanDev *__restrict__ plans,
     }
 }
 
+// k_regain: the gain of ENG:219-220 for ANOTHER loudness target of the same measurement (a sweep over
+// targets shares everything ahead of ENG:84): out[t] = {lufs[t], 10^((target - lufs[t]) / 20)}, the
+// expression k_gate evaluates for the plan's own target.
+__global__ void k_regain(const double2 *__restrict__ loud, int n_tracks, double target, double2 *__restrict__ out)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < n_tracks) {
+        const double lufs = loud[t].x;
+        out[t] = make_double2(lufs, pow(10.0, (target - lufs) / 20.0));
+    }
+}
+
 // =====================================================================================
 // k_final: re-float the processed track (ENG:82), one gain (ENG:222, float64 because the
 // loudness is a numpy float64 scalar), rational soft limiter (ENG:224-227), quantise #3

@@ -66,6 +66,45 @@ def main():
         res["multiband_on" if mb else "multiband_off"] = {
             "ms_per_step": ms, "clips_per_s": args.clips / (ms * 1e-3), "rtf": args.clips * SECONDS / (ms * 1e-3),
             "hbm_frac_8B_per_frame": 8.0 * args.clips * n / (ms * 1e-3) / 1e9 / 6450.6}
+    # The full grid on every clip (each clip x 4 presets x 3 targets): 12 outputs per clip.  Without sharing that
+    # is 12 whole chains per clip; b200m_master_batch_targets runs ENG:46-82 + the loudness measurement once
+    # per (clip, preset) and only gain / limiter / final cast per target.
+    gclips = max(1, args.clips // 12)
+    g_in = d_in[:gclips].repeat(4, 1, 1).contiguous()                # clip-major within a preset: preset p owns rows p*gclips ..
+    g_offs = [i * n for i in range(4 * gclips)]
+    g_fr, g_of = [n] * (4 * gclips), [ms_framing(n, RATE)] * (4 * gclips)
+    g_out = torch.empty((3,) + tuple(g_in.shape), dtype=torch.int16, device="cuda")
+    for mb in (False, True):
+        gplans = [make_plan(dict(PRESETS[p], saturation=25, width=1.2, multiband=mb, lufs=TARGETS[0]), RATE, 2) for p in range(4)]
+        gidx = [i // gclips for i in range(4 * gclips)]
+        g_sep = torch.empty_like(g_in)
+
+        def shared():
+            eng.master_raw(g_in, True, g_offs, g_fr, g_of, gplans, gidx, g_out, True, want_loudness=False, targets=TARGETS)
+
+        def separate():
+            for t in TARGETS:
+                pl = [make_plan(dict(PRESETS[p], saturation=25, width=1.2, multiband=mb, lufs=t), RATE, 2) for p in range(4)]
+                eng.master_raw(g_in, True, g_offs, g_fr, g_of, pl, gidx, g_sep, True, want_loudness=False)
+
+        out = {}
+        for name, fn in (("shared", shared), ("separate", separate)):
+            for _ in range(max(args.warmup, 1)):
+                fn()
+            eng.synchronize(); torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(args.steps):
+                fn()
+            eng.synchronize()
+            e1.record(); torch.cuda.synchronize()
+            out[name + "_ms_per_step"] = e0.elapsed_time(e1) / args.steps
+        separate()
+        eng.synchronize()
+        out["last_target_identical"] = bool(torch.equal(g_out[2], g_sep))
+        out["outputs"] = 12 * gclips
+        out["outputs_per_s_shared"] = 12 * gclips / (out["shared_ms_per_step"] * 1e-3)
+        res["grid_multiband_on" if mb else "grid_multiband_off"] = out
     print(json.dumps({"metric": "audio-sec mastered/sec (RTF)", "unit": "audio-s/s", "n_gpus": 1, "steps": args.steps,
                       "config": {"workload": f"cfg5: {args.clips} x 30-s 48 kHz s16 stereo clips, 4 presets x 3 loudness targets "
                                              "(12 plans in one batch), exciter 25% + width 1.2 + limiter"}, **res}))

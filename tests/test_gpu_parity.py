@@ -313,3 +313,21 @@ def test_ragged_unaligned_batch(eng, rate, channels):
                 assert abs(i["loudness"] - info["loudness"]) <= 1e-12
     finally:
         eng.set_chain_kernel(0)
+
+
+def test_loudness_sweep_shares_the_chain(eng):
+    """b200m_master_batch_targets: one chain + one loudness measurement per track, gain /
+    limiter / final cast per target -- bit-identical to one whole run per target, host-pipelined path."""
+    from b200master import synth
+    rate = 48000
+    st = dict(bass_boost=2.0, presence_boost=3.5, treble_boost=2.5, saturation=15, width=1.1, multiband=True)
+    tracks = [synth.make_track(90, 31.0, rate), synth.make_track(91, 2.25, rate), synth.make_track(92, 12.0, rate)]
+    targets = [-9.0, -14.0, -23.0]
+    outs, infos = eng.master_targets(tracks, rate, st, targets)
+    for k, tgt in enumerate(targets):
+        ref, rinfo = eng.master(tracks, rate, dict(st, lufs=tgt))
+        for t in range(len(tracks)):
+            assert np.array_equal(outs[k][t], ref[t]), f"target {tgt}, track {t}"
+            assert infos[t]["loudness"] == rinfo[t]["loudness"] and infos[t]["gain"][k] == rinfo[t]["gain"]
+    with pytest.raises(ValueError):
+        eng.master_targets(tracks, rate, st, [])            # the C-ABI wants 1..64 targets
