@@ -192,6 +192,23 @@ int b200m_master_batch_targets(b200m_handle *h,
                                void *pcm_out, int out_on_device,
                                double *loudness_out, double *gain_out);
 
+/* ENG:96-99 `mastered.export(buffer, format="wav")` folded into the batch: every track's output
+ * is a complete RIFF/WAVE file image -- the 44-byte header pydub's writer (the stdlib wave module: PCM, 16 bit)
+ * emits, written by the GPU immediately ahead of the samples -- so the host writes or uploads the span
+ * [44 bytes before the track's first sample, its last sample] as it is, without another sweep over the PCM.
+ *   out_offsets [n_tracks] first FRAME of each track's samples inside `out` (host); ascending, each track
+ *               preceded by >= 44 free bytes (11 stereo / 22 mono frames) after the end of the previous one;
+ *               samples that start at multiples of 16 bytes take the fast store path of the final kernel.
+ * Everything else as b200m_master_batch.  b200m_wav_header writes the same 44 bytes on the host. */
+int b200m_master_batch_wav(b200m_handle *h,
+                           const void *pcm_in, int in_on_device, int fmt,
+                           int n_tracks, const int64_t *in_offsets, const int64_t *in_frames,
+                           const int64_t *out_frames,
+                           const b200m_plan *plans, int n_plans, const int32_t *plan_index,
+                           const int64_t *out_offsets, void *out, int out_on_device,
+                           double *loudness_out, double *gain_out);
+int b200m_wav_header(int sample_rate, int channels, int64_t frames, unsigned char *out44);
+
 /* ---- one long track split along time over several GPUs (BASELINE config 4) ---------
  * Slices are cut at 30-s chunk boundaries (ENG:48-54: every filter and compressor restarts
  * there), so ENG:48-80 is local to a slice.  Only the loudness measurement (ENG:82-86,

@@ -80,6 +80,21 @@ def master_segments(segs, settings, device: int = 0):
     return out
 
 
+def master_segments_wav(segs, settings, device: int = 0):
+    """``master_segments`` with the WAV export (ENG:96-99) folded into the GPU batch: returns, per
+    segment, the bytes ``export(format="wav")`` would write (``b200m_master_batch_wav``: headers written
+    on the device ahead of the samples, no host pass over the PCM)."""
+    segs = list(segs)
+    groups, out = {}, [None] * len(segs)
+    for i, s in enumerate(segs):
+        groups.setdefault((s.frame_rate, s.channels), []).append(i)
+    for (rate, _ch), idx in groups.items():
+        images, _ = get_engine(device).master_wav([_segment_pcm(segs[i]) for i in idx], rate, settings)
+        for i, img in zip(idx, images):
+            out[i] = img
+    return out
+
+
 def process_audio_from_gcs(gcs_uri, settings):
     """ENG:24-113: download from GCS, master on the GPU, upload ``processed/mastered_<name>``
     and its ``.complete`` marker.  Exceptions propagate to the caller (ENG:110-113)."""
@@ -146,9 +161,15 @@ def batch_process_audio(settings, input_folder, output_folder, status_callback=N
         cls = segment_class()
         segs = [cls.from_file(os.path.join(input_folder, n)) for n in names]
         say(f"Mastering {len(segs)} files on the GPU...")
-        outs = master_segments(segs, settings)
-        for n, seg in zip(names, outs):
-            _export(seg, os.path.join(output_folder, f"mastered_{n}"))
+        if all(n.lower().endswith(".wav") for n in names):
+            # WAV in, WAV out: the GPU returns complete file images
+            for n, img in zip(names, master_segments_wav(segs, settings)):
+                with open(os.path.join(output_folder, f"mastered_{n}"), "wb") as f:
+                    f.write(img)
+        else:
+            outs = master_segments(segs, settings)
+            for n, seg in zip(names, outs):
+                _export(seg, os.path.join(output_folder, f"mastered_{n}"))
         say(f"Batch processing complete: {len(names)} files.")
     except Exception as e:
         say(f"Error: {e}")

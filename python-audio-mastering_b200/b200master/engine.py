@@ -167,6 +167,56 @@ class Engine:
             pos += n
         return outs, infos
 
+    def master_wav(self, tracks, rate: int, settings):
+        """``master`` with ENG:96-99 folded in: returns (list of uint8 arrays, each a complete RIFF/WAVE
+        file image = what ``export(format="wav")`` would write, views into ONE host buffer; infos).
+        The GPU writes the 44-byte headers ahead of the samples; nothing sweeps the PCM on the host."""
+        tracks = list(tracks)
+        if not tracks:
+            return [], []
+        ch = 1 if tracks[0].ndim == 1 else tracks[0].shape[1]
+        sets = [settings] * len(tracks) if isinstance(settings, dict) else list(settings)
+        plans, index, keys = [], [], {}
+        for s in sets:
+            k = repr(sorted((s or {}).items(), key=lambda kv: kv[0]))
+            if k not in keys:
+                keys[k] = len(plans)
+                plans.append(make_plan(s, rate, ch))
+            index.append(keys[k])
+        n = len(tracks)
+        fw = 2 * ch                                            # bytes per frame
+        in_frames = [int(t.shape[0]) for t in tracks]
+        out_frames = [ms_framing(f, rate) for f in in_frames]
+        # layout: samples start at multiples of 16 bytes, the header sits in the 44 bytes before them
+        offs, pos = [], 0
+        for f in out_frames:
+            start = (pos + 44 + 15) // 16 * 16
+            offs.append(start // fw)
+            pos = start + f * fw
+        buf = np.zeros(pos, dtype=np.uint8)
+        flat = np.ascontiguousarray(np.concatenate([np.ascontiguousarray(t, dtype=np.int16).reshape(-1) for t in tracks]))
+        off = np.ascontiguousarray(np.concatenate([[0], np.cumsum(in_frames)[:-1]]), dtype=np.int64)
+        inf = np.ascontiguousarray(in_frames, dtype=np.int64)
+        outf = np.ascontiguousarray(out_frames, dtype=np.int64)
+        oo = np.ascontiguousarray(offs, dtype=np.int64)
+        pidx = np.ascontiguousarray(index, dtype=np.int32)
+        loud, gain = np.empty(n, dtype=np.float64), np.empty(n, dtype=np.float64)
+        parr = (L.Plan * len(plans))(*plans)
+        self._ck(self._lib.b200m_master_batch_wav(
+            self._h, C.c_void_p(flat.ctypes.data), 0, L.FMT_S16, n, C.c_void_p(off.ctypes.data), C.c_void_p(inf.ctypes.data),
+            C.c_void_p(outf.ctypes.data), parr, len(plans), C.c_void_p(pidx.ctypes.data),
+            C.c_void_p(oo.ctypes.data), C.c_void_p(buf.ctypes.data), 0,
+            C.c_void_p(loud.ctypes.data), C.c_void_p(gain.ctypes.data)))
+        images = [buf[o * fw - 44:(o + f) * fw] for o, f in zip(offs, out_frames)]
+        infos = [{"loudness": float(loud[i]) if plans[index[i]].has_lufs else None,
+                  "gain": float(gain[i]) if plans[index[i]].has_lufs else None} for i in range(n)]
+        return images, infos
+
+    def wav_header(self, rate: int, channels: int, frames: int) -> bytes:
+        out = (C.c_ubyte * 44)()
+        self._ck(self._lib.b200m_wav_header(int(rate), int(channels), int(frames), out))
+        return bytes(out)
+
     def master_targets(self, tracks, rate: int, settings, targets):
         """``master`` for several loudness targets at once (a preset x loudness sweep): the chain and
         the loudness measurement run once per track, gain / limiter / final cast once per target.

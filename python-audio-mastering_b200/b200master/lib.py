@@ -48,7 +48,7 @@ _lib = None
 EXPORTS = [
     "b200m_abi_version", "b200m_create", "b200m_destroy", "b200m_last_error", "b200m_set_stream",
     "b200m_synchronize", "b200m_set_workspace_limit", "b200m_launch_count", "b200m_set_profiling",
-    "b200m_kernel_time_ms", "b200m_reset_profile", "b200m_set_recur_tiling", "b200m_recur_stats", "b200m_set_segment_tiles", "b200m_set_pipeline", "b200m_set_chain_kernel", "b200m_set_pipeline_shape", "b200m_plan_from_settings", "b200m_master_batch", "b200m_master_batch_targets",
+    "b200m_kernel_time_ms", "b200m_reset_profile", "b200m_set_recur_tiling", "b200m_recur_stats", "b200m_set_segment_tiles", "b200m_set_pipeline", "b200m_set_chain_kernel", "b200m_set_pipeline_shape", "b200m_plan_from_settings", "b200m_master_batch", "b200m_master_batch_targets", "b200m_master_batch_wav", "b200m_wav_header",
     "b200m_pcm16_to_float", "b200m_float_to_pcm16", "b200m_saturation", "b200m_stereo_width",
     "b200m_sosfilt", "b200m_multiband", "b200m_compress_dynamic_range", "b200m_integrated_loudness",
     "b200m_normalize_to_lufs", "b200m_soft_limiter",
@@ -93,6 +93,9 @@ def load():
                                        C.POINTER(Plan), C.c_int, vp, vp, C.c_int, vp, vp]
     lib.b200m_master_batch_targets.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, vp, vp, vp,
                                                C.POINTER(Plan), C.c_int, vp, vp, C.c_int, vp, C.c_int, vp, vp]
+    lib.b200m_master_batch_wav.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, vp, vp, vp,
+                                           C.POINTER(Plan), C.c_int, vp, vp, vp, C.c_int, vp, vp]
+    lib.b200m_wav_header.argtypes = [C.c_int, C.c_int, i64, vp]
     lib.b200m_pcm16_to_float.argtypes = [vp, vp, i64, vp]
     lib.b200m_float_to_pcm16.argtypes = [vp, vp, C.c_int, i64, vp]
     lib.b200m_saturation.argtypes = [vp, vp, i64, dbl, vp]

@@ -948,13 +948,19 @@ struct GroupPlan {
     int64_t F = 0, Fp = 0, in_total = 0, zoff = 0, out_base = 0;      // F: workspace frames (aligned track starts), Fp: packed output frames
     size_t desc_bytes = 0, res_off = 0, pin_bytes = 0, need = 0;
     int n_targets = 0;               // > 0: loudness sweep (b200m_master_batch_targets): that many outputs per track
+    bool wav = false;                // b200m_master_batch_wav: a 44-byte RIFF header ahead of every track's samples
 };
 
 static void plan_group(const b200m_handle *h, GroupPlan &gp, bool in_dev, bool out_dev, int t_begin, int t_end,
                        const int64_t *in_offsets, const int64_t *in_frames, const int64_t *out_frames,
-                       const b200m_plan *plans, const int32_t *plan_index, int64_t out_base, int n_targets = 0)
+                       const b200m_plan *plans, const int32_t *plan_index, int64_t out_base, int n_targets = 0,
+                       const int64_t *out_offsets = nullptr)
 {
     gp.n_targets = n_targets;
+    gp.wav = out_offsets != nullptr;
+    // WAV images: the group's span of the output starts at the header of its first track
+    const int64_t hdr = out_offsets ? 44 / (plans[0].channels * 2) : 0;
+    if (out_offsets) out_base = out_offsets[t_begin] - hdr;
     const size_t outs = (size_t)std::max(1, n_targets);
     const int ch = plans[0].channels, rate = plans[0].sample_rate;
     const int64_t chunk = 30LL * rate;          // ENG:48: 30 000 ms -> int(ms * rate / 1000) frames
@@ -968,7 +974,7 @@ static void plan_group(const b200m_handle *h, GroupPlan &gp, bool in_dev, bool o
         const b200m_plan &p = plans[plan_index[t]];
         TrackDesc &td = gp.tracks[t - t_begin];
         F = (F + 31) & ~(int64_t)31;            // workspace rows of the compressor are moved in aligned 4-byte pieces
-        td.off = F; td.dst_off = Fp; td.frames = out_frames[t]; td.plan = plan_index[t];
+        td.off = F; td.dst_off = out_offsets ? out_offsets[t] - out_base : Fp; td.frames = out_frames[t]; td.plan = plan_index[t];
         td.abs0 = 0; td.total_frames = out_frames[t]; td.j0 = 0; td.pad_ = 0;
         td.nblocks = p.has_lufs ? num_blocks(out_frames[t], rate) : 0;
         td.zoff = zoff; zoff += td.nblocks;
@@ -991,7 +997,7 @@ static void plan_group(const b200m_handle *h, GroupPlan &gp, bool in_dev, bool o
             gp.streams.push_back(sd);
         }
         F += out_frames[t];
-        Fp += out_frames[t];
+        Fp = out_offsets ? out_offsets[t] - out_base + out_frames[t] : Fp + out_frames[t];
         in_total += in_frames[t];
     }
     g.n_streams = (int)gp.streams.size();
@@ -1040,7 +1046,7 @@ static void plan_group(const b200m_handle *h, GroupPlan &gp, bool in_dev, bool o
     size_t need = 16384 + gp.desc_bytes + (size_t)g.n_tracks * 16 * (1 + (size_t)n_targets) + (size_t)F * ch * 2 /*proc*/ + (size_t)F * 4 /*kw*/ +
                   (size_t)zoff * 16 + 25 * 256;
     if (!in_dev) need += (size_t)in_total * ch * 2;
-    if (!out_dev) need += (size_t)Fp * ch * 2 * outs + 256 * outs;
+    if (!out_dev) need += (size_t)Fp * ch * 2 * outs + 256 * outs + 256;
     if (g.any_multiband) need += (size_t)F * 3 * ch * 2 + 3 * 256 + compressor_ws_bytes(h, g, F, 3);
     gp.need = (need + 1023) & ~(size_t)1023;
 }
@@ -1077,7 +1083,12 @@ static int exec_group(b200m_handle *h, GroupPlan &gp, char *ws, char *pin, const
     int16_t *d_in = nullptr, *d_out = nullptr;
     if (!in_dev) d_in = A.take<int16_t>((size_t)gp.in_total * ch);
     const size_t out_stride = ((size_t)gp.Fp * ch + 127) & ~(size_t)127;                    // samples between the staged copies (256-byte aligned)
-    if (!out_dev) d_out = A.take<int16_t>(out_stride * n_out);
+    if (!out_dev) {
+        d_out = A.take<int16_t>(out_stride * n_out + 8);
+        // WAV images: the staged span starts at a header, i.e. anywhere; keep the device address congruent to the
+        // host offset modulo 16 bytes so that samples the caller aligned stay aligned for k_final's 16-byte stores
+        if (gp.wav) d_out += ((gp.out_base * ch * 2) & 15) / 2;
+    }
     BandPtrs bp;
     double *d_spec = nullptr;
     std::memset(&bp, 0, sizeof bp);
@@ -1157,6 +1168,7 @@ static int exec_group(b200m_handle *h, GroupPlan &gp, char *ws, char *pin, const
         if (ch == 2) LAUNCH("k_final", k_final<2><<<gf, 256, 0, h->stream>>>(d_proc, d_tracks, h->d_plans, loud_k, dst_k));
         else         LAUNCH("k_final", k_final<1><<<gf, 256, 0, h->stream>>>(d_proc, d_tracks, h->d_plans, loud_k, dst_k));
     }
+    if (gp.wav) LAUNCH("k_wav_headers", k_wav_headers<<<(g.n_tracks + 127) / 128, 128, 0, h->stream>>>(d_tracks, h->d_plans, g.n_tracks, ch, d_dst));
     CK(cudaGetLastError());
     if (X.comp_done) { CK(cudaEventRecord(X.comp_done, X.comp)); CK(cudaStreamWaitEvent(X.out, X.comp_done, 0)); }
 
@@ -1183,7 +1195,7 @@ static cudaEvent_t sync_event(b200m_handle *h, size_t i)
 static int master_batch_impl(b200m_handle *h, const void *pcm_in, int in_on_device, int fmt, int n_tracks,
                              const int64_t *in_offsets, const int64_t *in_frames, const int64_t *out_frames,
                              const b200m_plan *plans, int n_plans, const int32_t *plan_index,
-                             const double *targets, int n_targets,
+                             const double *targets, int n_targets, const int64_t *out_offsets,
                              void *pcm_out, int out_on_device, double *loudness_out, double *gain_out)
 {
     if (!h) return B200M_ERR_INVALID;
@@ -1209,6 +1221,16 @@ static int master_batch_impl(b200m_handle *h, const void *pcm_in, int in_on_devi
     }
     int64_t out_total = 0;                      // frames of one packed copy of the batch output
     for (int t = 0; t < n_tracks; ++t) out_total += out_frames[t];
+    if (out_offsets) {                          // WAV images: room for a header ahead of every track, tracks in ascending order
+        const int64_t hdr = 44 / (ch * 2);
+        for (int t = 0; t < n_tracks; ++t) {
+            const int64_t prev_end = t ? out_offsets[t - 1] + out_frames[t - 1] : 0;
+            if (out_offsets[t] < prev_end + hdr)
+                return fail(h, B200M_ERR_INVALID, "out_offsets[%d]: needs 44 free bytes after the end of the previous track", t);
+            if ((uint64_t)out_frames[t] * ch * 2 > 0xffffffffull - 36)
+                return fail(h, B200M_ERR_INVALID, "track %d does not fit a RIFF file (4 GiB)", t);
+        }
+    }
     int rc = ensure_plans(h, plans, n_plans);
     if (rc) return rc;
     const bool in_dev = in_on_device != 0, out_dev = out_on_device != 0;
@@ -1235,7 +1257,8 @@ static int master_batch_impl(b200m_handle *h, const void *pcm_in, int in_on_devi
                 bytes += per_frame * f; fr += f; frames += out_frames[t1]; ++t1;
             }
             gps.emplace_back();
-            plan_group(h, gps.back(), in_dev, out_dev, t0, t1, in_offsets, in_frames, out_frames, plans, plan_index, out_base, targets ? n_targets : 0);
+            plan_group(h, gps.back(), in_dev, out_dev, t0, t1, in_offsets, in_frames, out_frames, plans, plan_index, out_base, targets ? n_targets : 0,
+                       out_offsets);
             out_base += frames;
             t0 = t1;
         }
@@ -1321,7 +1344,7 @@ extern "C" int b200m_master_batch(b200m_handle *h, const void *pcm_in, int in_on
                                   void *pcm_out, int out_on_device, double *loudness_out, double *gain_out)
 {
     return master_batch_impl(h, pcm_in, in_on_device, fmt, n_tracks, in_offsets, in_frames, out_frames, plans, n_plans, plan_index,
-                             nullptr, 0, pcm_out, out_on_device, loudness_out, gain_out);
+                             nullptr, 0, nullptr, pcm_out, out_on_device, loudness_out, gain_out);
 }
 
 extern "C" int b200m_master_batch_targets(b200m_handle *h, const void *pcm_in, int in_on_device, int fmt, int n_tracks,
@@ -1333,7 +1356,30 @@ extern "C" int b200m_master_batch_targets(b200m_handle *h, const void *pcm_in, i
     if (!h) return B200M_ERR_INVALID;
     if (!targets || n_targets <= 0 || n_targets > 64) return fail(h, B200M_ERR_INVALID, "b200m_master_batch_targets: 1..64 loudness targets");
     return master_batch_impl(h, pcm_in, in_on_device, fmt, n_tracks, in_offsets, in_frames, out_frames, plans, n_plans, plan_index,
-                             targets, n_targets, pcm_out, out_on_device, loudness_out, gain_out);
+                             targets, n_targets, nullptr, pcm_out, out_on_device, loudness_out, gain_out);
+}
+
+extern "C" int b200m_master_batch_wav(b200m_handle *h, const void *pcm_in, int in_on_device, int fmt, int n_tracks,
+                                      const int64_t *in_offsets, const int64_t *in_frames, const int64_t *out_frames,
+                                      const b200m_plan *plans, int n_plans, const int32_t *plan_index,
+                                      const int64_t *out_offsets, void *out, int out_on_device,
+                                      double *loudness_out, double *gain_out)
+{
+    if (!h) return B200M_ERR_INVALID;
+    if (!out_offsets) return fail(h, B200M_ERR_INVALID, "b200m_master_batch_wav: out_offsets is required");
+    return master_batch_impl(h, pcm_in, in_on_device, fmt, n_tracks, in_offsets, in_frames, out_frames, plans, n_plans, plan_index,
+                             nullptr, 0, out_offsets, out, out_on_device, loudness_out, gain_out);
+}
+
+extern "C" int b200m_wav_header(int sample_rate, int channels, int64_t frames, unsigned char *out44)
+{
+    if (!out44 || sample_rate <= 0 || (channels != 1 && channels != 2) || frames < 0 || (uint64_t)frames * channels * 2 > 0xffffffffull - 36)
+        return B200M_ERR_INVALID;
+    const uint32_t bytes = (uint32_t)(frames * channels * 2);
+    const uint32_t w[11] = {0x46464952u, 36u + bytes, 0x45564157u, 0x20746d66u, 16u, 1u | ((uint32_t)channels << 16), (uint32_t)sample_rate,
+                            (uint32_t)sample_rate * channels * 2u, ((uint32_t)channels * 2u) | (16u << 16), 0x61746164u, bytes};
+    std::memcpy(out44, w, 44);
+    return B200M_OK;
 }
 
 // ------------------------------------------------------------------------------------

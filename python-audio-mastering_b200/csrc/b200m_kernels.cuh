@@ -1596,6 +1596,31 @@ k_gate(const TrackDesc *__restrict__ tracks, const PlanDev *__restrict__ plans,
     }
 }
 
+// k_wav_headers: ENG:96-99 `export(format="wav")` folded into the batch.  pydub hands the samples to the
+// stdlib wave module, whose file is the canonical 44-byte RIFF/WAVE header (PCM, 16 bit) followed by the
+// data; the header of every track is written immediately ahead of its samples in the output buffer, so a
+// track's file image is one contiguous span that the host writes out (or uploads) as it is.
+__global__ void k_wav_headers(const TrackDesc *__restrict__ tracks, const PlanDev *__restrict__ plans, int n_tracks, int ch,
+                              int16_t *__restrict__ out)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_tracks) return;
+    const TrackDesc td = tracks[t];
+    const unsigned rate = (unsigned)plans[td.plan].rate, bytes = (unsigned)(td.frames * ch * 2);
+    unsigned *hd = reinterpret_cast<unsigned *>(out + td.dst_off * ch) - 11;      // 44 bytes ahead of the first sample (4-byte aligned)
+    hd[0] = 0x46464952u;                         // "RIFF"
+    hd[1] = 36u + bytes;
+    hd[2] = 0x45564157u;                         // "WAVE"
+    hd[3] = 0x20746d66u;                         // "fmt "
+    hd[4] = 16u;
+    hd[5] = 1u | ((unsigned)ch << 16);           // WAVE_FORMAT_PCM, channels
+    hd[6] = rate;
+    hd[7] = rate * (unsigned)ch * 2u;            // bytes per second
+    hd[8] = ((unsigned)ch * 2u) | (16u << 16);   // block align, bits per sample
+    hd[9] = 0x61746164u;                         // "data"
+    hd[10] = bytes;
+}
+
 // k_regain: the gain of ENG:219-220 for ANOTHER loudness target of the same measurement (a sweep over
 // targets shares everything ahead of ENG:84): out[t] = {lufs[t], 10^((target - lufs[t]) / 20)}, the
 // expression k_gate evaluates for the plan's own target.

@@ -331,3 +331,24 @@ def test_loudness_sweep_shares_the_chain(eng):
             assert infos[t]["loudness"] == rinfo[t]["loudness"] and infos[t]["gain"][k] == rinfo[t]["gain"]
     with pytest.raises(ValueError):
         eng.master_targets(tracks, rate, st, [])            # the C-ABI wants 1..64 targets
+
+
+def test_wav_images_match_the_wave_module(eng):
+    """b200m_master_batch_wav (ENG:96-99): every track comes back as the exact bytes
+    ``export(format="wav")`` writes (pydub -> stdlib wave: 44-byte header + samples), headers written by
+    the GPU, samples identical to the plain batch call; stereo and mono, ragged lengths."""
+    import io
+    from b200master import synth
+    from b200master.segment import PcmSegment
+    rate = 44100
+    st = dict(bass_boost=2.0, presence_boost=3.5, saturation=10, width=1.2, multiband=True, lufs=-14.0)
+    for ch in (2, 1):
+        tracks = [synth.make_track(95 + i, s, rate, ch) for i, s in enumerate([3.0, 31.5, 0.75])]
+        tracks[1] = tracks[1][:-3]
+        images, infos = eng.master_wav(tracks, rate, st)
+        outs, rinfos = eng.master(tracks, rate, st)
+        for img, o, i, ri in zip(images, outs, infos, rinfos):
+            f = io.BytesIO()
+            PcmSegment(o.tobytes(), 2, rate, ch).export(f, format="wav")
+            assert bytes(img) == f.getvalue()
+            assert i == ri

@@ -152,3 +152,23 @@ def test_struct_layouts_match_the_header(tmp_path):
     sizes = [int(v) for v in subprocess.check_output([str(exe)]).split()]
     assert sizes == [C.sizeof(L.Plan), C.sizeof(L.Band), C.sizeof(L.Biquad), C.sizeof(L.Settings)]
     assert sizes[0] == 576
+
+
+def test_wav_header_is_the_wave_modules():
+    """b200m_wav_header (host side of b200m_master_batch_wav): the 44 bytes the stdlib wave module writes
+    for 16-bit PCM, which is what pydub's export(format="wav") emits (ENG:96-99).  No device work."""
+    import ctypes as C
+    import io
+    import wave
+    from b200master import lib as L
+    lib = L.load()
+    for rate, ch, frames in [(44100, 2, 0), (48000, 2, 1440000), (96000, 1, 12345), (8000, 1, 1)]:
+        out = (C.c_ubyte * 44)()
+        assert lib.b200m_wav_header(rate, ch, frames, out) == 0
+        f = io.BytesIO()
+        with wave.open(f, "wb") as w:
+            w.setnchannels(ch); w.setsampwidth(2); w.setframerate(rate)
+            w.writeframesraw(b"\0" * (frames * ch * 2))
+        assert bytes(out) == f.getvalue()[:44]
+    assert lib.b200m_wav_header(44100, 3, 10, (C.c_ubyte * 44)()) != 0
+    assert lib.b200m_wav_header(44100, 2, 1 << 31, (C.c_ubyte * 44)()) != 0      # does not fit a RIFF file
