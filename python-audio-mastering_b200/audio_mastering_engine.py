@@ -12,6 +12,7 @@ built library and a CUDA device and raises otherwise.
 Reference surface mirrored here
     EQ_PRESETS                                     ENG:15-20
     process_audio_from_gcs(gcs_uri, settings)      ENG:24-113
+    process_audio_batch_from_gcs(jobs)             the same for several worker jobs in one GPU batch (extension)
     process_audio(settings, status_callback)       called at GUI:204 (absent from the snapshot)
     batch_process_audio(settings, in, out, cb)     called at GUI:220 (absent from the snapshot)
     audio_segment_to_float_array ... soft_limiter  ENG:117-227 (ten helpers)
@@ -98,26 +99,46 @@ def master_segments_wav(segs, settings, device: int = 0):
 def process_audio_from_gcs(gcs_uri, settings):
     """ENG:24-113: download from GCS, master on the GPU, upload ``processed/mastered_<name>``
     and its ``.complete`` marker.  Exceptions propagate to the caller (ENG:110-113)."""
+    process_audio_batch_from_gcs([(gcs_uri, settings)])
+
+
+def process_audio_batch_from_gcs(jobs):
+    """Several worker jobs in ONE GPU batch: ``jobs`` is a sequence of
+    ``(gcs_uri, settings)`` as ``worker/main.py:39`` receives them one by one.  Every object is
+    downloaded and decoded on the host (ENG:27-43), all tracks are mastered together with their own
+    settings, and each result is uploaded like ENG:91-108: the WAV image comes straight from the GPU
+    batch (``b200m_master_batch_wav``), then the ``.complete`` marker.  Exceptions propagate (ENG:110-113)."""
+    jobs = list(jobs)
     try:
         from google.cloud import storage
         client = storage.Client()
-        print(f"Fetching {gcs_uri} ...")
-        bucket_name, blob_name = gcs_uri.replace("gs://", "").split("/", 1)
-        bucket = client.bucket(bucket_name)
-        src = io.BytesIO()
-        bucket.blob(blob_name).download_to_file(src)
-        src.seek(0)
-        audio = segment_class().from_file(src)
-        print("Decoded; mastering on the GPU ...")
-        mastered = master_segment(audio, settings)
-        target = f"processed/mastered_{os.path.basename(blob_name)}"
-        print(f"Encoding and uploading {target} ...")
-        dst = io.BytesIO()
-        mastered.export(dst, format="wav")
-        dst.seek(0)
-        bucket.blob(target).upload_from_file(dst, content_type="audio/wav")
-        bucket.blob(f"{target}.complete").upload_from_string("")
-        print(f"Done: {target}.complete written.")
+        decoded = []
+        for gcs_uri, _settings in jobs:
+            print(f"Fetching {gcs_uri} ...")
+            bucket_name, blob_name = gcs_uri.replace("gs://", "").split("/", 1)
+            bucket = client.bucket(bucket_name)
+            src = io.BytesIO()
+            bucket.blob(blob_name).download_to_file(src)
+            src.seek(0)
+            decoded.append((bucket, blob_name, segment_class().from_file(src)))
+        print(f"Decoded {len(decoded)} object(s); mastering on the GPU ...")
+        groups = {}
+        for i, (_b, _n, seg) in enumerate(decoded):
+            groups.setdefault((seg.frame_rate, seg.channels), []).append(i)
+        images = [None] * len(jobs)
+        for (rate, _ch), idx in groups.items():
+            res, infos = get_engine().master_wav([_segment_pcm(decoded[i][2]) for i in idx], rate, [jobs[i][1] for i in idx])
+            for i, img, info in zip(idx, res, infos):
+                images[i] = img
+                if info.get("loudness") is not None:
+                    print(f"{decoded[i][1]}: measured {info['loudness']:.2f} LUFS; applied "
+                          f"{jobs[i][1].get('lufs') - info['loudness']:.2f} dB of gain.")
+        for (bucket, blob_name, _seg), img in zip(decoded, images):
+            target = f"processed/mastered_{os.path.basename(blob_name)}"
+            print(f"Uploading {target} ...")
+            bucket.blob(target).upload_from_file(io.BytesIO(img.tobytes()), content_type="audio/wav")
+            bucket.blob(f"{target}.complete").upload_from_string("")
+            print(f"Done: {target}.complete written.")
     except Exception as e:
         print(f"FATAL ERROR in mastering engine: {e}")
         raise

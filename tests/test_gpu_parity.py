@@ -352,3 +352,60 @@ def test_wav_images_match_the_wave_module(eng):
             PcmSegment(o.tobytes(), 2, rate, ch).export(f, format="wav")
             assert bytes(img) == f.getvalue()
             assert i == ri
+
+
+def test_worker_jobs_share_one_batch(eng, monkeypatch):
+    """process_audio_from_gcs / process_audio_batch_from_gcs (WRK:39, ENG:24-113) against an
+    in-memory google.cloud.storage: object naming, the .complete marker, WAV bytes equal to the
+    per-track path's export, per-job settings inside one batch."""
+    import io
+    import sys
+    import types
+    import audio_mastering_engine as ame
+    from b200master import synth
+    from b200master.segment import PcmSegment
+
+    store = {}
+
+    class Blob:
+        def __init__(self, key): self.key = key
+        def download_to_file(self, f): f.write(store[self.key])
+        def upload_from_file(self, f, content_type=None): store[self.key] = f.read()
+        def upload_from_string(self, s): store[self.key] = s.encode() if isinstance(s, str) else s
+
+    class Bucket:
+        def __init__(self, name): self.name = name
+        def blob(self, key): return Blob(f"{self.name}/{key}")
+
+    class Client:
+        def bucket(self, name): return Bucket(name)
+
+    google, cloud, storage = types.ModuleType("google"), types.ModuleType("google.cloud"), types.ModuleType("google.cloud.storage")
+    storage.Client = Client
+    cloud.storage = storage
+    google.cloud = cloud
+    for k, m in (("google", google), ("google.cloud", cloud), ("google.cloud.storage", storage)):
+        monkeypatch.setitem(sys.modules, k, m)
+    monkeypatch.setattr(ame, "segment_class", lambda: PcmSegment)
+
+    rate = 44100
+    jobs = []
+    for i, st in enumerate([dict(ame.EQ_PRESETS["pop"], lufs=-14.0), dict(ame.EQ_PRESETS["rock"], multiband=True, width=1.2, lufs=-9.0)]):
+        st.pop("description")
+        f = io.BytesIO()
+        PcmSegment(synth.make_track(97 + i, 2.0 + i, rate).tobytes(), 2, rate, 2).export(f, format="wav")
+        store[f"bkt/uploads/song{i}.wav"] = f.getvalue()
+        jobs.append((f"gs://bkt/uploads/song{i}.wav", st))
+    ame.process_audio_batch_from_gcs(jobs)
+    for i, (uri, st) in enumerate(jobs):
+        key = f"bkt/processed/mastered_song{i}.wav"
+        assert store[key + ".complete"] == b""
+        ref = ame.master_segment(PcmSegment.from_file(io.BytesIO(store[f"bkt/uploads/song{i}.wav"])), st)
+        g = io.BytesIO()
+        ref.export(g, format="wav")
+        assert store[key] == g.getvalue()
+    batch0 = store["bkt/processed/mastered_song0.wav"]
+    ame.process_audio_from_gcs(*jobs[0])                    # the single-job entry point is the batch of one
+    assert store["bkt/processed/mastered_song0.wav"] == batch0
+    with pytest.raises(KeyError):
+        ame.process_audio_from_gcs("gs://bkt/uploads/missing.wav", jobs[0][1])      # exceptions propagate (ENG:110-113)
