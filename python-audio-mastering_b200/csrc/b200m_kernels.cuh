@@ -686,32 +686,53 @@ k_detect(const StreamDesc *__restrict__ streams, const PlanDev *__restrict__ pla
     // ---- phase 1: frame energies, four frames per load (coalesced 16 / 8-byte pieces) -----------
     const int16_t *__restrict__ src = bp.band[band] + sd.out_off * CH;
     const bool vec = (reinterpret_cast<unsigned long long>(src) & (CH == 2 ? 15ull : 7ull)) == 0;   // chunk starts at odd rates may not be
-    for (int g = tid; g * 4 < R * DNT; g += DNT) {
-        const int k = g * 4, f = t0 - HP + k;       // f is a multiple of 4: a group never straddles frame 0
-        uint4 ev = make_uint4(0u, 0u, 0u, 0u);
-        if (k < ET && f >= 0 && f < sd.out_frames) {
-            if (!vec) {
-                unsigned t[4] = {0u, 0u, 0u, 0u};
+    if (vec) {
+        // four groups per thread and round: all four loads are issued before the first energy is formed
+        for (int g0 = tid; g0 * 4 < R * DNT; g0 += 4 * DNT) {
+            uint4 q[4];
+            bool ok[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int g = g0 + u * DNT, k = g * 4, f = t0 - HP + k;       // f is a multiple of 4: a group never straddles frame 0
+                ok[u] = k < R * DNT && k < ET && f >= 0 && f < sd.out_frames;
+                q[u] = make_uint4(0u, 0u, 0u, 0u);
+                if (ok[u]) {
+                    if (CH == 2) q[u] = __ldg(reinterpret_cast<const uint4 *>(src + (int64_t)f * 2));
+                    else { const uint2 h2 = __ldg(reinterpret_cast<const uint2 *>(src + f)); q[u].x = h2.x; q[u].y = h2.y; }
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int g = g0 + u * DNT, k = g * 4, f = t0 - HP + k;
+                if (k >= R * DNT) break;
+                uint4 ev = make_uint4(0u, 0u, 0u, 0u);
+                if (ok[u]) {
+                    if (CH == 2) {
+                        ev = make_uint4(energy2(q[u].x), energy2(q[u].y), energy2(q[u].z), energy2(q[u].w));
+                    } else {
+                        const int s0 = (int)(short)(q[u].x & 0xffffu), s1 = (int)q[u].x >> 16, s2 = (int)(short)(q[u].y & 0xffffu), s3 = (int)q[u].y >> 16;
+                        ev = make_uint4((unsigned)(s0 * s0), (unsigned)(s1 * s1), (unsigned)(s2 * s2), (unsigned)(s3 * s3));
+                    }
+                    if (f + 3 >= sd.out_frames) {           // the stream ends inside this group
+                        if (f + 1 >= sd.out_frames) ev.y = 0u;
+                        if (f + 2 >= sd.out_frames) ev.z = 0u;
+                        ev.w = 0u;
+                    }
+                }
+                reinterpret_cast<uint4 *>(e)[g] = ev;
+            }
+        }
+    } else {
+        for (int g = tid; g * 4 < R * DNT; g += DNT) {
+            const int k = g * 4, f = t0 - HP + k;
+            unsigned t[4] = {0u, 0u, 0u, 0u};
+            if (k < ET && f >= 0)
                 for (int i = 0; i < 4 && f + i < sd.out_frames; ++i) {
                     if (CH == 2) t[i] = energy2(*reinterpret_cast<const unsigned *>(src + (int64_t)(f + i) * 2));
                     else { const int v = src[f + i]; t[i] = (unsigned)(v * v); }
                 }
-                ev = make_uint4(t[0], t[1], t[2], t[3]);
-            } else if (CH == 2) {
-                const uint4 q = __ldg(reinterpret_cast<const uint4 *>(src + (int64_t)f * 2));
-                ev = make_uint4(energy2(q.x), energy2(q.y), energy2(q.z), energy2(q.w));
-            } else {
-                const uint2 q = __ldg(reinterpret_cast<const uint2 *>(src + f));
-                const int s0 = (int)(short)(q.x & 0xffffu), s1 = (int)q.x >> 16, s2 = (int)(short)(q.y & 0xffffu), s3 = (int)q.y >> 16;
-                ev = make_uint4((unsigned)(s0 * s0), (unsigned)(s1 * s1), (unsigned)(s2 * s2), (unsigned)(s3 * s3));
-            }
-            if (f + 3 >= sd.out_frames) {           // the stream ends inside this group
-                if (f + 1 >= sd.out_frames) ev.y = 0u;
-                if (f + 2 >= sd.out_frames) ev.z = 0u;
-                ev.w = 0u;
-            }
+            reinterpret_cast<uint4 *>(e)[g] = make_uint4(t[0], t[1], t[2], t[3]);
         }
-        reinterpret_cast<uint4 *>(e)[g] = ev;
     }
     if (tid < DT / 1024) sbits[tid] = 0xffffffffu;                 // blocks past the end count as held
     __syncthreads();
@@ -887,12 +908,12 @@ __device__ __forceinline__ double recur_step_pos(double a, double M, double inc,
     return p ? vu : vd;
 }
 
-// audioop.mul: floor(fbound(sample * factor)), fbound clipping to [-32768, 32767] ("val < minval + 1
-// -> minval").  Clipping the floored integer instead is the same function: for val in
-// (-32768, -32767) both give -32768, above 32767 both give 32767; F2I.FLOOR saturates.
-__device__ __forceinline__ int mul_floor16(int v, double g)
+// audioop.mul: floor(fbound(sample * factor)), fbound clipping to [-32768, 32767].  The factor here is a
+// gain in [0, 1] -- the attenuation is never negative (the recurrence clamps at +0) and exp10_gain(x <= 0)
+// <= 1 -- so |v g| <= |v| <= 32768 and the floor is in range without the clip.
+__device__ __forceinline__ int mul_floor16_le1(int v, double g)
 {
-    return max(-32768, min(32767, __double2int_rd(__dmul_rn((double)v, g))));
+    return __double2int_rd(__dmul_rn((double)v, g));
 }
 
 __global__ void __launch_bounds__(32 * RW)
@@ -1217,8 +1238,8 @@ __device__ __forceinline__ void apply_frame(int &acc0, int &acc1, unsigned smp, 
     // pydub multiplies only `if attenuation != 0.0`; exp10_gain(0) is exactly 1.0 (the polynomial at
     // r = 0 is its constant term) and floor(v * 1.0) == v, so the test needs no branch
     const double g = exp10_gain(a * -0.05);         // db_to_float(-att) = 10 ** (-att / 20)
-    v0 = mul_floor16(v0, g);
-    if (CH == 2) v1 = mul_floor16(v1, g);
+    v0 = mul_floor16_le1(v0, g);
+    if (CH == 2) v1 = mul_floor16_le1(v1, g);
     acc0 = first ? v0 : max(-32768, min(32767, acc0 + v0));
     if (CH == 2) acc1 = first ? v1 : max(-32768, min(32767, acc1 + v1));
 }
