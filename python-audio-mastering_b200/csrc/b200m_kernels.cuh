@@ -1345,10 +1345,52 @@ k_kweight(const IN *__restrict__ src_all, const TrackDesc *__restrict__ tracks, 
     float *__restrict__ dst = kw + td.off;
     float *myx = sx + tid * (SEG + 1);
     unsigned round = 0;
-    for (int64_t t0 = max((int64_t)0, sg.begin - sg.warm); t0 < sg.end; t0 += KTILE) {
+    // Whole tiles inside the track come in with cp.async (16-byte pieces, BPF per thread) while the tile before
+    // is filtered; every thread converts exactly the pieces it fetched, so cp.async.wait_group is the only
+    // synchronisation the staging needs.  The last, partial tile (and unaligned sources) are read directly.
+    constexpr int BPF = (int)sizeof(IN) * CH, FPP = 16 / BPF;       // bytes per frame, frames per piece
+    unsigned char *sraw = reinterpret_cast<unsigned char *>(wtot + 2 * 8 * 2);     // [KTILE * BPF], 16-byte aligned
+    const bool al = (reinterpret_cast<unsigned long long>(src) & 15ull) == 0;
+    auto staged = [&](int64_t t0) { return al && t0 + KTILE <= td.frames; };
+    auto fetch = [&](int64_t t0) {
+        if (staged(t0)) {
+            const unsigned char *g = reinterpret_cast<const unsigned char *>(src) + t0 * BPF;
+#pragma unroll
+            for (int k = 0; k < BPF; ++k) {
+                const int p = tid + k * KNT;
+                const unsigned sa = (unsigned)__cvta_generic_to_shared(sraw + 16 * p);
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(g + 16 * p) : "memory");
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    const int64_t t_first = max((int64_t)0, sg.begin - sg.warm);
+    fetch(t_first);
+    for (int64_t t0 = t_first; t0 < sg.end; t0 += KTILE) {
         const bool store = t0 >= sg.begin;           // warm-up tiles only advance the filter states
         const int nload = (int)min((int64_t)KTILE, td.frames - t0);
         const int nvalid = store ? (int)min((int64_t)KTILE, sg.end - t0) : 0;
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        if (staged(t0)) {
+#pragma unroll
+            for (int k = 0; k < BPF; ++k) {
+                const int p = tid + k * KNT, f0 = p * FPP;
+                const uint4 w = *reinterpret_cast<const uint4 *>(sraw + 16 * p);
+                const unsigned ww[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    if (sizeof(IN) == 2 && CH == 2) {
+                        // float32 (vL + vR) / 2 with vL, vR multiples of 2^-15: exact
+                        sx[pidx(f0 + i)] = (float)((int)(short)(ww[i] & 0xffffu) + ((int)ww[i] >> 16)) * (1.0f / 65536.0f);
+                    } else if (sizeof(IN) == 2) {
+                        sx[pidx(f0 + 2 * i)] = (float)(int)(short)(ww[i] & 0xffffu) * (1.0f / 32768.0f);
+                        sx[pidx(f0 + 2 * i + 1)] = (float)((int)ww[i] >> 16) * (1.0f / 32768.0f);
+                    } else {
+                        sx[pidx(f0 + i)] = __uint_as_float(ww[i]);
+                    }
+                }
+            }
+        } else
         for (int f = tid; f < KTILE; f += KNT) {
             float m = 0.0f;
             if (f < nload) {
@@ -1367,6 +1409,7 @@ k_kweight(const IN *__restrict__ src_all, const TrackDesc *__restrict__ tracks, 
             }
             sx[pidx(f)] = m;
         }
+        if (t0 + KTILE < sg.end) fetch(t0 + KTILE);  // this thread's pieces of sraw are consumed: the next tile may land
         __syncthreads();
         double x[SEG];
 #pragma unroll
@@ -1385,7 +1428,7 @@ k_kweight(const IN *__restrict__ src_all, const TrackDesc *__restrict__ tracks, 
 
 constexpr size_t kweight_smem_bytes()
 {
-    return 2 * sizeof(SecTab) + (size_t)(KTILE_PAD + (KTILE_PAD & 1)) * 4 + 4 * 8 + 2 * 8 * 2 * 8;
+    return 2 * sizeof(SecTab) + (size_t)(KTILE_PAD + (KTILE_PAD & 1)) * 4 + 4 * 8 + 2 * 8 * 2 * 8 + (size_t)KTILE * 4 /* raw tile */;
 }
 
 // =====================================================================================
