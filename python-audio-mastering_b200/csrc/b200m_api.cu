@@ -1155,7 +1155,7 @@ static int exec_group(b200m_handle *h, GroupPlan &gp, char *ws, char *pin, const
     if (ext_proc) return B200M_OK;
     rc = launch_loudness(h, g, d_proc, nullptr, d_kw, d_z, d_zsel, d_loud);
     if (rc) return rc;
-    const dim3 gf((unsigned)std::min<int64_t>((g.max_track_frames + 1023) / 1024, 8192), g.n_tracks);   // four frames per thread
+    const dim3 gf((unsigned)std::min<int64_t>((g.max_track_frames + 2047) / 2048, 8192), g.n_tracks);   // two vectors of four frames per thread
     for (int k = 0; k < n_out; ++k) {
         const double2 *loud_k = d_loud;
         int16_t *dst_k = d_dst;
@@ -1574,7 +1574,7 @@ extern "C" int b200m_slice_final(b200m_handle *h, const int16_t *proc_dev, int64
     const double2 lg = make_double2(0.0, gain);
     CK(cudaMemcpyAsync(d_tracks, &td, sizeof td, cudaMemcpyHostToDevice, h->stream));
     CK(cudaMemcpyAsync(d_loud, &lg, sizeof lg, cudaMemcpyHostToDevice, h->stream));
-    const dim3 gf((unsigned)std::min<int64_t>((frames + 1023) / 1024, 8192 * 4), 1);
+    const dim3 gf((unsigned)std::min<int64_t>((frames + 2047) / 2048, 8192 * 4), 1);
     if (p.channels == 2) LAUNCH("k_final", k_final<2><<<gf, 256, 0, h->stream>>>(proc_dev, d_tracks, h->d_plans, d_loud, out_dev));
     else                 LAUNCH("k_final", k_final<1><<<gf, 256, 0, h->stream>>>(proc_dev, d_tracks, h->d_plans, d_loud, out_dev));
     CK(cudaGetLastError());

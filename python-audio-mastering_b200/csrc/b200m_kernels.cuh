@@ -1520,7 +1520,7 @@ __device__ __forceinline__ float pw_tree_eval(const float *__restrict__ y, const
         const int lim = cnt - (cnt % 8);
         float v0 = p[k];
         float acc = __fmul_rn(v0, v0);
-#pragma unroll 4
+#pragma unroll 8
         for (int i = 8; i < lim; i += 8) {
             const float v = p[i + k];
             acc = __fadd_rn(acc, __fmul_rn(v, v));
@@ -1765,17 +1765,27 @@ k_final(const int16_t *__restrict__ proc, const TrackDesc *__restrict__ tracks,
     // starts always are, packed output starts are when the preceding tracks have multiples of 8 / CH frames
     const bool vec = ((reinterpret_cast<unsigned long long>(src) | reinterpret_cast<unsigned long long>(dst)) & 15ull) == 0;
     const int64_t nvec = vec ? nsamp / 8 : 0;
-    for (int64_t g = (int64_t)blockIdx.x * 256 + threadIdx.x; g < nvec; g += (int64_t)gridDim.x * 256) {
-        const uint4 w = __ldg(reinterpret_cast<const uint4 *>(src) + g);
-        const unsigned in[4] = {w.x, w.y, w.z, w.w};
-        unsigned o[4];
+    const int64_t stride = (int64_t)gridDim.x * 256;
+    for (int64_t g = (int64_t)blockIdx.x * 256 + threadIdx.x; g < nvec; g += 2 * stride) {
+        // two vectors per thread and round, both loads in flight before the first sample is touched
+        const int64_t g2 = g + stride;
+        const bool second = g2 < nvec;
+        uint4 w[2];
+        w[0] = __ldg(reinterpret_cast<const uint4 *>(src) + g);
+        w[1] = second ? __ldg(reinterpret_cast<const uint4 *>(src) + g2) : make_uint4(0u, 0u, 0u, 0u);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const int r0 = final_sample((int)(short)(in[k] & 0xffffu), has, gain);
-            const int r1 = final_sample((int)in[k] >> 16, has, gain);
-            o[k] = (unsigned)(r0 & 0xffff) | ((unsigned)r1 << 16);
+        for (int v = 0; v < 2; ++v) {
+            if (v == 1 && !second) break;
+            const unsigned in[4] = {w[v].x, w[v].y, w[v].z, w[v].w};
+            unsigned o[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int r0 = final_sample((int)(short)(in[k] & 0xffffu), has, gain);
+                const int r1 = final_sample((int)in[k] >> 16, has, gain);
+                o[k] = (unsigned)(r0 & 0xffff) | ((unsigned)r1 << 16);
+            }
+            reinterpret_cast<uint4 *>(dst)[v ? g2 : g] = make_uint4(o[0], o[1], o[2], o[3]);
         }
-        reinterpret_cast<uint4 *>(dst)[g] = make_uint4(o[0], o[1], o[2], o[3]);
     }
     for (int64_t i = nvec * 8 + (int64_t)blockIdx.x * 256 + threadIdx.x; i < nsamp; i += (int64_t)gridDim.x * 256)
         dst[i] = (int16_t)final_sample((int)src[i], has, gain);
