@@ -863,8 +863,9 @@ constexpr int RW = 4;               // warps per CTA in k_recur_tiles
 struct RecurWarpSmem {
     double m[32][33];               // M rows in (phase B), attenuation rows out (phase C -> D)
     uint16_t rms[32][32];           // RMS rows
-    unsigned long long base_curve[32], base_att[32];
-    int2 blk[32];                   // per lane: {first frame of its current block, frames to store (0 = warm-up)}
+    unsigned long long base_curve[32];
+    ulonglong2 row[32];             // per lane: {where its current block's attenuation row goes, frames to store (0 = warm-up)}:
+                                    // one 16-byte broadcast load per row in phase D (shared memory is this kernel's busiest unit)
 };
 constexpr size_t recur_smem_bytes() { return RW * sizeof(RecurWarpSmem); }
 
@@ -934,7 +935,7 @@ k_recur_tiles(const StreamDesc *__restrict__ streams, const PlanDev *__restrict_
     double A = 1.0, R = 1.0, rA = 1.0, rR = 1.0;
     bool exact = true;
     double a = 0.0;
-    W.base_curve[lane] = 0; W.base_att[lane] = 0;
+    W.base_curve[lane] = 0;
     const uint16_t *my_rms = nullptr;
     if (live) {
         const int s = chain / P.nbands, band = P.band_base + chain % P.nbands;
@@ -948,7 +949,6 @@ k_recur_tiles(const StreamDesc *__restrict__ streams, const PlanDev *__restrict_
             attp = bp.att[band] + sd.out_off;
             my_rms = bp.rms[band] + sd.out_off;
             W.base_curve[lane] = (unsigned long long)pl->curve[band];
-            W.base_att[lane] = (unsigned long long)attp;
             const BandDev &bd = pl->band[band];
             A = bd.attack_frames; R = bd.release_frames; rA = bd.r_attack; rR = bd.r_release;
             exact = bd.div_trick != 0;
@@ -1056,7 +1056,7 @@ k_recur_tiles(const StreamDesc *__restrict__ streams, const PlanDev *__restrict_
         // the value this tile stored earlier at the end of this block (repair rounds only)
         double old_last = 0.0;
         if (P.mode == 1 && on) old_last = attp[i0 + cnt - 1];
-        W.blk[lane] = make_int2(i0, is_main ? cnt : 0);
+        W.row[lane] = make_ulonglong2((unsigned long long)(attp + i0), (unsigned long long)(is_main ? cnt : 0));
         const bool any_work = __any_sync(FULL, on && work);       // else every lane's block is held: att stays put
         asm volatile("cp.async.wait_group 0;" ::: "memory");
         __syncwarp();
@@ -1070,7 +1070,8 @@ k_recur_tiles(const StreamDesc *__restrict__ streams, const PlanDev *__restrict_
             double v[B200M_RECUR_GB];
 #pragma unroll
             for (int j = 0; j < B200M_RECUR_GB; ++j) {
-                const double *curve = reinterpret_cast<const double *>(W.base_curve[q0 + j]);
+                const ulonglong2 cp2 = *reinterpret_cast<const ulonglong2 *>(&W.base_curve[(q0 + j) & ~1]);   // one load serves two rows
+                const double *curve = reinterpret_cast<const double *>((j & 1) ? cp2.y : cp2.x);
                 const unsigned r = W.rms[q0 + j][lane];
                 v[j] = (curve != nullptr && r != 0u) ? __ldg(curve + r) : 0.0;
             }
@@ -1116,8 +1117,8 @@ k_recur_tiles(const StreamDesc *__restrict__ streams, const PlanDev *__restrict_
             __syncwarp();
 #pragma unroll 8
             for (int q = 0; q < 32; ++q) {
-                const int2 d = W.blk[q];
-                if (lane < d.y) reinterpret_cast<double *>(W.base_att[q])[d.x + lane] = W.m[q][lane];
+                const ulonglong2 d = W.row[q];
+                if (lane < (int)d.y) reinterpret_cast<double *>(d.x)[lane] = W.m[q][lane];
             }
         }
         if (P.mode == 1 && on && __double_as_longlong(a) == __double_as_longlong(old_last)) merged = true;

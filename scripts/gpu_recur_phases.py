@@ -1,4 +1,9 @@
-"""Per-phase cycles of k_recur_tiles (library built with -DB200M_RECUR_TIMING, loaded via B200M_LIB)."""
+"""Per-phase cycles of k_recur_tiles (library built with -DB200M_RECUR_TIMING, loaded via B200M_LIB):
+
+    cd python-audio-mastering_b200 && nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 \
+        -Xcompiler -fPIC -shared -DB200M_RECUR_TIMING -o lib/libb200master_rt.so csrc/b200m_api.cu
+    B200M_LIB=$PWD/lib/libb200master_rt.so python ../scripts/gpu_recur_phases.py 1 8 64
+"""
 import os, sys, ctypes as C
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "python-audio-mastering_b200"))
