@@ -196,6 +196,14 @@ def run_b200_arm(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback)")
     torch.cuda.set_device(local)
+    try:
+        # host side of the e2e leg: run (and pin host memory) on the CPUs next to this rank's GPU, so that the
+        # 2 x 2.2 GB per step of every rank stay off the inter-socket link
+        import pynvml
+        pynvml.nvmlInit()
+        pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(local))
+    except Exception:
+        pass
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")     # keep NCCL's banner off stdout: rank 0 prints ONE JSON line there
