@@ -617,8 +617,14 @@ k_chainw(const int16_t *__restrict__ pcm_in, const StreamDesc *__restrict__ stre
 // by difference, rms = (unsigned)sqrt(sum/n) reproduced as an integer square root.
 // grid = (tiles, streams, bands).
 // =====================================================================================
-constexpr int DT = 4096;        // frames per tile
-constexpr int DNT = 384;
+#ifndef B200M_DT
+#define B200M_DT 4096
+#endif
+#ifndef B200M_DNT
+#define B200M_DNT 384
+#endif
+constexpr int DT = B200M_DT;    // frames per tile
+constexpr int DNT = B200M_DNT;
 
 __device__ __forceinline__ unsigned window_rms_rn(unsigned long long S, unsigned n, float rn);
 __device__ __forceinline__ unsigned window_rms(unsigned long long S, unsigned n)
