@@ -428,8 +428,11 @@ __device__ __forceinline__ void store_q16_w(int16_t *__restrict__ dst, const int
     }
 }
 
+#ifndef B200M_CHAINW_OCC
+#define B200M_CHAINW_OCC 2
+#endif
 template <int CH, bool NANCHK>
-__global__ void __launch_bounds__(32 * CW_WARPS, 2)
+__global__ void __launch_bounds__(32 * CW_WARPS, B200M_CHAINW_OCC)
 k_chainw(const int16_t *__restrict__ pcm_in, const StreamDesc *__restrict__ streams, const SegDesc *__restrict__ segs, int n_segs,
          const PlanDev *__restrict__ plans, int16_t *__restrict__ proc, BandPtrs bp)
 {

