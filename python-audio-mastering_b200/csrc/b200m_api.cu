@@ -916,7 +916,7 @@ static int launch_loudness(b200m_handle *h, const Group &g, const int16_t *d_pro
         if (hops) LAUNCH("k_hops", k_hops<<<gh, BNT, (size_t)h->hops_smem_floats * 4 + 16, h->stream>>>(d_kw, g.d_tracks, h->d_plans, d_zsel));
         if (g.max_blocks > 0) LAUNCH("k_blocks", k_blocks<<<gb, BNT, (size_t)h->blocks_smem_floats * 4 + 16, h->stream>>>(d_kw, g.d_tracks, h->d_plans, hops ? d_zsel : nullptr, d_z));
     }
-    LAUNCH("k_gate", k_gate<<<g.n_tracks, 32, 0, h->stream>>>(g.d_tracks, h->d_plans, d_z, d_zsel, d_loud));
+    LAUNCH("k_gate", k_gate<<<g.n_tracks, GNT, 0, h->stream>>>(g.d_tracks, h->d_plans, d_z, d_zsel, d_loud));
     CK(cudaGetLastError());
     return B200M_OK;
 }
@@ -1544,7 +1544,7 @@ extern "C" int b200m_gate(b200m_handle *h, const double *z_dev, int32_t n_blocks
     double *d_zsel = A.take<double>(n_blocks + 1);
     TrackDesc td = {0, 0, 0, 0, n_blocks, 0, 0, 0, 0, 0};
     CK(cudaMemcpyAsync(d_tracks, &td, sizeof td, cudaMemcpyHostToDevice, h->stream));
-    LAUNCH("k_gate", k_gate<<<1, 32, 0, h->stream>>>(d_tracks, h->d_plans, z_dev, d_zsel, d_loud));
+    LAUNCH("k_gate", k_gate<<<1, GNT, 0, h->stream>>>(d_tracks, h->d_plans, z_dev, d_zsel, d_loud));
     CK(cudaGetLastError());
     double2 res;
     CK(cudaMemcpyAsync(&res, d_loud, sizeof res, cudaMemcpyDeviceToHost, h->stream));

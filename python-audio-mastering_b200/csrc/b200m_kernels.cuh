@@ -1475,10 +1475,12 @@ __device__ __forceinline__ T np_pairwise_leaf(Get get, int64_t off, int n)
     return res;
 }
 
-template <typename T, typename Get>
-__device__ T np_pairwise_sum(Get get, int64_t n)
+// The recursion itself, with the leaves (<= 128 elements) left to `leaf(offset, count)`: the same walk
+// enumerates the leaves, sums serially, or combines leaf sums that were computed in parallel.
+template <typename T, typename Leaf>
+__device__ T np_pairwise_walk(Leaf leaf, int64_t n)
 {
-    if (n <= 128) return np_pairwise_leaf<T>(get, 0, (int)n);
+    if (n <= 128) return leaf((int64_t)0, (int)n);
     int64_t s_off[40], s_n[40];
     T s_acc[40];
     int s_stage[40];
@@ -1486,7 +1488,7 @@ __device__ T np_pairwise_sum(Get get, int64_t n)
     s_off[0] = 0; s_n[0] = n; s_stage[0] = 0; s_acc[0] = (T)0;
     T ret = (T)0;
     while (sp >= 0) {
-        if (s_n[sp] <= 128) { ret = np_pairwise_leaf<T>(get, s_off[sp], (int)s_n[sp]); --sp; continue; }
+        if (s_n[sp] <= 128) { ret = leaf(s_off[sp], (int)s_n[sp]); --sp; continue; }
         int64_t n2 = s_n[sp] / 2;
         n2 -= n2 % 8;
         if (s_stage[sp] == 0) {
@@ -1500,6 +1502,12 @@ __device__ T np_pairwise_sum(Get get, int64_t n)
         }
     }
     return ret;
+}
+
+template <typename T, typename Get>
+__device__ T np_pairwise_sum(Get get, int64_t n)
+{
+    return np_pairwise_walk<T>([&](int64_t off, int cnt) { return np_pairwise_leaf<T>(get, off, cnt); }, n);
 }
 
 // =====================================================================================
@@ -1612,31 +1620,95 @@ k_blocks(const float *__restrict__ kw, const TrackDesc *__restrict__ tracks,
 
 // =====================================================================================
 // k_gate: absolute (-70 LUFS) and relative (-10 LU) gating over the block energies,
-// integrated loudness and the linear gain of ENG:219-220.  One CTA (one warp does the
-// ordered compaction, thread 0 the pairwise fp64 means) per track.
+// integrated loudness and the linear gain of ENG:219-220.  One CTA per track: block-wide ordered
+// compaction, gated means in numpy's pairwise order with the leaves summed in parallel (a 2-hour
+// track has 72 000 blocks).
 // out[track] = {loudness, gain}
 // =====================================================================================
-__global__ void __launch_bounds__(32)
+constexpr int GNT = 256;            // threads per track in k_gate
+constexpr int GLEV = 11;            // the pairwise tree of a gated mean is expanded this deep in parallel
+constexpr int GSLOTS = 1 << GLEV;   // 2048 leaf slots: up to 225 k gated blocks (6.2 h of audio), beyond that the serial walk
+
+// np.mean of sel[0 .. cnt) in numpy's pairwise order by the whole CTA.  The recursion (n > 128: n2 = n/2 -
+// (n/2) % 8, sum(n2) + sum(n - n2)) is expanded level by level in place: node i of level d lives in slot
+// i * 2^(GLEV-d); a split leaves its left child there and puts the right child half a stride further, a node
+// that is already a leaf just stays.  Then every slot with elements is summed like numpy's leaf (eight
+// accumulators), and the levels are folded back, adding a right child wherever a split created one -- the
+// additions of the sequential recursion, each exactly once and with the same operands.
+__device__ double gate_mean(const double *__restrict__ sel, int cnt, int *s_off, int *s_n, double *s_val)
+{
+    const int tid = threadIdx.x;
+    auto get = [sel](int64_t i) { return sel[i]; };
+    __shared__ double s_res;
+    if (cnt <= 0) return __longlong_as_double(0x7ff8000000000000LL);      // np.mean([]) -> nan
+    bool serial = cnt <= 128 || cnt > 110 * GSLOTS;        // 110 + 16 (rounding of eleven splits) <= 128
+    if (!serial) {
+        for (int i = tid; i < GSLOTS; i += GNT) { s_n[i] = 0; s_off[i] = 0; }
+        __syncthreads();
+        if (tid == 0) s_n[0] = cnt;
+        __syncthreads();
+        for (int d = 0; d < GLEV; ++d) {
+            const int S = GSLOTS >> d;
+            for (int p = tid * S; p < GSLOTS; p += GNT * S) {
+                const int n = s_n[p];
+                if (n > 128) {
+                    int n2 = n / 2;
+                    n2 -= n2 % 8;
+                    const int off = s_off[p];
+                    s_n[p] = n2;
+                    s_off[p + S / 2] = off + n2;
+                    s_n[p + S / 2] = n - n2;
+                }
+            }
+            __syncthreads();
+        }
+        bool big = false;
+        for (int i = tid; i < GSLOTS; i += GNT) {
+            const int n = s_n[i];
+            big |= n > 128;
+            if (n > 0 && n <= 128) s_val[i] = np_pairwise_leaf<double>(get, s_off[i], n);
+        }
+        serial = __syncthreads_or(big);                                   // deeper than GLEV levels (cannot happen below 110 * GSLOTS)
+        if (!serial) {
+            for (int d = GLEV - 1; d >= 0; --d) {
+                const int S = GSLOTS >> d;
+                for (int p = tid * S; p < GSLOTS; p += GNT * S)
+                    if (s_n[p + S / 2] > 0) s_val[p] = s_val[p] + s_val[p + S / 2];
+                __syncthreads();
+            }
+            if (tid == 0) s_res = s_val[0] / (double)cnt;
+        }
+    }
+    if (serial && tid == 0) s_res = np_pairwise_sum<double>(get, cnt) / (double)cnt;
+    __syncthreads();
+    const double r = s_res;
+    __syncthreads();
+    return r;
+}
+
+__global__ void __launch_bounds__(GNT)
 k_gate(const TrackDesc *__restrict__ tracks, const PlanDev *__restrict__ plans,
        const double *__restrict__ z, double *__restrict__ zsel, double2 *__restrict__ out)
 {
+    __shared__ int s_off[GSLOTS], s_n[GSLOTS], s_wcnt[GNT / 32];
+    __shared__ double s_val[GSLOTS];
     const TrackDesc td = tracks[blockIdx.x];
     const PlanDev *__restrict__ pl = plans + td.plan;
-    const int lane = threadIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     if (!pl->has_lufs) {
-        if (lane == 0) out[blockIdx.x] = make_double2(__longlong_as_double(0x7ff8000000000000LL), 1.0);
+        if (tid == 0) out[blockIdx.x] = make_double2(__longlong_as_double(0x7ff8000000000000LL), 1.0);
         return;
     }
     const double *__restrict__ zt = z + td.zoff;
     double *__restrict__ sel = zsel + td.zoff;
     const int nb = td.nblocks;
-    const double nan = __longlong_as_double(0x7ff8000000000000LL);
     double gamma_r = 0.0;
-    double mean = nan;
+    double mean = 0.0;
     for (int pass = 0; pass < 2; ++pass) {
+        // ordered compaction of the blocks that pass the gate (the order is what np.mean's pairwise tree sees)
         int cnt = 0;
-        for (int j0 = 0; j0 < nb; j0 += 32) {
-            const int j = j0 + lane;
+        for (int j0 = 0; j0 < nb; j0 += GNT) {
+            const int j = j0 + tid;
             bool keep = false;
             double zj = 0.0;
             if (j < nb) {
@@ -1645,24 +1717,19 @@ k_gate(const TrackDesc *__restrict__ tracks, const PlanDev *__restrict__ plans,
                 keep = pass == 0 ? (lj >= -70.0) : (lj > gamma_r && lj > -70.0);
             }
             const unsigned m = __ballot_sync(FULL, keep);
-            if (keep) sel[cnt + __popc(m & ((1u << lane) - 1u))] = zj;
-            cnt += __popc(m);
+            if (lane == 0) s_wcnt[wid] = __popc(m);
+            __syncthreads();
+            int off = cnt, tot = 0;
+#pragma unroll
+            for (int w = 0; w < GNT / 32; ++w) { if (w < wid) off += s_wcnt[w]; tot += s_wcnt[w]; }
+            if (keep) sel[off + __popc(m & ((1u << lane) - 1u))] = zj;
+            cnt += tot;
+            __syncthreads();
         }
-        __syncwarp();
-        if (lane == 0) {
-            if (cnt > 0) {
-                const double *s = sel;
-                auto get = [s](int64_t i) { return s[i]; };
-                mean = np_pairwise_sum<double>(get, cnt) / (double)cnt;
-            } else {
-                mean = nan;                     // np.mean([]) -> nan
-            }
-        }
-        mean = __shfl_sync(FULL, mean, 0);
+        mean = gate_mean(sel, cnt, s_off, s_n, s_val);
         if (pass == 0) gamma_r = __dsub_rn(__dadd_rn(-0.691, __dmul_rn(10.0, log10(mean))), 10.0);
-        __syncwarp();
     }
-    if (lane == 0) {
+    if (tid == 0) {
         if (mean != mean) mean = 0.0;           // np.nan_to_num
         const double lufs = __dadd_rn(-0.691, __dmul_rn(10.0, log10(mean)));
         const double gain = pow(10.0, (pl->lufs - lufs) / 20.0);

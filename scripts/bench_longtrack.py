@@ -56,6 +56,7 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=2)
     ap.add_argument("--check", action="store_true")
+    ap.add_argument("--profile", action="store_true", help="rank 0 prints the CUDA-event time of every kernel per step (stderr)")
     args = ap.parse_args()
     import torch.distributed as dist
     from b200master import Engine, longtrack
@@ -98,6 +99,15 @@ def main():
         t = torch.tensor([ms], device=f"cuda:{local}")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
+    if args.profile:
+        eng.set_profiling(True); eng.reset_profile()
+        step(); eng.synchronize()
+        if rank == 0:
+            for k in ["k_stage_s24", "k_chain", "k_detect", "k_recur_tiles", "k_recur_repair", "k_recur_fix", "k_apply", "k_kweight", "k_hops",
+                      "k_blocks", "k_gate", "k_final"]:
+                t, c = eng.kernel_time_ms(k)
+                print(f"{k:16s} {t:8.3f} ms ({c} launches)", file=sys.stderr)
+        eng.set_profiling(False)
     ok = None
     if args.check:
         # every rank rebuilds the WHOLE track in the 16-bit domain and masters it alone
