@@ -197,7 +197,8 @@ int b200m_master_batch_targets(b200m_handle *h,
  * emits, written by the GPU immediately ahead of the samples -- so the host writes or uploads the span
  * [44 bytes before the track's first sample, its last sample] as it is, without another sweep over the PCM.
  *   out_offsets [n_tracks] first FRAME of each track's samples inside `out` (host); ascending, each track
- *               preceded by >= 44 free bytes (11 stereo / 22 mono frames) after the end of the previous one;
+ *               preceded by >= 44 free bytes (11 stereo / 22 mono frames) after the end of the previous one and
+ *               starting at a multiple of 4 bytes (mono: an even frame);
  *               samples that start at multiples of 16 bytes take the fast store path of the final kernel.
  * Everything else as b200m_master_batch.  b200m_wav_header writes the same 44 bytes on the host. */
 int b200m_master_batch_wav(b200m_handle *h,

@@ -1227,6 +1227,8 @@ static int master_batch_impl(b200m_handle *h, const void *pcm_in, int in_on_devi
             const int64_t prev_end = t ? out_offsets[t - 1] + out_frames[t - 1] : 0;
             if (out_offsets[t] < prev_end + hdr)
                 return fail(h, B200M_ERR_INVALID, "out_offsets[%d]: needs 44 free bytes after the end of the previous track", t);
+            if ((out_offsets[t] * ch * 2) % 4 != 0)
+                return fail(h, B200M_ERR_INVALID, "out_offsets[%d]: samples (and with them the header) must start at a multiple of 4 bytes", t);
             if ((uint64_t)out_frames[t] * ch * 2 > 0xffffffffull - 36)
                 return fail(h, B200M_ERR_INVALID, "track %d does not fit a RIFF file (4 GiB)", t);
         }
