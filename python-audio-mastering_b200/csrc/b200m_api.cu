@@ -634,10 +634,14 @@ extern "C" int b200m_create(int device, b200m_handle **out)
     if (e == cudaSuccess) e = allow_smem(k_chain<2, true>, chain_smem_bytes<2>());
     if (e == cudaSuccess) e = allow_smem(k_chain<1, false>, chain_smem_bytes<1>());
     if (e == cudaSuccess) e = allow_smem(k_chain<2, false>, chain_smem_bytes<2>());
-    if (e == cudaSuccess) e = allow_smem(k_chainw<1, true>, ChainW<1>::SMEM);
-    if (e == cudaSuccess) e = allow_smem(k_chainw<1, false>, ChainW<1>::SMEM);
-    if (e == cudaSuccess) e = allow_smem(k_chainw<2, true>, ChainW<2>::SMEM);
-    if (e == cudaSuccess) e = allow_smem(k_chainw<2, false>, ChainW<2>::SMEM);
+    if (e == cudaSuccess) e = allow_smem(k_chainw<1, true, true>, ChainW<1>::SMEM);
+    if (e == cudaSuccess) e = allow_smem(k_chainw<1, false, true>, ChainW<1>::SMEM);
+    if (e == cudaSuccess) e = allow_smem(k_chainw<2, true, true>, ChainW<2>::SMEM);
+    if (e == cudaSuccess) e = allow_smem(k_chainw<2, false, true>, ChainW<2>::SMEM);
+    if (e == cudaSuccess) e = allow_smem(k_chainw<1, true, false>, ChainW<1>::SMEM);
+    if (e == cudaSuccess) e = allow_smem(k_chainw<1, false, false>, ChainW<1>::SMEM);
+    if (e == cudaSuccess) e = allow_smem(k_chainw<2, true, false>, ChainW<2>::SMEM);
+    if (e == cudaSuccess) e = allow_smem(k_chainw<2, false, false>, ChainW<2>::SMEM);
     if (e == cudaSuccess) e = allow_smem(k_detect<1>, detect_smem_bytes(8192));
     if (e == cudaSuccess) e = allow_smem(k_detect<2>, detect_smem_bytes(8192));
     if (e == cudaSuccess) e = allow_smem(k_recur_tiles, recur_smem_bytes());
@@ -819,6 +823,7 @@ struct Group {
     const SegDesc *d_csegs = nullptr, *d_ksegs = nullptr;   // k_chain / k_kweight segments
     int n_csegs = 0, n_ksegs = 0;
     bool chain_warps = false;        // csegs are warp segments (k_chainw), padded to eight per CTA
+    int single_plan = -1;            // >= 0: every stream of the group uses this plan (its tables travel as a kernel parameter)
 };
 
 static RecurParams recur_params(const b200m_handle *h, const Group &g, int nbands, int band_base)
@@ -1001,6 +1006,8 @@ static void plan_group(const b200m_handle *h, GroupPlan &gp, bool in_dev, bool o
         in_total += in_frames[t];
     }
     g.n_streams = (int)gp.streams.size();
+    g.single_plan = gp.streams.empty() ? -1 : gp.streams[0].plan;
+    for (auto &sd : gp.streams) if (sd.plan != g.single_plan) g.single_plan = -1;
     {
         int64_t ctiles = 0, ktiles = 0;
         for (auto &sd : gp.streams) ctiles += (sd.out_frames + TILE - 1) / TILE;
@@ -1135,13 +1142,29 @@ static int exec_group(b200m_handle *h, GroupPlan &gp, char *ws, char *pin, const
     // ---- kernels (all on the handle's stream) ------------------------------------------------
     if (g.chain_warps) {
         const int nb = g.n_csegs / CW_WARPS;
-        if (ch == 2) {
-            if (g.chain_stable) LAUNCH("k_chain", k_chainw<2, false><<<nb, 32 * CW_WARPS, ChainW<2>::SMEM, h->stream>>>(d_src, d_streams, d_csegs, g.n_csegs, h->d_plans, d_proc, bp));
-            else                LAUNCH("k_chain", k_chainw<2, true><<<nb, 32 * CW_WARPS, ChainW<2>::SMEM, h->stream>>>(d_src, d_streams, d_csegs, g.n_csegs, h->d_plans, d_proc, bp));
-        } else {
-            if (g.chain_stable) LAUNCH("k_chain", k_chainw<1, false><<<nb, 32 * CW_WARPS, ChainW<1>::SMEM, h->stream>>>(d_src, d_streams, d_csegs, g.n_csegs, h->d_plans, d_proc, bp));
-            else                LAUNCH("k_chain", k_chainw<1, true><<<nb, 32 * CW_WARPS, ChainW<1>::SMEM, h->stream>>>(d_src, d_streams, d_csegs, g.n_csegs, h->d_plans, d_proc, bp));
+        ChainTabsC ct;                           // 3.6 KB, copied into the launch parameter buffer by the runtime
+        const bool pt = g.single_plan >= 0;
+        if (pt) {
+            const PlanDev &pd = h->plans_host[g.single_plan];
+            const SecTab *src[8] = {&pd.eq[0], &pd.eq[1], &pd.eq[2], &pd.eq[3], &pd.lp[0], &pd.lp[1], &pd.hp[0], &pd.hp[1]};
+            for (int s8 = 0; s8 < 8; ++s8) {
+                SecTabC &d = ct.sec[s8];
+                d.b0 = src[s8]->b0; d.b1 = src[s8]->b1; d.b2 = src[s8]->b2; d.a1 = src[s8]->a1; d.a2 = src[s8]->a2;
+                std::memcpy(d.g, src[s8]->g, sizeof d.g);
+                std::memcpy(d.P, src[s8]->P, sizeof d.P);
+            }
         }
+#define LAUNCH_CHAINW(CHN, NAN_, PT_) \
+        LAUNCH("k_chain", k_chainw<CHN, NAN_, PT_><<<nb, 32 * CW_WARPS, ChainW<CHN>::SMEM, h->stream>>>(d_src, d_streams, d_csegs, g.n_csegs, h->d_plans, d_proc, bp, ct))
+        const bool nanchk = !g.chain_stable;
+        if (ch == 2) {
+            if (pt) { if (nanchk) LAUNCH_CHAINW(2, true, true); else LAUNCH_CHAINW(2, false, true); }
+            else    { if (nanchk) LAUNCH_CHAINW(2, true, false); else LAUNCH_CHAINW(2, false, false); }
+        } else {
+            if (pt) { if (nanchk) LAUNCH_CHAINW(1, true, true); else LAUNCH_CHAINW(1, false, true); }
+            else    { if (nanchk) LAUNCH_CHAINW(1, true, false); else LAUNCH_CHAINW(1, false, false); }
+        }
+#undef LAUNCH_CHAINW
     } else if (ch == 2) {
         if (g.chain_stable) LAUNCH("k_chain", k_chain<2, false><<<g.n_csegs, NSEG * 2, chain_smem_bytes<2>(), h->stream>>>(d_src, d_streams, d_csegs, h->d_plans, d_proc, bp));
         else                LAUNCH("k_chain", k_chain<2, true><<<g.n_csegs, NSEG * 2, chain_smem_bytes<2>(), h->stream>>>(d_src, d_streams, d_csegs, h->d_plans, d_proc, bp));

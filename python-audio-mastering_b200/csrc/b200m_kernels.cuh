@@ -288,12 +288,27 @@ template <int CH> struct ChainW {
     static constexpr size_t SMEM = 8 * sizeof(SecTab) + CW_WARPS * WARP_BYTES;
 };
 
+// The lane-independent part of a SecTab, passed BY VALUE as a kernel parameter when the whole launch
+// uses one plan: kernel parameters live in the constant bank, so every table entry is a constant-bank
+// operand of the DFMA that uses it -- no load instruction, and nothing on the shared-memory / shuffle
+// data pipe, which is the busiest unit of this kernel (65 % of peak with the tables in shared memory).
+// Only Q[lane] (lane-dependent) still comes from the shared-memory copy.
+struct SecTabC {
+    double b0, b1, b2, a1, a2;
+    double g[SEG][2];
+    double P[5][4];
+};
+struct ChainTabsC { SecTabC sec[8]; };       // eq[4] lp[2] hp[2]: 3648 bytes
+static_assert(sizeof(ChainTabsC) <= 3800, "ChainTabsC must fit the 4 KB kernel parameter space next to the other arguments");
+
 // One biquad over the warp's tile.  j = lane within the channel group of NL lanes; carry (shared
 // memory, 2 doubles per section and channel) = the section state at the tile start, replaced by the
 // state after the tile's last sample.
-template <int NL>
-__device__ __forceinline__ void section_round_w(double (&x)[SEG], const SecTab *__restrict__ T, double *carry, int j)
+// U: the lane-independent tables (a SecTab in shared memory or a SecTabC in the constant bank), Q: A^(SEG j).
+template <int NL, typename TU>
+__device__ __forceinline__ void section_round_w(double (&x)[SEG], const TU &U, const double (*__restrict__ Q)[4], double *carry, int j)
 {
+    const TU *T = &U;
     // zero-state end state of the segment: even and odd samples accumulate separately (two chains
     // per component instead of one: half the dependent latency)
     double s0 = 0.0, s1 = 0.0, r0 = 0.0, r1 = 0.0;
@@ -319,8 +334,8 @@ __device__ __forceinline__ void section_round_w(double (&x)[SEG], const SecTab *
     double e1 = __shfl_up_sync(FULL, s1, 1, NL);
     if (j == 0) { e0 = 0.0; e1 = 0.0; }
     const double c0 = carry[0], c1 = carry[1];
-    double z0 = fma(T->Q[j][0], c0, fma(T->Q[j][1], c1, e0));
-    double z1 = fma(T->Q[j][2], c0, fma(T->Q[j][3], c1, e1));
+    double z0 = fma(Q[j][0], c0, fma(Q[j][1], c1, e0));
+    double z1 = fma(Q[j][2], c0, fma(Q[j][3], c1, e1));
     const double b0 = T->b0, b1 = T->b1, b2 = T->b2, na1 = -T->a1, na2 = -T->a2;
 #pragma unroll
     for (int n = 0; n < SEG; ++n) {
@@ -338,10 +353,12 @@ __device__ __forceinline__ void section_round_w(double (&x)[SEG], const SecTab *
 // Two INDEPENDENT biquads over the same tile side by side (the low-pass and the high-pass branch of
 // the crossover, ENG:200-201): the same arithmetic as two section_round_w calls, written so that the
 // two dependent chains interleave (twice the instruction-level parallelism of one).
-template <int NL>
-__device__ __forceinline__ void section_round_w2(double (&xa)[SEG], double (&xb)[SEG], const SecTab *__restrict__ Ta,
-                                                 const SecTab *__restrict__ Tb, double *carry_a, double *carry_b, int j)
+template <int NL, typename TU>
+__device__ __forceinline__ void section_round_w2(double (&xa)[SEG], double (&xb)[SEG], const TU &Ua, const TU &Ub,
+                                                 const double (*__restrict__ Qa)[4], const double (*__restrict__ Qb)[4],
+                                                 double *carry_a, double *carry_b, int j)
 {
+    const TU *Ta = &Ua, *Tb = &Ub;
     double a0 = 0.0, a1 = 0.0, b0s = 0.0, b1s = 0.0;
 #pragma unroll
     for (int n = 0; n < SEG; ++n) {
@@ -365,10 +382,10 @@ __device__ __forceinline__ void section_round_w2(double (&xa)[SEG], double (&xb)
     double eb0 = __shfl_up_sync(FULL, b0s, 1, NL), eb1 = __shfl_up_sync(FULL, b1s, 1, NL);
     if (j == 0) { ea0 = 0.0; ea1 = 0.0; eb0 = 0.0; eb1 = 0.0; }
     const double ca0 = carry_a[0], ca1 = carry_a[1], cb0 = carry_b[0], cb1 = carry_b[1];
-    double za0 = fma(Ta->Q[j][0], ca0, fma(Ta->Q[j][1], ca1, ea0));
-    double za1 = fma(Ta->Q[j][2], ca0, fma(Ta->Q[j][3], ca1, ea1));
-    double zb0 = fma(Tb->Q[j][0], cb0, fma(Tb->Q[j][1], cb1, eb0));
-    double zb1 = fma(Tb->Q[j][2], cb0, fma(Tb->Q[j][3], cb1, eb1));
+    double za0 = fma(Qa[j][0], ca0, fma(Qa[j][1], ca1, ea0));
+    double za1 = fma(Qa[j][2], ca0, fma(Qa[j][3], ca1, ea1));
+    double zb0 = fma(Qb[j][0], cb0, fma(Qb[j][1], cb1, eb0));
+    double zb1 = fma(Qb[j][2], cb0, fma(Qb[j][3], cb1, eb1));
     const double ab0 = Ta->b0, ab1 = Ta->b1, ab2 = Ta->b2, ana1 = -Ta->a1, ana2 = -Ta->a2;
     const double bb0 = Tb->b0, bb1 = Tb->b1, bb2 = Tb->b2, bna1 = -Tb->a1, bna2 = -Tb->a2;
 #pragma unroll
@@ -431,10 +448,11 @@ __device__ __forceinline__ void store_q16_w(int16_t *__restrict__ dst, const int
 #ifndef B200M_CHAINW_OCC
 #define B200M_CHAINW_OCC 2
 #endif
-template <int CH, bool NANCHK>
+// PT: the launch uses ONE plan and its lane-independent tables arrive in `ct` (constant bank).
+template <int CH, bool NANCHK, bool PT>
 __global__ void __launch_bounds__(32 * CW_WARPS, B200M_CHAINW_OCC)
 k_chainw(const int16_t *__restrict__ pcm_in, const StreamDesc *__restrict__ streams, const SegDesc *__restrict__ segs, int n_segs,
-         const PlanDev *__restrict__ plans, int16_t *__restrict__ proc, BandPtrs bp)
+         const PlanDev *__restrict__ plans, int16_t *__restrict__ proc, BandPtrs bp, const __grid_constant__ ChainTabsC ct)
 {
     using W = ChainW<CH>;
     constexpr int NL = W::NL, WT = W::WT;
@@ -554,7 +572,10 @@ k_chainw(const int16_t *__restrict__ pcm_in, const StreamDesc *__restrict__ stre
         // ---- EQ (bypassed sections were dropped at plan time, ENG:171,186) ---------------------------
 #pragma unroll
         for (int s = 0; s < 4; ++s)
-            if (s < n_eq) section_round_w<NL>(x, &tabs[s], carry + (s * CH + c) * 2, j);
+            if (s < n_eq) {
+                if (PT) section_round_w<NL>(x, ct.sec[s], tabs[s].Q, carry + (s * CH + c) * 2, j);
+                else    section_round_w<NL>(x, tabs[s], tabs[s].Q, carry + (s * CH + c) * 2, j);
+            }
 
         // ---- M/S width: the other channel of the same frames lives 16 lanes away ----------------------
         if (CH == 2 && width_on) {
@@ -597,8 +618,13 @@ k_chainw(const int16_t *__restrict__ pcm_in, const StreamDesc *__restrict__ stre
                 xh[n] = x[n];
             }
             // low-pass and high-pass branches side by side (both start from u)
-            section_round_w2<NL>(x, xh, &tabs[4], &tabs[6], carry + (4 * CH + c) * 2, carry + (6 * CH + c) * 2, j);
-            section_round_w2<NL>(x, xh, &tabs[5], &tabs[7], carry + (5 * CH + c) * 2, carry + (7 * CH + c) * 2, j);
+            if (PT) {
+                section_round_w2<NL>(x, xh, ct.sec[4], ct.sec[6], tabs[4].Q, tabs[6].Q, carry + (4 * CH + c) * 2, carry + (6 * CH + c) * 2, j);
+                section_round_w2<NL>(x, xh, ct.sec[5], ct.sec[7], tabs[5].Q, tabs[7].Q, carry + (5 * CH + c) * 2, carry + (7 * CH + c) * 2, j);
+            } else {
+                section_round_w2<NL>(x, xh, tabs[4], tabs[6], tabs[4].Q, tabs[6].Q, carry + (4 * CH + c) * 2, carry + (6 * CH + c) * 2, j);
+                section_round_w2<NL>(x, xh, tabs[5], tabs[7], tabs[5].Q, tabs[7].Q, carry + (5 * CH + c) * 2, carry + (7 * CH + c) * 2, j);
+            }
             // ---- low band; mid = x - low - high (ENG:202), same order of subtractions -----------------
 #pragma unroll
             for (int n = 0; n < SEG; ++n) q[n] = quant16s<NANCHK>(x[n]);
