@@ -645,9 +645,12 @@ extern "C" int b200m_create(int device, b200m_handle **out)
     if (e == cudaSuccess) e = allow_smem(k_detect<1>, detect_smem_bytes(8192));
     if (e == cudaSuccess) e = allow_smem(k_detect<2>, detect_smem_bytes(8192));
     if (e == cudaSuccess) e = allow_smem(k_recur_tiles, recur_smem_bytes());
-    if (e == cudaSuccess) e = allow_smem(k_kweight<1, int16_t>, kweight_smem_bytes());
-    if (e == cudaSuccess) e = allow_smem(k_kweight<2, int16_t>, kweight_smem_bytes());
-    if (e == cudaSuccess) e = allow_smem(k_kweight<1, float>, kweight_smem_bytes());
+    if (e == cudaSuccess) e = allow_smem(k_kweight<1, int16_t, true>, kweight_smem_bytes());
+    if (e == cudaSuccess) e = allow_smem(k_kweight<2, int16_t, true>, kweight_smem_bytes());
+    if (e == cudaSuccess) e = allow_smem(k_kweight<1, float, true>, kweight_smem_bytes());
+    if (e == cudaSuccess) e = allow_smem(k_kweight<1, int16_t, false>, kweight_smem_bytes());
+    if (e == cudaSuccess) e = allow_smem(k_kweight<2, int16_t, false>, kweight_smem_bytes());
+    if (e == cudaSuccess) e = allow_smem(k_kweight<1, float, false>, kweight_smem_bytes());
     if (e == cudaSuccess) e = allow_smem(k_sosfilt<float>, sosfilt_smem_bytes());
     if (e == cudaSuccess) e = allow_smem(k_sosfilt<double>, sosfilt_smem_bytes());
     if (e != cudaSuccess) {
@@ -805,6 +808,14 @@ extern "C" int b200m_reset_profile(b200m_handle *h)
     return rc;
 }
 
+static void fill_tabc(SecTabC &d, const SecTab &s)
+{
+    d.b0 = s.b0; d.b1 = s.b1; d.b2 = s.b2; d.a1 = s.a1; d.a2 = s.a2;
+    std::memcpy(d.g, s.g, sizeof d.g);
+    std::memcpy(d.P, s.P, sizeof d.P);
+    std::memcpy(d.PW, s.PW, sizeof d.PW);
+}
+
 // ------------------------------------------------------------------------------------
 // The chain on device buffers (shared by master_batch and the stage entry points)
 // ------------------------------------------------------------------------------------
@@ -907,13 +918,35 @@ static int launch_compressor(b200m_handle *h, const Group &g, const BandPtrs &bp
     return B200M_OK;
 }
 
+// The K-weighting tables of the current plans, by value, if every plan with a loudness target has the same ones
+// (they depend on the rate alone, and a batch has one rate).
+static bool kw_tables(const b200m_handle *h, KwTabsC &kt)
+{
+    const PlanDev *first = nullptr;
+    for (const PlanDev &p : h->plans_host) {
+        if (!p.has_lufs) continue;
+        if (!first) first = &p;
+        else if (std::memcmp(first->kw, p.kw, sizeof p.kw) != 0) return false;
+    }
+    if (!first) return false;
+    fill_tabc(kt.sec[0], first->kw[0]);
+    fill_tabc(kt.sec[1], first->kw[1]);
+    return true;
+}
+
 static int launch_loudness(b200m_handle *h, const Group &g, const int16_t *d_proc, const float *d_mono,
                            float *d_kw, double *d_z, double *d_zsel, double2 *d_loud)
 {
     if (g.any_lufs) {
-        if (d_mono)         LAUNCH("k_kweight", k_kweight<1, float><<<g.n_ksegs, KNT, kweight_smem_bytes(), h->stream>>>(d_mono, g.d_tracks, g.d_ksegs, h->d_plans, d_kw));
-        else if (g.ch == 2) LAUNCH("k_kweight", k_kweight<2, int16_t><<<g.n_ksegs, KNT, kweight_smem_bytes(), h->stream>>>(d_proc, g.d_tracks, g.d_ksegs, h->d_plans, d_kw));
-        else                LAUNCH("k_kweight", k_kweight<1, int16_t><<<g.n_ksegs, KNT, kweight_smem_bytes(), h->stream>>>(d_proc, g.d_tracks, g.d_ksegs, h->d_plans, d_kw));
+        KwTabsC kt;
+        const bool pt = kw_tables(h, kt);
+#define LAUNCH_KW(CHN, INT, SRC) do { \
+        if (pt) LAUNCH("k_kweight", k_kweight<CHN, INT, true><<<g.n_ksegs, KNT, kweight_smem_bytes(), h->stream>>>(SRC, g.d_tracks, g.d_ksegs, h->d_plans, d_kw, kt)); \
+        else    LAUNCH("k_kweight", k_kweight<CHN, INT, false><<<g.n_ksegs, KNT, kweight_smem_bytes(), h->stream>>>(SRC, g.d_tracks, g.d_ksegs, h->d_plans, d_kw, kt)); } while (0)
+        if (d_mono)         LAUNCH_KW(1, float, d_mono);
+        else if (g.ch == 2) LAUNCH_KW(2, int16_t, d_proc);
+        else                LAUNCH_KW(1, int16_t, d_proc);
+#undef LAUNCH_KW
         const dim3 gb(g.max_blocks, g.n_tracks);
         // hop sums go to d_zsel (k_gate's scratch, free until then): nblocks + 3 floats in nblocks doubles per track
         const bool hops = h->hops_smem_floats > 0 && g.max_blocks >= 3;
@@ -1147,12 +1180,7 @@ static int exec_group(b200m_handle *h, GroupPlan &gp, char *ws, char *pin, const
         if (pt) {
             const PlanDev &pd = h->plans_host[g.single_plan];
             const SecTab *src[8] = {&pd.eq[0], &pd.eq[1], &pd.eq[2], &pd.eq[3], &pd.lp[0], &pd.lp[1], &pd.hp[0], &pd.hp[1]};
-            for (int s8 = 0; s8 < 8; ++s8) {
-                SecTabC &d = ct.sec[s8];
-                d.b0 = src[s8]->b0; d.b1 = src[s8]->b1; d.b2 = src[s8]->b2; d.a1 = src[s8]->a1; d.a2 = src[s8]->a2;
-                std::memcpy(d.g, src[s8]->g, sizeof d.g);
-                std::memcpy(d.P, src[s8]->P, sizeof d.P);
-            }
+            for (int s8 = 0; s8 < 8; ++s8) fill_tabc(ct.sec[s8], *src[s8]);
         }
 #define LAUNCH_CHAINW(CHN, NAN_, PT_) \
         LAUNCH("k_chain", k_chainw<CHN, NAN_, PT_><<<nb, 32 * CW_WARPS, ChainW<CHN>::SMEM, h->stream>>>(d_src, d_streams, d_csegs, g.n_csegs, h->d_plans, d_proc, bp, ct))
@@ -1537,8 +1565,10 @@ extern "C" int b200m_slice_energies(b200m_handle *h, const int16_t *proc_ext_dev
     CK(cudaMemcpyAsync(d_segs, h->pin + sizeof td, segs.size() * sizeof(SegDesc), cudaMemcpyHostToDevice, h->stream));
     Group g;
     g.ch = ch; g.n_tracks = 1; g.d_tracks = d_tracks; g.d_ksegs = d_segs; g.n_ksegs = (int)segs.size();
-    if (ch == 2) LAUNCH("k_kweight", k_kweight<2, int16_t><<<g.n_ksegs, KNT, kweight_smem_bytes(), h->stream>>>(proc_ext_dev, d_tracks, d_segs, h->d_plans, d_kw));
-    else         LAUNCH("k_kweight", k_kweight<1, int16_t><<<g.n_ksegs, KNT, kweight_smem_bytes(), h->stream>>>(proc_ext_dev, d_tracks, d_segs, h->d_plans, d_kw));
+    KwTabsC kt;
+    kw_tables(h, kt);                            // one plan: its tables
+    if (ch == 2) LAUNCH("k_kweight", k_kweight<2, int16_t, true><<<g.n_ksegs, KNT, kweight_smem_bytes(), h->stream>>>(proc_ext_dev, d_tracks, d_segs, h->d_plans, d_kw, kt));
+    else         LAUNCH("k_kweight", k_kweight<1, int16_t, true><<<g.n_ksegs, KNT, kweight_smem_bytes(), h->stream>>>(proc_ext_dev, d_tracks, d_segs, h->d_plans, d_kw, kt));
     const dim3 gb((unsigned)(j1 - j0), 1);
     const bool hops = h->hops_smem_floats > 0 && j1 - j0 >= 3;
     if (hops) LAUNCH("k_hops", k_hops<<<dim3((unsigned)(j1 - j0 + 3), 1), BNT, (size_t)h->hops_smem_floats * 4 + 16, h->stream>>>(d_kw, d_tracks, h->d_plans, d_hops));

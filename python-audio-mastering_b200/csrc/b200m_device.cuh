@@ -107,11 +107,24 @@ struct TrackDesc {
 //   pass 2  the true DF2T recurrence from the now-known start state          (5 FMA/sample)
 // `carry` (smem, 2 doubles) holds the section state at the tile start and is advanced to
 // the tile end.  Contains exactly one __syncthreads(): call it uniformly across the CTA.
-template <int NW>
-__device__ __forceinline__ void section_round(double (&x)[SEG], const SecTab *__restrict__ T,
+// The lane-independent part of a SecTab.  Passed BY VALUE as a kernel parameter it lives in the constant
+// bank: table entries reach the DFMAs without going through the shared-memory / shuffle data pipe, the
+// busiest unit of the filter kernels (65 % of peak in k_chainw with the tables in shared memory).  Only
+// Q[lane] (lane-dependent) still comes from the shared-memory copy of the SecTab.
+struct SecTabC {
+    double b0, b1, b2, a1, a2;
+    double g[SEG][2];
+    double P[5][4];
+    double PW[4];
+};
+
+// U: the lane-independent tables (a SecTab in shared memory or a SecTabC in the constant bank), Q: A^(SEG lane).
+template <int NW, typename TU>
+__device__ __forceinline__ void section_round(double (&x)[SEG], const TU &U, const double (*__restrict__ Q)[4],
                                               double *carry, double *wtot, int lane, int wid,
                                               bool writer)
 {
+    const TU *T = &U;
     double s0 = 0.0, s1 = 0.0;
 #pragma unroll
     for (int n = 0; n < SEG; ++n) {
@@ -142,8 +155,8 @@ __device__ __forceinline__ void section_round(double (&x)[SEG], const SecTab *__
         w0 = n0; w1 = n1;
     }
     if (writer) { carry[0] = w0; carry[1] = w1; }
-    double z0 = fma(T->Q[lane][0], m0, fma(T->Q[lane][1], m1, e0));
-    double z1 = fma(T->Q[lane][2], m0, fma(T->Q[lane][3], m1, e1));
+    double z0 = fma(Q[lane][0], m0, fma(Q[lane][1], m1, e0));
+    double z1 = fma(Q[lane][2], m0, fma(Q[lane][3], m1, e1));
     const double b0 = T->b0, b1 = T->b1, b2 = T->b2, na1 = -T->a1, na2 = -T->a2;
     // scipy _sosfilt (DF2T): y = b0 x + z0; z0 = b1 x - a1 y + z1; z1 = b2 x - a2 y.  The terms that do
     // not depend on y are formed first, so the dependent chain is two FMAs per sample (y -> z0 -> y).

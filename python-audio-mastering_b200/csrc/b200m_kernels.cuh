@@ -168,7 +168,7 @@ k_chain(const int16_t *__restrict__ pcm_in, const StreamDesc *__restrict__ strea
 #pragma unroll
         for (int s = 0; s < 4; ++s) {
             if (s < n_eq) {
-                section_round<4>(x, &tabs[s], carry + (s * CH + c) * 2,
+                section_round<4>(x, tabs[s], tabs[s].Q, carry + (s * CH + c) * 2,
                                  wtot + (((round & 1) * CH + c) * 4) * 2, lane, wid, j == 0);
                 ++round;
             }
@@ -221,9 +221,9 @@ k_chain(const int16_t *__restrict__ pcm_in, const StreamDesc *__restrict__ strea
                 myx[n] = u;
                 x[n] = (double)u;
             }
-            section_round<4>(x, &tabs[4], carry + (4 * CH + c) * 2,
+            section_round<4>(x, tabs[4], tabs[4].Q, carry + (4 * CH + c) * 2,
                              wtot + (((round & 1) * CH + c) * 4) * 2, lane, wid, j == 0); ++round;
-            section_round<4>(x, &tabs[5], carry + (5 * CH + c) * 2,
+            section_round<4>(x, tabs[5], tabs[5].Q, carry + (5 * CH + c) * 2,
                              wtot + (((round & 1) * CH + c) * 4) * 2, lane, wid, j == 0); ++round;
             // ---- low band staged now; mid = x - low - high (ENG:202) keeps x - low ---------
             double rest[SEG];
@@ -235,9 +235,9 @@ k_chain(const int16_t *__restrict__ pcm_in, const StreamDesc *__restrict__ strea
                 x[n] = u;
             }
             stage_q16(myq + 0 * CH * NSEG * QW, q);
-            section_round<4>(x, &tabs[6], carry + (6 * CH + c) * 2,
+            section_round<4>(x, tabs[6], tabs[6].Q, carry + (6 * CH + c) * 2,
                              wtot + (((round & 1) * CH + c) * 4) * 2, lane, wid, j == 0); ++round;
-            section_round<4>(x, &tabs[7], carry + (7 * CH + c) * 2,
+            section_round<4>(x, tabs[7], tabs[7].Q, carry + (7 * CH + c) * 2,
                              wtot + (((round & 1) * CH + c) * 4) * 2, lane, wid, j == 0); ++round;
 #pragma unroll
             for (int n = 0; n < SEG; ++n) q[n] = quant16<NANCHK>(__dsub_rn(rest[n], x[n]));
@@ -288,18 +288,10 @@ template <int CH> struct ChainW {
     static constexpr size_t SMEM = 8 * sizeof(SecTab) + CW_WARPS * WARP_BYTES;
 };
 
-// The lane-independent part of a SecTab, passed BY VALUE as a kernel parameter when the whole launch
-// uses one plan: kernel parameters live in the constant bank, so every table entry is a constant-bank
-// operand of the DFMA that uses it -- no load instruction, and nothing on the shared-memory / shuffle
-// data pipe, which is the busiest unit of this kernel (65 % of peak with the tables in shared memory).
-// Only Q[lane] (lane-dependent) still comes from the shared-memory copy.
-struct SecTabC {
-    double b0, b1, b2, a1, a2;
-    double g[SEG][2];
-    double P[5][4];
-};
-struct ChainTabsC { SecTabC sec[8]; };       // eq[4] lp[2] hp[2]: 3648 bytes
-static_assert(sizeof(ChainTabsC) <= 3800, "ChainTabsC must fit the 4 KB kernel parameter space next to the other arguments");
+// The lane-independent tables of the launch's single plan (SecTabC, b200m_device.cuh), by value.
+struct ChainTabsC { SecTabC sec[8]; };       // eq[4] lp[2] hp[2]: 3904 bytes
+struct KwTabsC { SecTabC sec[2]; };          // K-weighting shelf and high-pass (a function of the rate alone)
+static_assert(sizeof(ChainTabsC) <= 3936, "ChainTabsC must fit the 4 KB kernel parameter space next to the other arguments");
 
 // One biquad over the warp's tile.  j = lane within the channel group of NL lanes; carry (shared
 // memory, 2 doubles per section and channel) = the section state at the tile start, replaced by the
@@ -1355,10 +1347,12 @@ constexpr int KTILE_PAD = KTILE + KNT;
 #ifndef B200M_KW_OCC
 #define B200M_KW_OCC 4
 #endif
-template <int CH, typename IN>
+// PT: every plan of the launch has the same K-weighting filters (they depend on the rate alone) and their
+// lane-independent tables arrive in `kt` (constant bank).
+template <int CH, typename IN, bool PT>
 __global__ void __launch_bounds__(KNT, B200M_KW_OCC)
 k_kweight(const IN *__restrict__ src_all, const TrackDesc *__restrict__ tracks, const SegDesc *__restrict__ segs,
-          const PlanDev *__restrict__ plans, float *__restrict__ kw)
+          const PlanDev *__restrict__ plans, float *__restrict__ kw, const __grid_constant__ KwTabsC kt)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     SecTab *tabs = reinterpret_cast<SecTab *>(smem_raw);                    // kw[2]
@@ -1450,10 +1444,14 @@ k_kweight(const IN *__restrict__ src_all, const TrackDesc *__restrict__ tracks, 
         double x[SEG];
 #pragma unroll
         for (int n = 0; n < SEG; ++n) x[n] = (double)myx[n];
-        section_round<8>(x, &tabs[0], carry + 0, wtot + (round & 1) * 16, lane, wid, tid == 0); ++round;
+        if (PT) section_round<8>(x, kt.sec[0], tabs[0].Q, carry + 0, wtot + (round & 1) * 16, lane, wid, tid == 0);
+        else    section_round<8>(x, tabs[0], tabs[0].Q, carry + 0, wtot + (round & 1) * 16, lane, wid, tid == 0);
+        ++round;
 #pragma unroll
         for (int n = 0; n < SEG; ++n) x[n] = (double)(float)x[n];   // input_data[:,ch] = ... (float32 store)
-        section_round<8>(x, &tabs[1], carry + 2, wtot + (round & 1) * 16, lane, wid, tid == 0); ++round;
+        if (PT) section_round<8>(x, kt.sec[1], tabs[1].Q, carry + 2, wtot + (round & 1) * 16, lane, wid, tid == 0);
+        else    section_round<8>(x, tabs[1], tabs[1].Q, carry + 2, wtot + (round & 1) * 16, lane, wid, tid == 0);
+        ++round;
 #pragma unroll
         for (int n = 0; n < SEG; ++n) myx[n] = (float)x[n];
         __syncthreads();
@@ -2024,7 +2022,7 @@ k_sosfilt(const IN *__restrict__ in, int64_t nframes, int channels, const SecTab
 #pragma unroll
         for (int n = 0; n < SEG; ++n) x[n] = myx[n];
         for (int s = 0; s < nsec; ++s) {
-            section_round<8>(x, &tabs[s], carry + 2 * s, wtot + (round & 1) * 16, lane, wid, tid == 0);
+            section_round<8>(x, tabs[s], tabs[s].Q, carry + 2 * s, wtot + (round & 1) * 16, lane, wid, tid == 0);
             ++round;
         }
 #pragma unroll
