@@ -1183,7 +1183,7 @@ static int exec_group(b200m_handle *h, GroupPlan &gp, char *ws, char *pin, const
             for (int s8 = 0; s8 < 8; ++s8) fill_tabc(ct.sec[s8], *src[s8]);
         }
 #define LAUNCH_CHAINW(CHN, NAN_, PT_) \
-        LAUNCH("k_chain", k_chainw<CHN, NAN_, PT_><<<nb, 32 * CW_WARPS, ChainW<CHN>::SMEM, h->stream>>>(d_src, d_streams, d_csegs, g.n_csegs, h->d_plans, d_proc, bp, ct))
+        LAUNCH("k_chain", k_chainw<CHN, NAN_, PT_><<<nb, 32 * CW_WARPS, (PT_) ? ChainW<CHN>::SMEM_PT : ChainW<CHN>::SMEM, h->stream>>>(d_src, d_streams, d_csegs, g.n_csegs, h->d_plans, d_proc, bp, ct))
         const bool nanchk = !g.chain_stable;
         if (ch == 2) {
             if (pt) { if (nanchk) LAUNCH_CHAINW(2, true, true); else LAUNCH_CHAINW(2, false, true); }

@@ -271,13 +271,20 @@ constexpr size_t chain_smem_bytes()
 //   * the M/S width exchange is one shuffle (xor 16) per sample instead of a trip through shared memory;
 //   * raw PCM comes in as 16-byte cp.async pieces straight into the layout the lanes read back as
 //     128-bit words, and the quantised bands leave as 16-byte stores after a shuffle interleave.
-// Warps of a CTA never wait for each other after the section tables are staged, so their fp64-heavy
-// and integer-heavy phases overlap freely.  Segments are joined by overlap-discard exactly like
+// Warps never wait for each other, so their fp64-heavy and integer-heavy phases overlap freely.  Segments are joined by overlap-discard exactly like
 // k_chain's; since eight times as many independent segments are needed, the host picks this kernel
 // for batches large enough to keep the warm-up share small (b200m_set_chain_kernel).
-// The eight segments of a CTA belong to one stream (the host pads with empty segments).
+// One warp per CTA (CW_WARPS); with more, the segments of a CTA belong to one stream (the host pads).
 // =====================================================================================
-constexpr int CW_WARPS = 8;
+// Warps per CTA of k_chainw.  ONE: everything a warp does then depends on blockIdx and kernel parameters
+// only, the compiler can prove its control flow uniform, and the shuffles lose their divergence guards (the
+// code shrinks from 6400 to 3300 instructions, no spills); with the tables in the constant bank a CTA needs
+// 12 KB of shared memory, so 16 of them fit an SM like two CTAs of eight warps did.  Measured: 10.5 -> 9.5 ms
+// on 64 tracks, 1.49 -> 1.38 ms on 8.  (> 1: segments per stream are padded to a multiple of it.)
+#ifndef B200M_CW_WARPS
+#define B200M_CW_WARPS 1
+#endif
+constexpr int CW_WARPS = B200M_CW_WARPS;
 template <int CH> struct ChainW {
     static constexpr int NL = 32 / CH;                      // lanes per channel
     static constexpr int WT = NL * SEG;                     // frames per warp tile
@@ -285,7 +292,9 @@ template <int CH> struct ChainW {
     static constexpr int RAW_WORDS = NL * RSTRIDE;
     static constexpr int USTRIDE = 20;                      // floats per lane in the re-floated stash
     static constexpr size_t WARP_BYTES = (size_t)RAW_WORDS * 4 + 32 * USTRIDE * 4 + 8 * CH * 2 * 8;
-    static constexpr size_t SMEM = 8 * sizeof(SecTab) + CW_WARPS * WARP_BYTES;
+    static constexpr size_t QTAB_BYTES = 8 * 32 * 4 * 8;  // Q[lane] of the eight sections: all the shared memory the tables need when the rest travels as a parameter
+    static constexpr size_t SMEM = 8 * sizeof(SecTab) + CW_WARPS * WARP_BYTES;     // tables in shared memory (several plans in the launch)
+    static constexpr size_t SMEM_PT = QTAB_BYTES + CW_WARPS * WARP_BYTES;          // tables in the constant bank
 };
 
 // The lane-independent tables of the launch's single plan (SecTabC, b200m_device.cuh), by value.
@@ -442,16 +451,17 @@ __device__ __forceinline__ void store_q16_w(int16_t *__restrict__ dst, const int
 #endif
 // PT: the launch uses ONE plan and its lane-independent tables arrive in `ct` (constant bank).
 template <int CH, bool NANCHK, bool PT>
-__global__ void __launch_bounds__(32 * CW_WARPS, B200M_CHAINW_OCC)
+__global__ void __launch_bounds__(32 * CW_WARPS, B200M_CHAINW_OCC * 8 / CW_WARPS)
 k_chainw(const int16_t *__restrict__ pcm_in, const StreamDesc *__restrict__ streams, const SegDesc *__restrict__ segs, int n_segs,
          const PlanDev *__restrict__ plans, int16_t *__restrict__ proc, BandPtrs bp, const __grid_constant__ ChainTabsC ct)
 {
     using W = ChainW<CH>;
     constexpr int NL = W::NL, WT = W::WT;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    SecTab *tabs = reinterpret_cast<SecTab *>(smem_raw);                 // eq[4] lp[2] hp[2] of the CTA's plan
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    unsigned char *wbase = smem_raw + 8 * sizeof(SecTab) + (size_t)warp * W::WARP_BYTES;
+    SecTab *tabs = reinterpret_cast<SecTab *>(smem_raw);                 // !PT: eq[4] lp[2] hp[2] of the CTA's plan
+    double (*sQ)[32][4] = reinterpret_cast<double (*)[32][4]>(smem_raw); //  PT: only their Q[lane] tables
+    const int warp = CW_WARPS == 1 ? 0 : (int)(threadIdx.x >> 5), lane = threadIdx.x & 31;    // one warp per CTA: everything below is CTA-uniform
+    unsigned char *wbase = smem_raw + (PT ? W::QTAB_BYTES : 8 * sizeof(SecTab)) + (size_t)warp * W::WARP_BYTES;
     unsigned *raw = reinterpret_cast<unsigned *>(wbase);                 // [NL][RSTRIDE] raw PCM of the tile being fetched
     float *su = reinterpret_cast<float *>(wbase + (size_t)W::RAW_WORDS * 4) + lane * W::USTRIDE;   // this lane's 16 re-floated samples
     double *carry = reinterpret_cast<double *>(wbase + (size_t)W::RAW_WORDS * 4 + 32 * W::USTRIDE * 4);   // [8][CH][2]
@@ -459,7 +469,11 @@ k_chainw(const int16_t *__restrict__ pcm_in, const StreamDesc *__restrict__ stre
     const int sidx = blockIdx.x * CW_WARPS + warp;
     const SegDesc sg0 = segs[blockIdx.x * CW_WARPS];                     // the CTA's first segment names the stream (and so the plan)
     const PlanDev *__restrict__ pl = plans + streams[sg0.owner].plan;
-    {
+    if (PT) {
+        const SecTab *src = pl->eq;                                      // eq[4] lp[2] hp[2] are contiguous in PlanDev
+        double *dst = reinterpret_cast<double *>(sQ);
+        for (int i = threadIdx.x; i < 8 * 128; i += 32 * CW_WARPS) dst[i] = reinterpret_cast<const double *>(src[i >> 7].Q)[i & 127];
+    } else {
         const double *src = reinterpret_cast<const double *>(pl->eq);
         double *dst = reinterpret_cast<double *>(tabs);
         for (int i = threadIdx.x; i < 8 * (int)(sizeof(SecTab) / 8); i += 32 * CW_WARPS) dst[i] = src[i];
@@ -565,7 +579,7 @@ k_chainw(const int16_t *__restrict__ pcm_in, const StreamDesc *__restrict__ stre
 #pragma unroll
         for (int s = 0; s < 4; ++s)
             if (s < n_eq) {
-                if (PT) section_round_w<NL>(x, ct.sec[s], tabs[s].Q, carry + (s * CH + c) * 2, j);
+                if (PT) section_round_w<NL>(x, ct.sec[s], sQ[s], carry + (s * CH + c) * 2, j);
                 else    section_round_w<NL>(x, tabs[s], tabs[s].Q, carry + (s * CH + c) * 2, j);
             }
 
@@ -611,8 +625,8 @@ k_chainw(const int16_t *__restrict__ pcm_in, const StreamDesc *__restrict__ stre
             }
             // low-pass and high-pass branches side by side (both start from u)
             if (PT) {
-                section_round_w2<NL>(x, xh, ct.sec[4], ct.sec[6], tabs[4].Q, tabs[6].Q, carry + (4 * CH + c) * 2, carry + (6 * CH + c) * 2, j);
-                section_round_w2<NL>(x, xh, ct.sec[5], ct.sec[7], tabs[5].Q, tabs[7].Q, carry + (5 * CH + c) * 2, carry + (7 * CH + c) * 2, j);
+                section_round_w2<NL>(x, xh, ct.sec[4], ct.sec[6], sQ[4], sQ[6], carry + (4 * CH + c) * 2, carry + (6 * CH + c) * 2, j);
+                section_round_w2<NL>(x, xh, ct.sec[5], ct.sec[7], sQ[5], sQ[7], carry + (5 * CH + c) * 2, carry + (7 * CH + c) * 2, j);
             } else {
                 section_round_w2<NL>(x, xh, tabs[4], tabs[6], tabs[4].Q, tabs[6].Q, carry + (4 * CH + c) * 2, carry + (6 * CH + c) * 2, j);
                 section_round_w2<NL>(x, xh, tabs[5], tabs[7], tabs[5].Q, tabs[7].Q, carry + (5 * CH + c) * 2, carry + (7 * CH + c) * 2, j);
