@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define B200M_ABI_VERSION 1
+#define B200M_ABI_VERSION 2
 
 enum {
     B200M_OK = 0,
@@ -99,6 +99,15 @@ typedef struct {
     b200m_band band[3];      /* low, mid, high */
     b200m_biquad kw[2];      /* K-weighting: high shelf, high pass (pyloudnorm) */
     double lufs;
+    /* ENG:128-134 only ever sees x = int16 / 32768: the exciter is a pure function of the 65536 possible
+     * samples.  sat_lut (HOST pointer, 65536 float32, entry [(uint16_t)s] for the int16 sample s) holds
+     * (1 - mix) x + mix tanh(x (1 + 4 mix)) as the HOST's numpy evaluates it in float32 -- numpy's float32 tanh
+     * is a SIMD polynomial that no device routine reproduces bit for bit, so the Python host tabulates it
+     * with numpy itself (b200master/plan.py) and the kernels gather.  NULL: the library tabulates the same
+     * expression with its own libm tanhf (<= 1 ulp from numpy's; non-Python hosts).  sat_lut_key names the
+     * table's CONTENT for the plan cache (same key = same 65536 values); 0 = the library hashes the table. */
+    const float *sat_lut;
+    uint64_t sat_lut_key;
 } b200m_plan;
 
 /* ---- lifetime ------------------------------------------------------------------ */
@@ -257,6 +266,11 @@ int b200m_pcm16_to_float(b200m_handle *h, const int16_t *pcm, int64_t n_samples,
 int b200m_float_to_pcm16(b200m_handle *h, const void *x, int is_f64, int64_t n_samples, int16_t *out);
 /* ENG:128-134 apply_saturation on float32 samples (any layout, elementwise). */
 int b200m_saturation(b200m_handle *h, const float *x, int64_t n_samples, double saturation_percent, float *out);
+/* ENG:117-134 on int16 samples: audio_segment_to_float_array followed by apply_saturation, as ONE gather
+ * from the 65536-entry table of b200m_plan::sat_lut (same conventions: host pointer, content key or 0) --
+ * bit-exact with the host's numpy, unlike b200m_saturation's tanhf (<= 1 ulp) on arbitrary floats. */
+int b200m_saturation_pcm(b200m_handle *h, const int16_t *pcm, int64_t n_samples, const float *sat_lut,
+                         uint64_t sat_lut_key, float *out);
 /* ENG:136-144 apply_stereo_width on interleaved (n, 2) samples, float32 or float64. */
 int b200m_stereo_width(b200m_handle *h, const void *x, int is_f64, int64_t n_frames, double width, void *out);
 /* ENG:183/194/200-201 scipy.signal.sosfilt from zero state: n_sections biquads applied in

@@ -84,6 +84,36 @@ def cases():
     }
 
 
+def write_exciter_tables(saturations):
+    """``exciter_tables.npz``: the exciter (ENG:128-134) of THIS host's numpy over the 65536 int16 samples, for every
+    saturation value the fixtures use.  numpy's float32 tanh is a SIMD polynomial that may differ by an ulp between
+    CPU dispatch targets, and the fixtures' outputs were computed with this host's; a GPU test replays the stored
+    table (``plan.install_exciter_table``) so that it compares like with like on any box.  Stored compactly: the ulp
+    difference of np.tanh(float32) from float32(np.tanh(float64)) (int8, mostly 0 / +-1), plus a SHA-256 of the
+    table the loader must reproduce (``tests/conftest.py: authoring_exciter_table``)."""
+    import hashlib
+    from b200master.plan import exciter_table
+    out = {}
+    for sat in sorted(set(saturations)):
+        if sat == 0:
+            continue
+        s16 = np.arange(65536, dtype=np.uint16).view(np.int16)
+        x = s16.astype(np.float32) / (2 ** 15)
+        mix = (sat / 100.0) ** 2
+        arg = x * (1 + mix * 4)
+        t32 = np.tanh(arg)
+        t0 = np.tanh(arg.astype(np.float64)).astype(np.float32)
+        d = t32.view(np.int32).astype(np.int64) - t0.view(np.int32).astype(np.int64)
+        assert np.abs(d).max() <= 100
+        table = exciter_table(sat)
+        assert np.array_equal(table.view(np.int32), ((1 - mix) * x + mix * t32).astype(np.float32).view(np.int32))
+        tag = repr(float(sat))
+        out["d_" + tag] = d.astype(np.int8)
+        out["sha_" + tag] = np.array(hashlib.sha256(table.tobytes()).hexdigest())
+        print(f"exciter table sat={sat}: {int((d != 0).sum())} entries differ from the correctly rounded tanh")
+    np.savez_compressed(os.path.join(GOLDEN, "exciter_tables.npz"), **out)
+
+
 def main():
     warnings.simplefilter("ignore", DeprecationWarning)
     os.makedirs(GOLDEN, exist_ok=True)
@@ -127,6 +157,7 @@ def main():
         lowshelf_L=lowshelf, peak_R=peak, loudness=np.float64(thirdparty.Meter.last_loudness),
         normalized=norm, limited=lim, limited32=lim32, final=fin.to_numpy())
     manifest["stages"] = dict(frames=int(pcm.shape[0]), rate=rate, settings=st)
+    write_exciter_tables([st.get("saturation", 0) for _p, _r, st in cases().values()] + [35])
     with open(os.path.join(GOLDEN, "MANIFEST.json"), "w") as f:
         json.dump(manifest, f, indent=1, sort_keys=True)
     print("stages.npz written")

@@ -322,8 +322,21 @@ class Engine:
         return np.ascontiguousarray(x)
 
     def saturation(self, x: np.ndarray, pct) -> np.ndarray:
+        """ENG:128-134.  Samples that came from ENG:117-121 (every value an int16 / 2^15, which is all the
+        reference's chain ever feeds it) go through the host-tabulated exciter table and are bit-exact with
+        numpy; anything else takes the device's float32 tanhf (<= 1 ulp)."""
         x = np.ascontiguousarray(x, dtype=np.float32)
         out = np.empty_like(x)
+        if pct == 0 or x.size == 0:
+            out[...] = x
+            return out
+        k = x * np.float32(32768.0)
+        if np.all((k >= -32768.0) & (k <= 32767.0)) and np.array_equal(k, np.rint(k)):
+            from .plan import _exciter_lut
+            table, key = _exciter_lut(pct)
+            pcm = k.astype(np.int16)
+            self._ck(self._lib.b200m_saturation_pcm(self._h, pcm.ctypes.data, pcm.size, table.ctypes.data, key, out.ctypes.data))
+            return out
         self._ck(self._lib.b200m_saturation(self._h, x.ctypes.data, x.size, float(pct), out.ctypes.data))
         return out
 

@@ -40,7 +40,10 @@ class Plan(C.Structure):
                 ("eq", Biquad * 4), ("width", C.c_double),
                 ("multiband", C.c_int32), ("has_lufs", C.c_int32),
                 ("lp", Biquad * 2), ("hp", Biquad * 2), ("band", Band * 3), ("kw", Biquad * 2),
-                ("lufs", C.c_double)]
+                ("lufs", C.c_double),
+                ("sat_lut", C.c_void_p), ("sat_lut_key", C.c_uint64)]
+
+ABI_VERSION = 2
 
 
 _lib = None
@@ -49,7 +52,7 @@ EXPORTS = [
     "b200m_abi_version", "b200m_create", "b200m_destroy", "b200m_last_error", "b200m_set_stream",
     "b200m_synchronize", "b200m_set_workspace_limit", "b200m_launch_count", "b200m_set_profiling",
     "b200m_kernel_time_ms", "b200m_reset_profile", "b200m_set_recur_tiling", "b200m_recur_stats", "b200m_set_segment_tiles", "b200m_set_pipeline", "b200m_set_chain_kernel", "b200m_set_pipeline_shape", "b200m_plan_from_settings", "b200m_master_batch", "b200m_master_batch_targets", "b200m_master_batch_wav", "b200m_wav_header",
-    "b200m_pcm16_to_float", "b200m_float_to_pcm16", "b200m_saturation", "b200m_stereo_width",
+    "b200m_pcm16_to_float", "b200m_float_to_pcm16", "b200m_saturation", "b200m_saturation_pcm", "b200m_stereo_width",
     "b200m_sosfilt", "b200m_multiband", "b200m_compress_dynamic_range", "b200m_integrated_loudness",
     "b200m_normalize_to_lufs", "b200m_soft_limiter",
     "b200m_stage_pcm", "b200m_slice_halo", "b200m_slice_chain", "b200m_slice_energies", "b200m_track_blocks",
@@ -99,6 +102,7 @@ def load():
     lib.b200m_pcm16_to_float.argtypes = [vp, vp, i64, vp]
     lib.b200m_float_to_pcm16.argtypes = [vp, vp, C.c_int, i64, vp]
     lib.b200m_saturation.argtypes = [vp, vp, i64, dbl, vp]
+    lib.b200m_saturation_pcm.argtypes = [vp, vp, i64, vp, C.c_uint64, vp]
     lib.b200m_stereo_width.argtypes = [vp, vp, C.c_int, i64, dbl, vp]
     lib.b200m_sosfilt.argtypes = [vp, C.POINTER(Biquad), C.c_int, vp, C.c_int, i64, C.c_int, vp]
     lib.b200m_multiband.argtypes = [vp, C.POINTER(Plan), vp, i64, vp]

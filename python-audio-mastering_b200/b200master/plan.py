@@ -10,12 +10,60 @@ same design (``b200m_plan_from_settings``) for non-Python hosts.
 """
 from __future__ import annotations
 
+import hashlib
 import math
+import threading
 
 import numpy as np
 from scipy.signal import butter
 
 from . import lib as L
+
+# ENG:128-134 sees only x = int16 / 32768, so the exciter is a pure function of the 65536 possible samples.
+# numpy's float32 tanh is a SIMD polynomial (neither correctly rounded nor reproducible by a device routine),
+# so the table is made HERE, by the very numpy expression the reference evaluates, and the kernels gather from it
+# (b200m_plan.sat_lut).  Tables are kept alive for the life of the process: the plan holds a raw pointer.
+_LUT_LOCK = threading.Lock()
+_LUT_CACHE: dict = {}          # saturation value -> (float32[65536] indexed by the uint16 bit pattern, content key)
+_LUT_MAX = 64
+
+
+def exciter_table(saturation) -> np.ndarray:
+    """(1 - mix) * x + mix * tanh(x * (1 + 4 mix)) in float32 for every int16 sample, indexed by ``uint16(sample)``;
+    the statements of ENG:131-134 on the array ENG:121 produces."""
+    s16 = np.arange(65536, dtype=np.uint16).view(np.int16)
+    x = s16.astype(np.float32) / (2 ** 15)                    # ENG:121
+    mix = (saturation / 100.0) ** 2                            # ENG:131
+    saturated = np.tanh(x * (1 + mix * 4))                     # ENG:133
+    return np.ascontiguousarray((1 - mix) * x + mix * saturated, dtype=np.float32)   # ENG:134
+
+
+def _lut_key(table: np.ndarray) -> int:
+    return int.from_bytes(hashlib.blake2b(table.tobytes(), digest_size=8).digest(), "little") or 1
+
+
+def install_exciter_table(saturation, table) -> None:
+    """Use ``table`` for plans with this ``saturation`` from now on (``None`` forgets it).  Lets a test replay
+    the table of the host that wrote a golden fixture; production code never calls this."""
+    with _LUT_LOCK:
+        if table is None:
+            _LUT_CACHE.pop(saturation, None)
+            return
+        t = np.ascontiguousarray(table, dtype=np.float32)
+        if t.shape != (65536,):
+            raise ValueError("an exciter table has 65536 float32 entries")
+        _LUT_CACHE[saturation] = (t, _lut_key(t))
+
+
+def _exciter_lut(saturation):
+    with _LUT_LOCK:
+        hit = _LUT_CACHE.get(saturation)
+        if hit is None:
+            if len(_LUT_CACHE) >= _LUT_MAX:
+                _LUT_CACHE.pop(next(iter(_LUT_CACHE)))        # plans made earlier keep their own reference (Plan._lut)
+            t = exciter_table(saturation)
+            hit = _LUT_CACHE[saturation] = (t, _lut_key(t))
+        return hit
 
 # ENG:207-209: (attack_ms, release_ms) of the low / mid / high compressor
 BAND_TIMES = ((10.0, 200.0), (5.0, 150.0), (1.0, 50.0))
@@ -129,6 +177,10 @@ def make_plan(settings: dict, rate: int, channels: int, low_crossover=250, high_
     p.sat_on = int(sat != 0)
     mix = (sat / 100.0) ** 2                                    # ENG:131
     p.sat_clean, p.sat_mix, p.sat_drive = np.float32(1 - mix), np.float32(mix), np.float32(1 + mix * 4)
+    if p.sat_on:
+        table, key = _exciter_lut(sat)
+        p._lut = table                                          # keeps the table alive as long as the plan
+        p.sat_lut, p.sat_lut_key = table.ctypes.data, key
     secs = [shelf_biquad(rate, 250, s["bass_boost"], "low"),    # ENG:154-161, in order
             peak_biquad(rate, 1000, -s["mid_cut"]),
             peak_biquad(rate, 4000, s["presence_boost"]),

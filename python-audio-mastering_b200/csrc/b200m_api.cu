@@ -35,7 +35,12 @@ struct b200m_handle {
     std::vector<PlanDev> plans_host;
     PlanDev *d_plans = nullptr;
     size_t d_plans_cap = 0;
-    std::map<std::tuple<double, double>, double *> curves;
+    // device tables keyed by content, least-recently-used entries evicted beyond a bound (a long-lived host --
+    // the reference's worker is one -- sees a new slider combination per job; ensure_plans)
+    struct DevTab { void *ptr; uint64_t stamp; };
+    std::map<std::tuple<double, double>, DevTab> curves;     // (thresh_rms, slope) -> CURVE_N doubles
+    std::map<uint64_t, DevTab> sat_luts;                     // content key -> 65536 floats (2^15 * exciter)
+    uint64_t tab_tick = 0;
     std::map<int, std::pair<int32_t *, int>> pw_trees;      // block length -> (device table, smem floats)
     int blocks_smem_floats = 0;                              // max over the current plans
     int hops_smem_floats = 0;                                // the same for the hop trees (0: no plan shares hops)
@@ -415,6 +420,22 @@ extern "C" int b200m_plan_from_settings(const b200m_settings *s, int sample_rate
 // ------------------------------------------------------------------------------------
 // Plan upload (device tables), cached across calls with identical plans
 // ------------------------------------------------------------------------------------
+constexpr size_t MAX_CURVES = 96, MAX_SAT_LUTS = 32;        // 25 MB + 8 MB of device tables at most (beyond what one call uses)
+
+// Make room in a table cache: entries not touched by the rebuild in progress (stamp < tick) go first, oldest first.
+// The caller has synchronised the handle's stream, so nothing in flight reads them.
+template <typename M> static void evict_tables(M &m, size_t cap, uint64_t tick)
+{
+    while (m.size() >= cap) {
+        auto victim = m.end();
+        for (auto it = m.begin(); it != m.end(); ++it)
+            if (it->second.stamp < tick && (victim == m.end() || it->second.stamp < victim->second.stamp)) victim = it;
+        if (victim == m.end()) return;           // everything is in use by this very call: grow
+        cudaFree(victim->second.ptr);
+        m.erase(victim);
+    }
+}
+
 static int get_curve(b200m_handle *h, const b200m_band &b, const double **out, std::vector<double> *host_copy)
 {
     // pydub: db = 20 * math.log(rms / thresh_rms, 10) = 20 * (log(x) / log(10));
@@ -434,11 +455,63 @@ static int get_curve(b200m_handle *h, const b200m_band &b, const double **out, s
     if (host_copy) *host_copy = tab;
     auto key = std::make_tuple(b.thresh_rms, b.slope);
     auto it = h->curves.find(key);
-    if (it != h->curves.end()) { *out = it->second; return B200M_OK; }
+    if (it != h->curves.end()) { it->second.stamp = h->tab_tick; *out = (const double *)it->second.ptr; return B200M_OK; }
+    evict_tables(h->curves, MAX_CURVES, h->tab_tick);
     double *d = nullptr;
     CK(cudaMalloc(&d, CURVE_N * sizeof(double)));
-    CK(cudaMemcpy(d, tab.data(), CURVE_N * sizeof(double), cudaMemcpyHostToDevice));
-    h->curves[key] = d;
+    if (cudaMemcpy(d, tab.data(), CURVE_N * sizeof(double), cudaMemcpyHostToDevice) != cudaSuccess) {
+        cudaFree(d);
+        return fail(h, B200M_ERR_CUDA, "upload of a compressor curve failed: %s", cudaGetErrorString(cudaGetLastError()));
+    }
+    h->curves[key] = {d, h->tab_tick};
+    *out = d;
+    return B200M_OK;
+}
+
+static uint64_t hash_words(const void *p, size_t bytes, uint64_t seed)
+{
+    uint64_t hsh = 0xcbf29ce484222325ull ^ seed;
+    const unsigned char *c = (const unsigned char *)p;
+    size_t i = 0;
+    for (; i + 8 <= bytes; i += 8) { uint64_t w; std::memcpy(&w, c + i, 8); hsh = (hsh ^ w) * 0x100000001b3ull; hsh ^= hsh >> 29; }
+    for (; i < bytes; ++i) hsh = (hsh ^ c[i]) * 0x100000001b3ull;
+    return hsh;
+}
+
+// ENG:128-134 tabulated over the 65536 int16 samples (b200m_plan::sat_lut), uploaded pre-scaled by 2^15 (exact):
+// the chain kernels work on 2^15 x up to quantise #1.
+static int get_sat_lut(b200m_handle *h, const b200m_plan &p, const float **out)
+{
+    std::vector<float> own;
+    const float *src = p.sat_lut;
+    uint64_t key = p.sat_lut_key;
+    if (!src) {
+        // no table from the host: the same expression with libm's tanhf, every product / sum rounded to float32
+        own.resize(65536);
+        for (int i = 0; i < 65536; ++i) {
+            const float x = (float)(int16_t)(uint16_t)i / 32768.0f;
+            volatile float arg = x * p.sat_drive;
+            volatile float a = p.sat_clean * x, b = p.sat_mix * std::tanh((float)arg);
+            own[i] = a + b;
+        }
+        src = own.data();
+        const float par[3] = {p.sat_clean, p.sat_mix, p.sat_drive};
+        key = hash_words(par, sizeof par, 0x6c69626dull /* "libm" */);
+    } else if (key == 0) {
+        key = hash_words(src, 65536 * sizeof(float), 0);
+    }
+    auto it = h->sat_luts.find(key);
+    if (it != h->sat_luts.end()) { it->second.stamp = h->tab_tick; *out = (const float *)it->second.ptr; return B200M_OK; }
+    evict_tables(h->sat_luts, MAX_SAT_LUTS, h->tab_tick);
+    std::vector<float> scaled(65536);
+    for (int i = 0; i < 65536; ++i) scaled[i] = src[i] * 32768.0f;      // exact (power of two; |value| ~ 1)
+    float *d = nullptr;
+    CK(cudaMalloc(&d, 65536 * sizeof(float)));
+    if (cudaMemcpy(d, scaled.data(), 65536 * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess) {
+        cudaFree(d);
+        return fail(h, B200M_ERR_CUDA, "upload of an exciter table failed: %s", cudaGetErrorString(cudaGetLastError()));
+    }
+    h->sat_luts[key] = {d, h->tab_tick};
     *out = d;
     return B200M_OK;
 }
@@ -525,13 +598,16 @@ static int ensure_plans(b200m_handle *h, const b200m_plan *plans, int n)
     if ((int)h->plans_key.size() == n && n > 0 &&
         std::memcmp(h->plans_key.data(), plans, n * sizeof(b200m_plan)) == 0)
         return B200M_OK;
-    CK(cudaStreamSynchronize(h->stream));   // previous launches may still read d_plans
-    h->plans_host.assign(n, PlanDev());
-    h->blocks_smem_floats = 0;
-    h->hops_smem_floats = 0;
+    CK(cudaStreamSynchronize(h->stream));   // previous launches may still read d_plans and the cached tables
+    // Everything is built into locals and swapped in only after the upload succeeded; the cache key is
+    // dropped first, so a rebuild that fails half-way can never be mistaken for the plans it replaced.
+    h->plans_key.clear();
+    ++h->tab_tick;
+    std::vector<PlanDev> host(n);
+    int blocks_smem = 0, hops_smem = 0;
     for (int i = 0; i < n; ++i) {
         const b200m_plan &p = plans[i];
-        PlanDev &d = h->plans_host[i];
+        PlanDev &d = host[i];
         std::memset(&d, 0, sizeof d);
         if (p.channels != 1 && p.channels != 2) return fail(h, B200M_ERR_INVALID, "plan %d: channels must be 1 or 2", i);
         if (p.n_eq < 0 || p.n_eq > 4) return fail(h, B200M_ERR_INVALID, "plan %d: n_eq out of range", i);
@@ -539,6 +615,7 @@ static int ensure_plans(b200m_handle *h, const b200m_plan *plans, int n)
         d.width_on = p.width_on && p.channels == 2; d.multiband = p.multiband; d.has_lufs = p.has_lufs;
         d.sat_clean = p.sat_clean; d.sat_mix = p.sat_mix; d.sat_drive = p.sat_drive;
         d.width = p.width; d.lufs = p.lufs;
+        if (p.sat_on) { int rc = get_sat_lut(h, p, &d.sat_lut); if (rc) return rc; }
         for (int s = 0; s < p.n_eq; ++s) build_sectab(p.eq[s], d.eq[s]);
         build_sectab(p.kw[0], d.kw[0]);
         build_sectab(p.kw[1], d.kw[1]);
@@ -547,7 +624,7 @@ static int ensure_plans(b200m_handle *h, const b200m_plan *plans, int n)
             int fl = 0;
             int rc = get_pw_tree(h, (int)(int64_t)(0.4 * (0.0 * 0.25 + 1.0) * (double)p.sample_rate), &d.ptree, &fl);
             if (rc) return rc;
-            h->blocks_smem_floats = std::max(h->blocks_smem_floats, fl);
+            blocks_smem = std::max(blocks_smem, fl);
             // numpy's tree over n elements splits at n2 = n/2 - (n/2) % 8: when n is a multiple of 32 the
             // first two levels cut at n/2 and n/4, i.e. a block is four hop trees (k_hops)
             const int nblk = (int)(int64_t)(0.4 * (0.0 * 0.25 + 1.0) * (double)p.sample_rate);
@@ -555,7 +632,7 @@ static int ensure_plans(b200m_handle *h, const b200m_plan *plans, int n)
                 int hf = 0;
                 rc = get_pw_tree(h, nblk / 4, &d.htree, &hf);
                 if (rc) return rc;
-                if (d.htree) { d.hop = nblk / 4; h->hops_smem_floats = std::max(h->hops_smem_floats, hf); }
+                if (d.htree) { d.hop = nblk / 4; hops_smem = std::max(hops_smem, hf); }
             }
         }
         if (p.multiband) {
@@ -582,7 +659,6 @@ static int ensure_plans(b200m_handle *h, const b200m_plan *plans, int n)
                 }
                 d.band[b] = {bb.thresh_rms, bb.attack_frames, bb.release_frames, bb.slope,
                              1.0 / bb.attack_frames, 1.0 / bb.release_frames, bb.look_frames, trick ? 1 : 0, hold_max, 0};
-                if (rc) return rc;
             }
         }
     }
@@ -592,8 +668,11 @@ static int ensure_plans(b200m_handle *h, const b200m_plan *plans, int n)
         CK(cudaMalloc(&h->d_plans, n * sizeof(PlanDev)));
         h->d_plans_cap = n;
     }
-    CK(cudaMemcpyAsync(h->d_plans, h->plans_host.data(), n * sizeof(PlanDev), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->d_plans, host.data(), n * sizeof(PlanDev), cudaMemcpyHostToDevice, h->stream));
     CK(cudaStreamSynchronize(h->stream));
+    h->plans_host.swap(host);
+    h->blocks_smem_floats = blocks_smem;
+    h->hops_smem_floats = hops_smem;
     h->plans_key.assign(plans, plans + n);
     return B200M_OK;
 }
@@ -677,7 +756,8 @@ extern "C" void b200m_destroy(b200m_handle *h)
     if (h->d_plans) cudaFree(h->d_plans);
     if (h->pin) cudaFreeHost(h->pin);
     if (h->d_counters) cudaFree(h->d_counters);
-    for (auto &kv : h->curves) cudaFree(kv.second);
+    for (auto &kv : h->curves) cudaFree(kv.second.ptr);
+    for (auto &kv : h->sat_luts) cudaFree(kv.second.ptr);
     for (auto &kv : h->pw_trees) if (kv.second.first) cudaFree(kv.second.first);
     for (auto &r : h->prof_recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
     for (auto e : h->ev_pool) cudaEventDestroy(e);
@@ -1686,6 +1766,23 @@ extern "C" int b200m_saturation(b200m_handle *h, const float *x, int64_t n, doub
     return elementwise(h, x, n * 4, out, n * 4, [&](char *di, char *dn) {
         LAUNCH("k_saturation", k_saturation<<<grid_for(n), 256, 0, h->stream>>>((const float *)di, n, (float)(1 - mix), (float)mix,
                                                                                   (float)(1 + mix * 4), (float *)dn));
+    });
+}
+
+extern "C" int b200m_saturation_pcm(b200m_handle *h, const int16_t *pcm, int64_t n, const float *sat_lut, uint64_t key, float *out)
+{
+    if (!h || n < 0 || !sat_lut || (n && (!pcm || !out))) return h ? fail(h, B200M_ERR_INVALID, "saturation_pcm: bad argument") : B200M_ERR_INVALID;
+    CK(cudaSetDevice(h->device));
+    CK(cudaStreamSynchronize(h->stream));       // get_sat_lut may evict a table: nothing in flight may read it
+    b200m_plan p;
+    std::memset(&p, 0, sizeof p);
+    p.sat_lut = sat_lut; p.sat_lut_key = key;
+    ++h->tab_tick;
+    const float *d_lut = nullptr;
+    int rc = get_sat_lut(h, p, &d_lut);
+    if (rc) return rc;
+    return elementwise(h, pcm, n * 2, out, n * 4, [&](char *di, char *dn) {
+        LAUNCH("k_saturation_pcm", k_saturation_pcm<<<grid_for(n), 256, 0, h->stream>>>((const int16_t *)di, n, d_lut, (float *)dn));
     });
 }
 

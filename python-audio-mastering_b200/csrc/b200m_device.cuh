@@ -59,6 +59,7 @@ struct PlanDev {
     const int32_t *ptree;         // numpy pairwise-sum tree of a full 400 ms block (k_blocks), or NULL
     const int32_t *htree;         // the same for one 100 ms hop when the block tree is four hop trees (k_hops), or NULL
     int32_t hop, pad2_;           // hop length in samples (0: no hop sharing at this rate)
+    const float *sat_lut;         // sat_on: 2^15 * exciter(s / 2^15) for the 65536 int16 samples s, indexed by (uint16_t)s (ENG:128-134)
     SecTab eq[4], lp[2], hp[2], kw[2];
 };
 
@@ -199,7 +200,9 @@ __device__ __forceinline__ int quant16s(double ys)
     return (int)(short)iv;
 }
 
-// ENG:128-134 in float32 with every product / sum separately rounded (numpy semantics).
+// ENG:128-134 in float32 with every product / sum separately rounded (numpy semantics), for the stand-alone
+// apply_saturation helper on arbitrary floats (tanhf: <= 1 ulp from numpy's SIMD tanh).  The chain kernels
+// never call it: their inputs are int16 / 2^15, so they gather from PlanDev::sat_lut, which the host tabulated.
 __device__ __forceinline__ float exciter(float x, float clean, float mix, float drive)
 {
     float t = tanhf(__fmul_rn(x, drive));

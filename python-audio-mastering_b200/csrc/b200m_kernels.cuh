@@ -98,7 +98,7 @@ k_chain(const int16_t *__restrict__ pcm_in, const StreamDesc *__restrict__ strea
         for (int i = tid; i < 8 * CH * 2; i += NT) carry[i] = 0.0;
     }
     const int sat_on = pl->sat_on, n_eq = pl->n_eq, width_on = pl->width_on, multiband = pl->multiband;
-    const float s_clean = pl->sat_clean, s_mix = pl->sat_mix, s_drive = pl->sat_drive;
+    const float *__restrict__ lut = pl->sat_lut;
     const double width = pl->width;
     const float widthf = (float)width;
 
@@ -137,21 +137,21 @@ k_chain(const int16_t *__restrict__ pcm_in, const StreamDesc *__restrict__ strea
         const bool store = t0 >= seg_begin;          // warm-up tiles only advance the filter states
         const int nvalid = store ? min(TILE, seg_end - t0) : 0;
         // ---- stage: interleaved int16 -> planar float32 (+ exciter), ENG:117-134 ---------
+        // Everything up to quantise #1 runs on 2^15 x: the filters and the widener are linear and scaling by
+        // a power of two commutes with every rounding, so the quantiser sees fl(2^15 y) without a multiply.
+        // The exciter is a pure function of the int16 sample: one gather from the host-tabulated table.
         asm volatile("cp.async.wait_group 0;" ::: "memory");
 #pragma unroll
         for (int k = 0; k < FPT; ++k) {
             const int f = tid + k * NT;
             const int rw = sraw[f];
             float v[CH];
-            if (CH == 2) {
-                v[0] = (float)(short)(rw & 0xffff) * (1.0f / 32768.0f);
-                v[CH - 1] = (float)(rw >> 16) * (1.0f / 32768.0f);
-            } else {
-                v[0] = (float)rw * (1.0f / 32768.0f);
-            }
             if (sat_on) {
-#pragma unroll
-                for (int q = 0; q < CH; ++q) v[q] = exciter(v[q], s_clean, s_mix, s_drive);
+                v[0] = __ldg(lut + (rw & 0xffff));
+                if (CH == 2) v[CH - 1] = __ldg(lut + ((unsigned)rw >> 16));
+            } else {
+                v[0] = (float)(short)(rw & 0xffff);
+                if (CH == 2) v[CH - 1] = (float)(rw >> 16);
             }
 #pragma unroll
             for (int q = 0; q < CH; ++q) sx[q * TILE_PAD + pidx(f)] = v[q];
@@ -208,7 +208,7 @@ k_chain(const int16_t *__restrict__ pcm_in, const StreamDesc *__restrict__ strea
         if (!multiband) {
             // ---- quantise #1 -> proc --------------------------------------------------
 #pragma unroll
-            for (int n = 0; n < SEG; ++n) q[n] = quant16<NANCHK>(x[n]);
+            for (int n = 0; n < SEG; ++n) q[n] = quant16s<NANCHK>(x[n]);
             stage_q16(myq, q);
             __syncthreads();
             store_q16_tile<CH>(proc + (sd.out_off + t0) * CH, stq, nvalid, tid);
@@ -217,7 +217,7 @@ k_chain(const int16_t *__restrict__ pcm_in, const StreamDesc *__restrict__ strea
             // ---- quantise #1, re-float (ENG:199), crossover ------------------------------
 #pragma unroll
             for (int n = 0; n < SEG; ++n) {
-                const float u = (float)quant16<NANCHK>(x[n]) * (1.0f / 32768.0f);
+                const float u = (float)quant16s<NANCHK>(x[n]);     // 2^15 u of ENG:199: the crossover stays in the scaled domain
                 myx[n] = u;
                 x[n] = (double)u;
             }
@@ -230,7 +230,7 @@ k_chain(const int16_t *__restrict__ pcm_in, const StreamDesc *__restrict__ strea
 #pragma unroll
             for (int n = 0; n < SEG; ++n) {
                 const double u = (double)myx[n];
-                q[n] = quant16<NANCHK>(x[n]);
+                q[n] = quant16s<NANCHK>(x[n]);
                 rest[n] = __dsub_rn(u, x[n]);
                 x[n] = u;
             }
@@ -240,10 +240,10 @@ k_chain(const int16_t *__restrict__ pcm_in, const StreamDesc *__restrict__ strea
             section_round<4>(x, tabs[7], tabs[7].Q, carry + (7 * CH + c) * 2,
                              wtot + (((round & 1) * CH + c) * 4) * 2, lane, wid, j == 0); ++round;
 #pragma unroll
-            for (int n = 0; n < SEG; ++n) q[n] = quant16<NANCHK>(__dsub_rn(rest[n], x[n]));
+            for (int n = 0; n < SEG; ++n) q[n] = quant16s<NANCHK>(__dsub_rn(rest[n], x[n]));
             stage_q16(myq + 1 * CH * NSEG * QW, q);
 #pragma unroll
-            for (int n = 0; n < SEG; ++n) q[n] = quant16<NANCHK>(x[n]);
+            for (int n = 0; n < SEG; ++n) q[n] = quant16s<NANCHK>(x[n]);
             stage_q16(myq + 2 * CH * NSEG * QW, q);
             __syncthreads();
 #pragma unroll
@@ -485,10 +485,11 @@ k_chainw(const int16_t *__restrict__ pcm_in, const StreamDesc *__restrict__ stre
     if (sg.begin >= sg.end) return;
     const StreamDesc sd = streams[sg.owner];
     const int sat_on = pl->sat_on, n_eq = pl->n_eq, width_on = pl->width_on, multiband = pl->multiband;
-    const float s_clean = pl->sat_clean, s_mix = pl->sat_mix, s_drive = pl->sat_drive;
+    const float *__restrict__ lut = pl->sat_lut;
     const double width = pl->width;
     const float widthf = (float)width;
     const int c = CH == 2 ? lane >> 4 : 0, j = CH == 2 ? lane & 15 : lane;
+    const unsigned csel = c ? 0x4432u : 0x4410u;                        // __byte_perm selector: this lane's channel of a packed frame
 
     const int16_t *__restrict__ in = pcm_in + sd.in_off * CH;
     const bool in16 = (reinterpret_cast<unsigned long long>(in) & 15ull) == 0;
@@ -539,9 +540,12 @@ k_chainw(const int16_t *__restrict__ pcm_in, const StreamDesc *__restrict__ stre
         asm volatile("cp.async.wait_group 0;" ::: "memory");
         __syncwarp();
         // ---- int16 -> float32 (+ exciter), ENG:117-134: this lane's 16 samples of its channel ----------
+        // Everything up to quantise #1 runs on 2^15 x (linear stages, power-of-two scale: every rounding is the
+        // reference's, and the quantiser needs no multiply).  The exciter is a pure function of the int16
+        // sample: one gather from the table the host tabulated with numpy (PlanDev::sat_lut, pre-scaled).
         double x[SEG];
         {
-            float v[SEG];
+            unsigned s16[SEG];                       // the lane's 16 samples as uint16 bit patterns
             if (CH == 2) {
                 const uint4 *rp = reinterpret_cast<const uint4 *>(raw + W::RSTRIDE * j);
 #pragma unroll
@@ -549,8 +553,7 @@ k_chainw(const int16_t *__restrict__ pcm_in, const StreamDesc *__restrict__ stre
                     const uint4 w = rp[i];
                     const unsigned ww[4] = {w.x, w.y, w.z, w.w};
 #pragma unroll
-                    for (int k = 0; k < 4; ++k)
-                        v[4 * i + k] = (float)(c ? (int)ww[k] >> 16 : (int)(short)(ww[k] & 0xffffu)) * (1.0f / 32768.0f);
+                    for (int k = 0; k < 4; ++k) s16[4 * i + k] = __byte_perm(ww[k], 0u, csel);
                 }
             } else {
                 const uint4 *rp = reinterpret_cast<const uint4 *>(raw + W::RSTRIDE * j);
@@ -560,17 +563,21 @@ k_chainw(const int16_t *__restrict__ pcm_in, const StreamDesc *__restrict__ stre
                     const unsigned ww[4] = {w.x, w.y, w.z, w.w};
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
-                        v[8 * i + 2 * k] = (float)(int)(short)(ww[k] & 0xffffu) * (1.0f / 32768.0f);
-                        v[8 * i + 2 * k + 1] = (float)((int)ww[k] >> 16) * (1.0f / 32768.0f);
+                        s16[8 * i + 2 * k] = ww[k] & 0xffffu;
+                        s16[8 * i + 2 * k + 1] = ww[k] >> 16;
                     }
                 }
             }
             if (sat_on) {
+                float v[SEG];
 #pragma unroll
-                for (int n = 0; n < SEG; ++n) v[n] = exciter(v[n], s_clean, s_mix, s_drive);
+                for (int n = 0; n < SEG; ++n) v[n] = __ldg(lut + s16[n]);      // all 16 gathers in flight together
+#pragma unroll
+                for (int n = 0; n < SEG; ++n) x[n] = (double)v[n];
+            } else {
+#pragma unroll
+                for (int n = 0; n < SEG; ++n) x[n] = (double)(int)(short)s16[n];
             }
-#pragma unroll
-            for (int n = 0; n < SEG; ++n) x[n] = (double)v[n];
         }
         __syncwarp();                                // raw[] is free again
         if (t0 + WT < seg_end) fetch(t0 + WT);
@@ -608,7 +615,7 @@ k_chainw(const int16_t *__restrict__ pcm_in, const StreamDesc *__restrict__ stre
         const int64_t o0 = (sd.out_off + t0) * CH;
         if (!multiband) {
 #pragma unroll
-            for (int n = 0; n < SEG; ++n) q[n] = quant16<NANCHK>(x[n]);
+            for (int n = 0; n < SEG; ++n) q[n] = quant16s<NANCHK>(x[n]);
             store_q16_w<CH>(proc + o0, q, j, c, nvalid, out16);
         } else {
             // ---- quantise #1, re-float (ENG:199), crossover: run on 2^15 u, i.e. on the integer itself ----
@@ -618,7 +625,7 @@ k_chainw(const int16_t *__restrict__ pcm_in, const StreamDesc *__restrict__ stre
             double xh[SEG];
 #pragma unroll
             for (int n = 0; n < SEG; ++n) {
-                const int q1 = quant16<NANCHK>(x[n]);
+                const int q1 = quant16s<NANCHK>(x[n]);
                 sq[n] = q1;
                 x[n] = (double)q1;
                 xh[n] = x[n];
@@ -1948,6 +1955,13 @@ __global__ void k_saturation(const float *__restrict__ in, int64_t n, float clea
 {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
         out[i] = exciter(in[i], clean, mix, drive);
+}
+
+// ENG:117-134 on int16 samples: lut = 2^15 * exciter(s / 2^15) (PlanDev::sat_lut); the division by 2^15 is exact
+__global__ void k_saturation_pcm(const int16_t *__restrict__ in, int64_t n, const float *__restrict__ lut, float *__restrict__ out)
+{
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        out[i] = __ldg(lut + (unsigned)(unsigned short)in[i]) * (1.0f / 32768.0f);
 }
 
 template <typename T>

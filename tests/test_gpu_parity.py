@@ -3,15 +3,20 @@ the C-ABI (ctypes), against (1) the golden vectors produced by the UNCHANGED ref
 engine and (2) the CPU oracle on freshly seeded inputs.
 
 Tolerances (north star: <= 1e-4 FS, loudness within 0.01 LU, 16-bit within +-1 LSB):
-  * every stage except the float32 tanh exciter is compared BIT-EXACT;
-  * whole-chain cases with saturation == 0 are BIT-EXACT (samples and loudness);
-  * whole-chain cases with saturation != 0 inherit numpy's float32 tanh, a SIMD polynomial
-    that is neither correctly rounded nor the same on every CPU (AVX-512 / AVX2 / libm
-    dispatch): CUDA tanhf agrees with it on ~90 % of inputs and is within 1 ulp on the rest.
-    A 1-ulp difference flips a truncating quantiser (ENG:125) on ~1e-3 of samples by ONE LSB;
-    that LSB then passes through the make-up gain of ENG:219-222.  The bound is therefore
-    one LSB *ahead of the gain*: |diff| <= ceil(gain) LSB at the output, >= 99 % of samples
-    bit-exact, loudness within 1e-5 LU (north star: 0.01 LU).
+  * 16-bit output: BIT-EXACT in every whole-chain comparison, exciter on or off.  ENG:128-134 only
+    ever sees int16 / 2^15, so the exciter is a 65536-entry table that the host fills with numpy's own
+    float32 tanh (b200master/plan.py) and the kernels gather from.  numpy's tanh is a SIMD polynomial that
+    may differ by an ulp between CPU dispatch targets: comparisons with the on-box oracle use the box's
+    numpy on both sides; comparisons with the golden fixtures replay the table of the host that wrote
+    them (``conftest.golden_exciter``, tests/golden/exciter_tables.npz);
+  * loudness: within one ulp of log10 (<= 1e-12 LU);
+  * full-length tracks (8.64 M frames x 2 channels x 5 truncating quantisers): the blocked IIR scan is
+    within ~3e-14 of scipy's sequential DF2T, so a product within 1e-9 of an integer may truncate the
+    other way about once per 10^9 samples; those tests allow |diff| <= 1 LSB on <= 1e-5 of the samples
+    and report the count (none observed so far).
+  * the stand-alone helpers: every stage bit-exact (window RMS, attenuation trajectory, compressed
+    samples, K-weighted loudness, gain, limiters, quantisers), blocked-scan EQ within 1e-12 of sosfilt;
+    ``apply_saturation`` on arbitrary floats (not int16 / 2^15) uses tanhf: <= 1 ulp.
 """
 import json
 import math
@@ -20,11 +25,9 @@ import os
 import numpy as np
 import pytest
 
-from conftest import golden_names, load_golden
+from conftest import golden_exciter, golden_names, load_golden
 
 pytestmark = pytest.mark.gpu
-
-SAT_MIN_EXACT = 0.99     # see module docstring
 
 
 @pytest.fixture(scope="module")
@@ -38,29 +41,22 @@ def eng():
     assert e.launch_count() > n0, "no CUDA kernel was launched: the native path did not run"
 
 
-def _compare(out, ref, saturated, gain=None):
+def _compare(out, ref):
     assert out.shape == ref.shape
     d = np.abs(out.astype(np.int32) - ref.astype(np.int32))
-    if not saturated:
-        assert d.max(initial=0) == 0, f"{int((d != 0).sum())} samples differ, max {int(d.max())} LSB"
-    else:
-        lim = 1 if gain is None or not math.isfinite(gain) else max(1, math.ceil(gain))
-        assert d.max(initial=0) <= lim, f"max {int(d.max())} LSB > {lim} (= one LSB ahead of the x{gain} make-up gain)"
-        assert np.mean(d == 0) >= SAT_MIN_EXACT
+    assert d.max(initial=0) == 0, f"{int((d != 0).sum())} samples differ, max {int(d.max())} LSB"
 
 
 @pytest.mark.parametrize("name", golden_names())
 def test_golden_whole_chain(eng, name):
     g = load_golden(name)
-    outs, infos = eng.master([g["pcm"]], g["rate"], g["settings"])
-    sat = g["settings"].get("saturation", 0) != 0
-    _compare(outs[0], g["out"], sat, infos[0]["gain"])
+    with golden_exciter(g["settings"]):
+        outs, infos = eng.master([g["pcm"]], g["rate"], g["settings"])
+    _compare(outs[0], g["out"])
     if g["settings"].get("lufs") is not None:
         got, ref = infos[0]["loudness"], g["loudness"]
         if math.isinf(ref):
             assert got == ref
-        elif sat:
-            assert abs(got - ref) < 1e-5
         else:
             assert abs(got - ref) <= 1e-12, "loudness may differ by one ulp of log10 only"
 
@@ -69,9 +65,28 @@ def test_golden_batch_mixed_settings(eng):
     """Several tracks with different settings / lengths in ONE launch equal the per-track results."""
     names = ["cfg1_pop_44k", "cfg2_full_44k", "no_lufs_no_eq", "rock_custom_bands", "ragged_tail_a", "silence"]
     gs = [load_golden(n) for n in names]
-    outs, infos = eng.master([g["pcm"] for g in gs], 44100, [g["settings"] for g in gs])
-    for g, o, i in zip(gs, outs, infos):
-        _compare(o, g["out"], g["settings"].get("saturation", 0) != 0, i["gain"])
+    with golden_exciter([g["settings"] for g in gs]):
+        outs, infos = eng.master([g["pcm"] for g in gs], 44100, [g["settings"] for g in gs])
+    for g, o in zip(gs, outs):
+        _compare(o, g["out"])
+
+
+def test_exciter_table_is_numpys(eng):
+    """ENG:117-134 through the table path vs numpy on THIS host, for every int16 value and several drives;
+    and the library's own libm table (non-Python hosts, sat_lut == NULL) is within one ulp of it."""
+    from b200master.plan import exciter_table
+    s16 = np.arange(65536, dtype=np.uint16).view(np.int16)
+    x = s16.astype(np.float32) / (2 ** 15)
+    for pct in (25, 3.5, 100, 250):
+        mix = (pct / 100.0) ** 2
+        ref = (1 - mix) * x + mix * np.tanh(x * (1 + mix * 4))
+        got = eng.saturation(x, pct)
+        assert np.array_equal(got.view(np.int32), ref.view(np.int32)), f"saturation {pct}"
+        assert np.array_equal(exciter_table(pct).view(np.int32), ref.view(np.int32))
+    own = eng.saturation(x + np.float32(1e-7), 25)              # not int16 / 2^15: the tanhf path
+    ref = (1 - 0.0625) * (x + np.float32(1e-7)) + 0.0625 * np.tanh((x + np.float32(1e-7)) * 1.25)
+    ulp = np.abs(own.view(np.int32).astype(np.int64) - ref.astype(np.float32).view(np.int32))
+    assert ulp.max() <= 2
 
 
 def test_stage_goldens(eng):
@@ -82,9 +97,9 @@ def test_stage_goldens(eng):
     g = load_golden("stages")
     rate, st = g["rate"], g["settings"]
     assert np.array_equal(eng.pcm16_to_float(g["pcm"]), g["to_float"])
-    sat = eng.saturation(g["to_float"], 35)
-    ulp = np.abs(sat.view(np.int32).astype(np.int64) - g["saturation35"].view(np.int32))
-    assert ulp.max() <= 1                                   # float32 tanh: within one ulp
+    with golden_exciter(dict(saturation=35)):
+        sat = eng.saturation(g["to_float"], 35)
+    assert np.array_equal(sat.view(np.int32), g["saturation35"].view(np.int32))     # the table path: bit-exact
     eq = ame.apply_eq_to_samples(g["saturation35"], rate, st)
     assert np.abs(eq - g["eq"]).max() <= 1e-12              # blocked scan vs sequential DF2T
     assert np.abs(ame.apply_shelf_filter(g["to_float"][:, 0], rate, 250, 4.0, "low") - g["lowshelf_L"]).max() <= 1e-12
@@ -155,15 +170,16 @@ def test_recurrence_tiling_is_exact_for_any_tile_length(eng):
 
 @pytest.mark.parametrize("rate,seconds", [(44100, 61.0), (48000, 35.0)])
 def test_oracle_multi_chunk(eng, rate, seconds):
-    """Fresh seeded multi-chunk tracks (saturation 0 => bit-exact), oracle with the C compressor."""
+    """Fresh seeded multi-chunk tracks, exciter on and off: bit-exact against the on-box oracle (C compressor)."""
     from b200master import synth
     from oracle import port
     pcm = synth.make_track(50 + rate % 7, seconds, rate)
-    st = dict(bass_boost=4.0, mid_cut=3.0, presence_boost=1.0, treble_boost=3.0, width=1.2, multiband=True, lufs=-14.0)
-    outs, infos = eng.master([pcm], rate, st)
-    ref, info = port.master(pcm, rate, st)
-    assert np.array_equal(outs[0], ref)
-    assert abs(infos[0]["loudness"] - info["loudness"]) <= 1e-12, "loudness may differ by one ulp of log10 only"
+    for sat in (25, 0):
+        st = dict(bass_boost=4.0, mid_cut=3.0, presence_boost=1.0, treble_boost=3.0, saturation=sat, width=1.2, multiband=True, lufs=-14.0)
+        outs, infos = eng.master([pcm], rate, st)
+        ref, info = port.master(pcm, rate, st)
+        assert np.array_equal(outs[0], ref), f"saturation {sat}"
+        assert abs(infos[0]["loudness"] - info["loudness"]) <= 1e-12, "loudness may differ by one ulp of log10 only"
 
 
 def test_chunk_independence_and_batch_invariance(eng):
@@ -229,7 +245,7 @@ def test_drop_in_module_surface(eng, tmp_path):
     src = tmp_path / "in"; dst = tmp_path / "out"; src.mkdir()
     PcmSegment(pcm.tobytes(), 2, rate, 2).export(str(src / "a.wav"))
     PcmSegment(pcm[::-1].copy().tobytes(), 2, rate, 2).export(str(src / "b.wav"))
-    st = dict(ame.EQ_PRESETS["pop"], saturation=0, width=1.1, multiband=True, lufs=-14.0,
+    st = dict(ame.EQ_PRESETS["pop"], saturation=12, width=1.1, multiband=True, lufs=-14.0,
               low_band_threshold=-28.0, low_band_ratio=5.0)           # GUI spelling (GUI:187-189)
     msgs = []
     ame.batch_process_audio(st, str(src), str(dst), msgs.append)
@@ -296,10 +312,10 @@ def test_ragged_unaligned_batch(eng, rate, channels):
     that are not multiples of four): chunk and track starts fall on addresses that are
     not 8 / 16-byte aligned, so every kernel takes its element-wise load / store path (k_chain tile
     stores, k_detect RMS quads, the recurrence's RMS rows, k_final's vector path).  Bit-exact against the
-    oracle (saturation 0), with both chain kernels."""
+    oracle (exciter on), with both chain kernels."""
     from b200master import synth
     from oracle import port
-    st = dict(bass_boost=3.0, mid_cut=2.0, presence_boost=1.5, treble_boost=2.0, width=1.15, multiband=True, lufs=-16.0)
+    st = dict(bass_boost=3.0, mid_cut=2.0, presence_boost=1.5, treble_boost=2.0, saturation=18, width=1.15, multiband=True, lufs=-16.0)
     lens = [31.013, 2.507, 30.0, 0.731]
     tracks = [synth.make_track(80 + i, s, rate, channels) for i, s in enumerate(lens)]
     tracks = [t[: t.shape[0] - (i % 3)] for i, t in enumerate(tracks)]          # odd frame counts
@@ -323,12 +339,17 @@ def test_loudness_sweep_shares_the_chain(eng):
     st = dict(bass_boost=2.0, presence_boost=3.5, treble_boost=2.5, saturation=15, width=1.1, multiband=True)
     tracks = [synth.make_track(90, 31.0, rate), synth.make_track(91, 2.25, rate), synth.make_track(92, 12.0, rate)]
     targets = [-9.0, -14.0, -23.0]
+    from oracle import port
     outs, infos = eng.master_targets(tracks, rate, st, targets)
     for k, tgt in enumerate(targets):
         ref, rinfo = eng.master(tracks, rate, dict(st, lufs=tgt))
         for t in range(len(tracks)):
             assert np.array_equal(outs[k][t], ref[t]), f"target {tgt}, track {t}"
             assert infos[t]["loudness"] == rinfo[t]["loudness"] and infos[t]["gain"][k] == rinfo[t]["gain"]
+            o_ref, o_info = port.master(tracks[t], rate, dict(st, lufs=tgt))          # the checker is the oracle, not the library
+            assert np.array_equal(outs[k][t], o_ref), f"oracle: target {tgt}, track {t}"
+            assert abs(infos[t]["loudness"] - o_info["loudness"]) <= 1e-12
+            assert infos[t]["gain"][k] == pytest.approx(o_info["gain"], rel=1e-12)
     with pytest.raises(ValueError):
         eng.master_targets(tracks, rate, st, [])            # the C-ABI wants 1..64 targets
 
@@ -364,6 +385,7 @@ def test_worker_jobs_share_one_batch(eng, monkeypatch):
     import audio_mastering_engine as ame
     from b200master import synth
     from b200master.segment import PcmSegment
+    from oracle import port
 
     store = {}
 
@@ -404,6 +426,11 @@ def test_worker_jobs_share_one_batch(eng, monkeypatch):
         g = io.BytesIO()
         ref.export(g, format="wav")
         assert store[key] == g.getvalue()
+        # the arithmetic of the uploaded file is the oracle's (ENG:46-89 on the decoded PCM), header included
+        o_ref, _ = port.master(synth.make_track(97 + i, 2.0 + i, rate), rate, st)
+        g2 = io.BytesIO()
+        PcmSegment(o_ref.tobytes(), 2, rate, 2).export(g2, format="wav")
+        assert store[key] == g2.getvalue()
     batch0 = store["bkt/processed/mastered_song0.wav"]
     ame.process_audio_from_gcs(*jobs[0])                    # the single-job entry point is the batch of one
     assert store["bkt/processed/mastered_song0.wav"] == batch0
@@ -436,6 +463,7 @@ def test_full_size_batch_properties(eng):
         torch.cuda.synchronize()
         return out, loud, gain
 
+    from oracle import port
     try:
         eng.set_chain_kernel(0)
         full, loud, gain = run(d_in)
@@ -443,6 +471,13 @@ def test_full_size_batch_properties(eng):
             alone, l1, g1 = run(d_in[t:t + 1].contiguous())
             assert torch.equal(alone[0], full[t]), f"track {t} depends on its batch"
             assert l1[0] == loud[t] and g1[0] == gain[t]
+            # (0) the rows of the timed batch ARE the reference's result: the oracle on the same bytes (C compressor loop)
+            ref, info = port.master(d_in[t].cpu().numpy(), rate, st)
+            d = np.abs(full[t].cpu().numpy().astype(np.int32) - ref.astype(np.int32))
+            print(f"full-size track {t}: {int((d != 0).sum())} of {d.size} samples differ from the oracle, max {int(d.max())} LSB, "
+                  f"loudness {loud[t]!r} vs {info['loudness']!r}")
+            assert d.max() <= 1 and np.mean(d != 0) <= 1e-5, "see the module docstring: full-length tolerance"
+            assert abs(loud[t] - info["loudness"]) <= 1e-9
         eng.set_chain_kernel(1)
         full1, _, _ = run(d_in)
         assert torch.equal(full1, full), "k_chain and k_chainw disagree on the full batch"

@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(lib, n), f"{n} declared in include/b200_master.h but not exported"
     assert set(names) == set(L.EXPORTS)
-    assert lib.b200m_abi_version() == 1
+    assert lib.b200m_abi_version() == L.ABI_VERSION == 2
 
 
 def test_no_cpu_fallback_without_device(has_cuda):
@@ -151,7 +151,7 @@ def test_struct_layouts_match_the_header(tmp_path):
     subprocess.check_call(["gcc", str(src), "-o", str(exe)])
     sizes = [int(v) for v in subprocess.check_output([str(exe)]).split()]
     assert sizes == [C.sizeof(L.Plan), C.sizeof(L.Band), C.sizeof(L.Biquad), C.sizeof(L.Settings)]
-    assert sizes[0] == 576
+    assert sizes[0] == 592
 
 
 def test_wav_header_is_the_wave_modules():
