@@ -657,8 +657,11 @@ static int ensure_plans(b200m_handle *h, const b200m_plan *plans, int n)
                     hold_max = r - 1;
                     for (; r < CURVE_N; ++r) if (tab[r] == 0.0) { hold_max = -1; break; }
                 }
+                // the recurrence keeps 0 <= att <= max(curve) when every curve value is finite and >= +0
+                bool bounded = true;
+                for (double m : tab) if (!(m >= 0.0) || !(m <= 5000.0) || std::signbit(m)) { bounded = false; break; }
                 d.band[b] = {bb.thresh_rms, bb.attack_frames, bb.release_frames, bb.slope,
-                             1.0 / bb.attack_frames, 1.0 / bb.release_frames, bb.look_frames, trick ? 1 : 0, hold_max, 0};
+                             1.0 / bb.attack_frames, 1.0 / bb.release_frames, bb.look_frames, trick ? 1 : 0, hold_max, bounded ? 1 : 0};
             }
         }
     }
@@ -723,7 +726,10 @@ extern "C" int b200m_create(int device, b200m_handle **out)
     if (e == cudaSuccess) e = allow_smem(k_chainw<2, false, false>, ChainW<2>::SMEM);
     if (e == cudaSuccess) e = allow_smem(k_detect<1>, detect_smem_bytes(8192));
     if (e == cudaSuccess) e = allow_smem(k_detect<2>, detect_smem_bytes(8192));
-    if (e == cudaSuccess) e = allow_smem(k_recur_tiles, recur_smem_bytes());
+    if (e == cudaSuccess) e = allow_smem(k_comp<1, 1>, recur_smem_bytes(1));
+    if (e == cudaSuccess) e = allow_smem(k_comp<2, 1>, recur_smem_bytes(1));
+    if (e == cudaSuccess) e = allow_smem(k_comp<1, 3>, recur_smem_bytes(3));
+    if (e == cudaSuccess) e = allow_smem(k_comp<2, 3>, recur_smem_bytes(3));
     if (e == cudaSuccess) e = allow_smem(k_kweight<1, int16_t, true>, kweight_smem_bytes());
     if (e == cudaSuccess) e = allow_smem(k_kweight<2, int16_t, true>, kweight_smem_bytes());
     if (e == cudaSuccess) e = allow_smem(k_kweight<1, float, true>, kweight_smem_bytes());
@@ -917,20 +923,22 @@ struct Group {
     int single_plan = -1;            // >= 0: every stream of the group uses this plan (its tables travel as a kernel parameter)
 };
 
+#ifndef B200M_COMP_CTAS
+#define B200M_COMP_CTAS 4           // resident CTAs per SM (48 KB of shared memory each) k_comp's automatic tile length aims at
+#endif
 static RecurParams recur_params(const b200m_handle *h, const Group &g, int nbands, int band_base)
 {
-    const int chains = std::max(1, g.n_streams * nbands);
     RecurParams P;
     P.nbands = nbands; P.band_base = band_base; P.n_streams = g.n_streams;
     P.warm = std::max(32, (h->recur_warm + 31) & ~31);
     if (h->recur_tile > 0) {
         P.tile_len = std::max(32, (h->recur_tile + 31) & ~31);
     } else {
-        // about three quarters of a resident wave of (chain, tile) lanes (148 SMs x 12 warps x 32); tiles of 2048 ..
-        // 65536 frames: every lane also runs the warm-up (`warm` active frames), so long tiles waste
-        // less work (measured: 32768-frame tiles beat 16384 by 1.28x on a 64-track batch) and short
-        // tiles give a small batch enough lanes
-        const double want_tiles = 148.0 * 12 * 32 / chains;
+        // One lane per (stream, tile), one warp per band: about one resident wave of lanes (148 SMs x
+        // B200M_COMP_CTAS CTAs x 32); tiles of 2048 .. 65536 frames.  Every lane also runs the warm-up
+        // (`warm` active frames, level detector -> curve -> recurrence only), so long tiles waste less
+        // work and short tiles give a small batch enough lanes.
+        const double want_tiles = 148.0 * B200M_COMP_CTAS * 32 / std::max(1, g.n_streams);
         const double len = std::min(65536.0, std::max(2048.0, g.max_stream_frames / want_tiles));
         P.tile_len = ((int)len + 1023) & ~1023;
     }
@@ -944,56 +952,59 @@ static size_t recur_spec_doubles(const b200m_handle *h, const Group &g, int nban
     return 4 * (size_t)g.n_streams * nbands * P.tiles;       // ss / se ping-pong
 }
 
-static size_t compressor_ws_bytes(const b200m_handle *h, const Group &g, int64_t F, int nbands)
+// debug_att: the per-frame attenuation trajectory is materialised too (b200m_compress_dynamic_range's att_out)
+static size_t compressor_ws_bytes(const b200m_handle *h, const Group &g, int64_t F, int nbands, bool debug_att = false)
 {
-    const size_t per_band = (size_t)F * 2 /*rms*/ + (size_t)F * 8 /*att*/ + (size_t)g.total_blocks * 4 /*hold*/ + 4 * 256;
+    const size_t per_band = (size_t)F * 2 /*rms*/ + (debug_att ? (size_t)F * 8 : 0) + (size_t)(g.total_blocks + 1) * (4 /*hold*/ + 32 * 8 /*bend*/) + 4 * 256;
     return nbands * per_band + recur_spec_doubles(h, g, nbands) * 8 + 256;
 }
 
-// rms / hold / att for `nbands` bands starting at band_base, and the speculation scratch
-static double *take_compressor_ws(b200m_handle *h, Arena &A, const Group &g, int64_t F, int nbands, int band_base, BandPtrs &bp)
+// rms / hold / bend (/ att) for `nbands` bands starting at band_base, and the speculation scratch
+static double *take_compressor_ws(b200m_handle *h, Arena &A, const Group &g, int64_t F, int nbands, int band_base, BandPtrs &bp, bool debug_att = false)
 {
     for (int b = band_base; b < band_base + nbands; ++b) bp.rms[b] = A.take<uint16_t>(F);
-    for (int b = band_base; b < band_base + nbands; ++b) bp.att[b] = A.take<double>(F);
+    for (int b = band_base; b < band_base + nbands; ++b) bp.att[b] = debug_att ? A.take<double>(F) : nullptr;
     for (int b = band_base; b < band_base + nbands; ++b) bp.hold[b] = A.take<uint32_t>(g.total_blocks + 1);
+    for (int b = band_base; b < band_base + nbands; ++b) bp.bend[b] = A.take<double>((size_t)(g.total_blocks + 1) * 32);
     return A.take<double>(recur_spec_doubles(h, g, nbands));
 }
 
 static int launch_compressor(b200m_handle *h, const Group &g, const BandPtrs &bp, int nbands, int band_base, int16_t *d_proc, double *d_spec)
 {
+    if (!((nbands == 3 && band_base == 0) || nbands == 1))
+        return fail(h, B200M_ERR_INVALID, "internal: compressor runs on one band or on all three");
     const dim3 gd((g.max_stream_frames + DT - 1) / DT, g.n_streams, nbands);
     const size_t smem = detect_smem_bytes(g.max_look);
     if (g.ch == 2) LAUNCH("k_detect", k_detect<2><<<gd, DNT, smem, h->stream>>>(g.d_streams, h->d_plans, bp, band_base));
     else           LAUNCH("k_detect", k_detect<1><<<gd, DNT, smem, h->stream>>>(g.d_streams, h->d_plans, bp, band_base));
-    const int chains = g.n_streams * nbands;
     const RecurParams P = recur_params(h, g, nbands, band_base);
-    const size_t lanes = (size_t)chains * P.tiles;
+    const size_t lanes = (size_t)g.n_streams * P.tiles;              // one lane per (stream, tile), all bands
+    const size_t slots = lanes * nbands;
     RecurParams P0 = P;
     P0.mode = 0;
-    double *ss[2] = {d_spec, d_spec + 2 * lanes}, *se[2] = {d_spec + lanes, d_spec + 3 * lanes};
-    const unsigned gr = (unsigned)((lanes + 32 * RW - 1) / (32 * RW));
-    const size_t rs = recur_smem_bytes();
-    LAUNCH("k_recur_tiles", k_recur_tiles<<<gr, 32 * RW, rs, h->stream>>>(g.d_streams, h->d_plans, P0, bp, nullptr, nullptr, ss[0], se[0], h->d_counters));
+    double *ss[2] = {d_spec, d_spec + 2 * slots}, *se[2] = {d_spec + slots, d_spec + 3 * slots};
+    const unsigned gr = (unsigned)((lanes + 31) / 32);
+#define LAUNCH_COMP(NAME, PP, SSI, SEI, SSO, SEO) do { \
+        if (nbands == 3) { if (g.ch == 2) LAUNCH(NAME, k_comp<2, 3><<<gr, 96, recur_smem_bytes(3), h->stream>>>(g.d_streams, h->d_plans, PP, bp, d_proc, SSI, SEI, SSO, SEO, h->d_counters)); \
+                           else           LAUNCH(NAME, k_comp<1, 3><<<gr, 96, recur_smem_bytes(3), h->stream>>>(g.d_streams, h->d_plans, PP, bp, d_proc, SSI, SEI, SSO, SEO, h->d_counters)); } \
+        else             { if (g.ch == 2) LAUNCH(NAME, k_comp<2, 1><<<gr, 32, recur_smem_bytes(1), h->stream>>>(g.d_streams, h->d_plans, PP, bp, d_proc, SSI, SEI, SSO, SEO, h->d_counters)); \
+                           else           LAUNCH(NAME, k_comp<1, 1><<<gr, 32, recur_smem_bytes(1), h->stream>>>(g.d_streams, h->d_plans, PP, bp, d_proc, SSI, SEI, SSO, SEO, h->d_counters)); } } while (0)
+    LAUNCH_COMP("k_comp", P0, nullptr, nullptr, ss[0], se[0]);
     int cur = 0;
     if (P.tiles > 1) {
         RecurParams P1 = P;
         P1.mode = 1;
         for (int round = 0; round < h->recur_rounds; ++round) {      // parallel repair rounds
-            LAUNCH("k_recur_repair", k_recur_tiles<<<gr, 32 * RW, rs, h->stream>>>(g.d_streams, h->d_plans, P1, bp, ss[cur], se[cur], ss[cur ^ 1], se[cur ^ 1], h->d_counters));
+            LAUNCH_COMP("k_comp_repair", P1, ss[cur], se[cur], ss[cur ^ 1], se[cur ^ 1]);
             cur ^= 1;
         }
     }
-    LAUNCH("k_recur_fix", k_recur_fix<<<(chains + 3) / 4, 128, 0, h->stream>>>(g.d_streams, h->d_plans, P, bp, ss[cur], se[cur], h->d_counters));
-    const dim3 ga((g.max_stream_frames + 511) / 512, g.n_streams);
-    if (nbands == 3 && band_base == 0) {
-        if (g.ch == 2) LAUNCH("k_apply", k_apply<2, 3><<<ga, 256, 0, h->stream>>>(g.d_streams, h->d_plans, bp, 0, d_proc));
-        else           LAUNCH("k_apply", k_apply<1, 3><<<ga, 256, 0, h->stream>>>(g.d_streams, h->d_plans, bp, 0, d_proc));
-    } else if (nbands == 1) {
-        if (g.ch == 2) LAUNCH("k_apply", k_apply<2, 1><<<ga, 256, 0, h->stream>>>(g.d_streams, h->d_plans, bp, band_base, d_proc));
-        else           LAUNCH("k_apply", k_apply<1, 1><<<ga, 256, 0, h->stream>>>(g.d_streams, h->d_plans, bp, band_base, d_proc));
-    } else {
-        return fail(h, B200M_ERR_INVALID, "internal: compressor runs on one band or on all three");
-    }
+#undef LAUNCH_COMP
+    const unsigned gfx = (unsigned)((g.n_streams + 3) / 4);
+    if (nbands == 3) { if (g.ch == 2) LAUNCH("k_comp_fix", k_comp_fix<2, 3><<<gfx, 128, 0, h->stream>>>(g.d_streams, h->d_plans, P, bp, d_proc, ss[cur], se[cur], h->d_counters));
+                       else           LAUNCH("k_comp_fix", k_comp_fix<1, 3><<<gfx, 128, 0, h->stream>>>(g.d_streams, h->d_plans, P, bp, d_proc, ss[cur], se[cur], h->d_counters)); }
+    else             { if (g.ch == 2) LAUNCH("k_comp_fix", k_comp_fix<2, 1><<<gfx, 128, 0, h->stream>>>(g.d_streams, h->d_plans, P, bp, d_proc, ss[cur], se[cur], h->d_counters));
+                       else           LAUNCH("k_comp_fix", k_comp_fix<1, 1><<<gfx, 128, 0, h->stream>>>(g.d_streams, h->d_plans, P, bp, d_proc, ss[cur], se[cur], h->d_counters)); }
     CK(cudaGetLastError());
     return B200M_OK;
 }
@@ -1373,7 +1384,7 @@ static int master_batch_impl(b200m_handle *h, const void *pcm_in, int in_on_devi
     // ---- cut the batch into groups ---------------------------------------------------------
     // a group must fit one workspace slot; with host buffers it is also at most ~1/8 of the batch
     // (and at least ~8 M frames) so that copies and kernels of neighbouring groups overlap
-    const double per_frame = ch * 2 * (2 + std::max(1, n_targets)) + 4 + 3 * (ch * 2 + 2 + 8) + 2;
+    const double per_frame = ch * 2 * (2 + std::max(1, n_targets)) + 4 + 3 * (ch * 2 + 2 + 0.26) + 2;
     const double slot_limit = (double)h->ws_limit / slots;
     const double pipe_frames = pipelined ? std::max<double>(8e6, (double)total_frames / (double)h->pipe_groups) : 1e300;
     std::vector<GroupPlan> gps;
@@ -1899,7 +1910,7 @@ extern "C" int b200m_compress_dynamic_range(b200m_handle *h, const int16_t *pcm,
     g.ch = channels; g.n_streams = 1; g.n_tracks = 1; g.max_stream_frames = (int)nframes;
     g.max_look = band->look_frames;
     g.total_blocks = (nframes + 1023) / 1024;
-    rc = ws_reserve(h, 16384 + F * channels * 2 * 2 + compressor_ws_bytes(h, g, (int64_t)F, 1));
+    rc = ws_reserve(h, 16384 + F * channels * 2 * 2 + compressor_ws_bytes(h, g, (int64_t)F, 1, att_out != nullptr));
     if (rc) return rc;
     Arena A(h->ws);
     StreamDesc *d_streams = A.take<StreamDesc>(1);
@@ -1908,7 +1919,7 @@ extern "C" int b200m_compress_dynamic_range(b200m_handle *h, const int16_t *pcm,
     BandPtrs bp;
     std::memset(&bp, 0, sizeof bp);
     bp.band[0] = d_in;
-    double *d_spec = take_compressor_ws(h, A, g, (int64_t)F, 1, 0, bp);
+    double *d_spec = take_compressor_ws(h, A, g, (int64_t)F, 1, 0, bp, att_out != nullptr);
     StreamDesc sd = {0, 0, (int32_t)nframes, (int32_t)nframes, 0, 0, 0, 0};
     CK(cudaMemcpyAsync(d_streams, &sd, sizeof sd, cudaMemcpyHostToDevice, h->stream));
     CK(cudaMemcpyAsync(d_in, pcm, F * channels * 2, cudaMemcpyHostToDevice, h->stream));

@@ -43,7 +43,7 @@ struct BandDev {
     int32_t look;                 // int(attack_frames)
     int32_t div_trick;            // 1: M/A and M/R via div_const are exact for this band's curve
     int32_t hold_max;             // curve[r] == 0 exactly for r <= hold_max (-1: no such prefix; then nothing is ever "held")
-    int32_t pad_;
+    int32_t att_bounded;          // 1: 0 <= attenuation <= 5000 dB whatever the input (curve finite, >= +0, max <= 5000): 10^(-att/20) needs no underflow path
 };
 
 // Compressor static curve: max attenuation M for each of the 32769 possible integer RMS

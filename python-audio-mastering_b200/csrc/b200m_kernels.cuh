@@ -6,9 +6,10 @@ namespace b200m {
 
 struct BandPtrs {
     int16_t *band[3];    // in: quantised crossover bands (ENG:204-206), interleaved
-    uint16_t *rms[3];    // per frame: integer window RMS (audioop.rms) -- k_detect -> k_recur_*
+    uint16_t *rms[3];    // per frame: integer window RMS (audioop.rms) -- k_detect -> k_comp
     uint32_t *hold[3];   // bit per 32-frame block of a stream: 1 = rms <= threshold in the whole block (state held)
-    double *att[3];      // per frame: attenuation trajectory (pydub's `attenuation`) -- k_recur_* -> k_apply
+    double *bend[3];     // per 32-frame block: pydub's `attenuation` after the block's last frame (merge test of the repair passes)
+    double *att[3];      // NULL, or per frame: the attenuation trajectory (debug output of b200m_compress_dynamic_range)
 };
 
 // =====================================================================================
@@ -855,10 +856,11 @@ k_detect(const StreamDesc *__restrict__ streams, const PlanDev *__restrict__ pla
 }
 
 // =====================================================================================
-// k_recur_count / k_recur_tiles / k_recur_fix: pydub compress_dynamic_range after the level
-// detector (ENG:207-209 run per chunk, state reset to 0 at every chunk): static curve,
-// attenuation recurrence and gain application, fused.  With M_i = curve[rms_i] the per-frame
-// maximum attenuation (M_i != 0  <=>  rms_i > threshold):
+// k_comp / k_comp_fix: pydub compress_dynamic_range after the level detector (ENG:207-209 run per
+// chunk, state reset to 0 at every chunk) for ALL bands of a stream, fused with the gain
+// application and the overlay (ENG:210): static curve, attenuation recurrence, 10^(-att/20),
+// audioop.mul, two saturating adds -- the attenuation trajectory never goes to HBM.  With
+// M_i = curve[rms_i] the per-frame maximum attenuation (M_i != 0  <=>  rms_i > threshold):
 //   if M_i != 0 and att <= M_i:  att = min(att + M_i/A, M_i)   else  att = max(att - M_i/R, 0)
 //   frame_i *= 10^(-att/20) via audioop.mul (floor of the clamped product) when att != 0
 // Every decision of the recurrence is an integer compare on bit patterns (att >= +0 always), both
@@ -866,44 +868,44 @@ k_detect(const StreamDesc *__restrict__ streams, const PlanDev *__restrict__ pla
 // instructions, off the dependent chain).
 //
 // The recurrence is not a linear scan, but two trajectories coincide for ever
-// once they are equal, and clamps (att = M, att = 0) make them equal.  So each (stream, band)
-// chain is cut into time tiles, one lane per tile:
-//   mode 0  speculate: warm up over the preceding `warm` ACTIVE frames from att = 0 (no stores),
-//           then run the tile, recording the assumed start state and the reached end state;
-//   mode 1  repair round (Jacobi): every tile whose assumed start differs from its predecessor's
-//           current end state is re-run from that state until it meets its stored trajectory
-//           (compared at the end of every 32-frame block, bp.bend);
-// and k_recur_fix finally walks each chain's tiles in order and repairs, sequentially, whatever
+// once they are equal, and clamps (att = M, att = 0) make them equal.  So each stream is cut into
+// time tiles; a CTA takes 32 tiles, one lane each, and gives every band its own warp:
+//   mode 0  speculate: per band, warm up over the preceding `warm` ACTIVE frames from att = 0
+//           (no stores; held stretches are skipped via the hold words), then run the tile with
+//           the CTA's bands in lockstep, recording per band the assumed start state, the reached
+//           end state and the state at the end of every 32-frame block (bp.bend);
+//   mode 1  repair round (Jacobi): every tile in which some band's assumed start differs from its
+//           predecessor's current end state is re-run from those states (samples included) until
+//           all bands meet their stored trajectory at the end of a block;
+// and k_comp_fix finally walks each stream's tiles in order and repairs, sequentially, whatever
 // is still inconsistent -- so the result is exact for any input and any tile length, and the
 // sequential path only runs in the worst case.
 //
-// Data movement per 32-frame block of a warp (32 lanes = 32 different tiles): the 64-byte RMS
-// rows of the 32 tiles are brought into shared memory with cp.async
-// one block ahead; phase B expands RMS -> M row-wise (coalesced table gathers); phase C runs the
-// 32 dependent steps, one lane per tile; phase D stores the attenuation as coalesced 256-byte
-// rows.  HBM traffic per frame and band: 2 B in (plus warm-up re-reads), 8 B out.  The gain itself
-// (an fp64 exp10 per frame) is applied by k_apply at full occupancy.
+// Data movement per 32-frame block of a warp (32 lanes = 32 different tiles of one band): the 64-byte RMS
+// rows and the 128-byte sample rows of the 32 tiles are brought into shared memory with cp.async one
+// block ahead; phase B expands RMS -> M row-wise (one lane per frame: coalesced table gathers); then
+// every lane walks its own row: recurrence step, and -- off the dependent chain, so neighbouring frames
+// interleave -- 10^(-att/20) and the floor-multiply, leaving the compressed frames in shared memory;
+// after a CTA barrier the three bands' rows are overlaid row-wise (two saturating adds in band order)
+// and leave as coalesced 128-byte stores of `proc`.  HBM traffic per frame: 6 B of RMS and 12 B of band
+// samples in (plus warm-up re-reads of the RMS), 4 B out, 0.75 B of block-end states -- the fp64
+// attenuation rows (24 B written + 24 B read per frame when k_apply was a kernel of its own) never exist.
 // =====================================================================================
-constexpr int RW = 4;               // warps per CTA in k_recur_tiles
 #ifndef B200M_RECUR_GB
 #define B200M_RECUR_GB 32           // rows of curve gathers in flight per batch (phase B): 32 beats 16 by 1.4 ms per 64-track step
 #endif
-// -DB200M_RECUR_TIMING: lane 0 of every warp adds the cycles it spent per phase to counters[8 ..]
-// (build experiment only; scripts/gpu_recur_phases.py)
-#ifdef B200M_RECUR_TIMING
-#define RT_MARK(slot) do { const long long t_ = clock64(); rt_acc[slot] += t_ - rt_t; rt_t = t_; } while (0)
-#else
-#define RT_MARK(slot) do { } while (0)
-#endif
 
-struct RecurWarpSmem {
-    double m[32][33];               // M rows in (phase B), attenuation rows out (phase C -> D)
-    uint16_t rms[32][32];           // RMS rows
+constexpr int SROW = 36;            // 32-bit words per sample row (32 used; mono: 16): lane-serial 128-bit accesses stay conflict free
+struct RecurWarpSmem {              // one per warp = per band of the CTA's 32 (stream, tile) lanes
+    double m[32][34];               // M rows in (phase B, row-wise), read back lane-wise (128-bit) by the recurrence, which leaves
+                                    // the block's compressed frames in the first 128 bytes of each row
+    unsigned smp[32][SROW];         // band samples of the block being worked on: one packed frame per word (mono: two)
+    uint16_t rms[32][32];           // RMS rows of the block being worked on
     unsigned long long base_curve[32];
-    ulonglong2 row[32];             // per lane: {where its current block's attenuation row goes, frames to store (0 = warm-up)}:
-                                    // one 16-byte broadcast load per row in phase D (shared memory is this kernel's busiest unit)
+    ulonglong2 row[32];             // per lane: {first workspace frame of its current block, frames to produce (0 = none)}:
+                                    // one 16-byte broadcast load per row in the row-wise overlay
 };
-constexpr size_t recur_smem_bytes() { return RW * sizeof(RecurWarpSmem); }
+constexpr size_t recur_smem_bytes(int nb) { return (size_t)nb * (sizeof(RecurWarpSmem) + 32); }
 
 struct RecurParams {
     int tile_len, warm, tiles, nbands, band_base, n_streams, mode;
@@ -953,290 +955,6 @@ __device__ __forceinline__ int mul_floor16_le1(int v, double g)
     return __double2int_rd(__dmul_rn((double)v, g));
 }
 
-__global__ void __launch_bounds__(32 * RW)
-k_recur_tiles(const StreamDesc *__restrict__ streams, const PlanDev *__restrict__ plans, RecurParams P,
-              BandPtrs bp, const double *__restrict__ ss_in,
-              const double *__restrict__ se_in, double *__restrict__ ss_out, double *__restrict__ se_out,
-              unsigned long long *__restrict__ counters)
-{
-    extern __shared__ __align__(16) unsigned char recur_smem[];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    RecurWarpSmem &W = reinterpret_cast<RecurWarpSmem *>(recur_smem)[warp];
-    const int gl = (blockIdx.x * RW + warp) * 32 + lane;
-    const int chain = gl / P.tiles, tile = gl % P.tiles;
-    bool live = chain < P.n_streams * P.nbands;
-    int start = 0, end = 0, wstart = 0;
-    const uint32_t *hold = nullptr;
-    const double *attp = nullptr;
-    double A = 1.0, R = 1.0, rA = 1.0, rR = 1.0;
-    bool exact = true;
-    double a = 0.0;
-    W.base_curve[lane] = 0;
-    const uint16_t *my_rms = nullptr;
-    if (live) {
-        const int s = chain / P.nbands, band = P.band_base + chain % P.nbands;
-        const StreamDesc sd = streams[s];
-        const PlanDev *__restrict__ pl = plans + sd.plan;
-        start = tile * P.tile_len;
-        live = pl->multiband && start < sd.out_frames;
-        if (live) {
-            end = min(start + P.tile_len, sd.out_frames);
-            hold = bp.hold[band] + sd.blk_off;
-            attp = bp.att[band] + sd.out_off;
-            my_rms = bp.rms[band] + sd.out_off;
-            W.base_curve[lane] = (unsigned long long)pl->curve[band];
-            const BandDev &bd = pl->band[band];
-            A = bd.attack_frames; R = bd.release_frames; rA = bd.r_attack; rR = bd.r_release;
-            exact = bd.div_trick != 0;
-            const size_t slot = (size_t)chain * P.tiles + tile;
-            if (P.mode == 0) {
-                // warm up over the preceding frames until `warm` ACTIVE frames have been seen: walk the
-                // hold words (32 blocks = 1024 frames each) backwards; a held stretch carries the
-                // state unchanged, so it neither helps nor costs anything
-                int need = P.warm >> 5, wb = start >> 5;
-                while (wb > 0 && need > 0) {
-                    const int w = (wb - 1) >> 5, lo = w << 5, nbits = wb - lo;
-                    const unsigned mask = nbits == 32 ? 0xffffffffu : ((1u << nbits) - 1u);
-                    need -= nbits - __popc(hold[w] & mask);
-                    wb = lo;
-                }
-                wstart = wb << 5;
-            } else {
-                wstart = start;
-                const double mine = ss_in[slot], mine_end = se_in[slot];
-                const double prev = tile == 0 ? 0.0 : se_in[slot - 1];
-                if (tile == 0 || __double_as_longlong(mine) == __double_as_longlong(prev)) {
-                    ss_out[slot] = mine; se_out[slot] = mine_end;     // consistent: nothing to do
-                    live = false;
-                } else {
-                    a = prev;
-                    atomicAdd(&counters[2], 1ull);
-                }
-            }
-        }
-    }
-    const double a_in = a;
-    const bool all_exact = __all_sync(FULL, exact || !live);
-    // Every lane walks its own cursor over 32-frame blocks [wstart, end): held blocks of the
-    // warm-up are skipped outright (the state cannot change there), so the warp iterates
-    // max-over-lanes of the blocks that need work, not the span.
-    const int sb = start >> 5, eb = (end + 31) >> 5;
-    int hw_idx = -1;
-    unsigned hw_val = 0u;
-#define HOLD_WORD(w) (((w) != hw_idx) ? (hw_idx = (w), hw_val = hold[(w)]) : hw_val)   /* the hold word of blocks 32w .. 32w+31, kept while the cursor stays inside it */
-    auto skip_held = [&](int cb) {               // first block >= cb that needs work (warm-up part only)
-        if (live) {
-            while (cb < sb) {
-                const unsigned wv = HOLD_WORD(cb >> 5) >> (cb & 31);
-                if (!(wv & 1u)) break;
-                const int run = (~wv) ? __ffs(~wv) - 1 : 32;     // run of held blocks (shifted-in zeros end it)
-                cb = min(cb + run, sb);
-            }
-        }
-        return cb;
-    };
-    // The RMS rows of every lane's block `cbn` -> W.rms: 64 bytes per row, moved as 16-byte cp.async
-    // pieces, eight rows per instruction (lane l: row q0 + l / 4, piece l % 4, so every 32-byte sector is
-    // asked for once and the shared-memory side is one contiguous 512-byte span).  The source address
-    // of a row travels by shuffle from the lane that owns it.  Rows of held blocks, of lanes without
-    // work and the ragged last block of a stream are written by their owner: zeros (r = 0 gives
-    // M = 0, a hold, i.e. an identity step, so partial rows need no branches later) plus whatever
-    // valid elements there are.
-    const bool rms16 = (reinterpret_cast<unsigned long long>(my_rms) & 15ull) == 0;    // chunk starts at odd rates may not be
-    auto issue_rms = [&](int cbn, bool valid) {
-        const bool on_n = valid && cbn < eb;
-        const int i0n = cbn << 5;
-        const int cntn = on_n ? min(32, end - i0n) : 0;
-        const bool heldn = on_n && ((HOLD_WORD(cbn >> 5) >> (cbn & 31)) & 1u);
-        const bool work_n = on_n && !heldn;      // this lane's block can change its state
-        const uint16_t *srcp = (work_n && cntn == 32 && rms16) ? my_rms + i0n : nullptr;
-        if (srcp == nullptr) {
-            uint16_t *row = &W.rms[lane][0];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) reinterpret_cast<uint4 *>(row)[j] = make_uint4(0u, 0u, 0u, 0u);
-            if (work_n)
-                for (int k = 0; k < cntn; ++k) row[k] = my_rms[i0n + k];
-        }
-        const int sub = lane >> 2, piece = lane & 3;
-#pragma unroll
-        for (int q0 = 0; q0 < 32; q0 += 8) {
-            const unsigned long long p = __shfl_sync(FULL, (unsigned long long)srcp, q0 + sub);
-            if (p != 0ull) {
-                const unsigned sa = (unsigned)__cvta_generic_to_shared(&W.rms[q0 + sub][piece * 8]);
-                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(p + 16ull * piece) : "memory");
-            }
-        }
-        asm volatile("cp.async.commit_group;" ::: "memory");
-        return work_n;
-    };
-    __syncwarp();
-    int cb = skip_held(wstart >> 5);
-    bool work = issue_rms(cb, live);
-    double a_start = a;
-    bool merged = false;
-#ifdef B200M_RECUR_TIMING
-    long long rt_acc[6] = {0, 0, 0, 0, 0, 0}, rt_t = clock64();
-    const long long rt_begin = rt_t;
-    long long rt_blocks = 0;
-#endif
-    for (;;) {
-        const bool on = live && !merged && cb < eb;
-        if (!__any_sync(FULL, on)) break;
-#ifdef B200M_RECUR_TIMING
-        ++rt_blocks;
-#endif
-        const int i0 = cb << 5;
-        const int cnt = on ? min(32, end - i0) : 0;
-        const bool is_main = on && cb >= sb;
-        if (on && cb == sb) a_start = a;
-        // the value this tile stored earlier at the end of this block (repair rounds only)
-        double old_last = 0.0;
-        if (P.mode == 1 && on) old_last = attp[i0 + cnt - 1];
-        W.row[lane] = make_ulonglong2((unsigned long long)(attp + i0), (unsigned long long)(is_main ? cnt : 0));
-        const bool any_work = __any_sync(FULL, on && work);       // else every lane's block is held: att stays put
-        asm volatile("cp.async.wait_group 0;" ::: "memory");
-        __syncwarp();
-        RT_MARK(0);
-        // ---- phase B: RMS rows -> M rows through the static curve (row-wise: consecutive frames
-        //      have neighbouring RMS values, so a row's gathers touch a few cache lines) --------
-        // (B200M_RECUR_GB rows per batch: all their gathers are in flight together)
-        if (any_work) {
-#pragma unroll
-        for (int q0 = 0; q0 < 32; q0 += B200M_RECUR_GB) {
-            double v[B200M_RECUR_GB];
-#pragma unroll
-            for (int j = 0; j < B200M_RECUR_GB; ++j) {
-                const ulonglong2 cp2 = *reinterpret_cast<const ulonglong2 *>(&W.base_curve[(q0 + j) & ~1]);   // one load serves two rows
-                const double *curve = reinterpret_cast<const double *>((j & 1) ? cp2.y : cp2.x);
-                const unsigned r = W.rms[q0 + j][lane];
-                v[j] = (curve != nullptr && r != 0u) ? __ldg(curve + r) : 0.0;
-            }
-#pragma unroll
-            for (int j = 0; j < B200M_RECUR_GB; ++j) W.m[q0 + j][lane] = v[j];
-        }
-        }
-        __syncwarp();
-        RT_MARK(1);
-        // ---- the RMS rows of the next block start moving now -----------------------------------
-        const bool any_main = __any_sync(FULL, is_main);
-        const int nb = on ? skip_held(cb + 1) : cb;
-        work = issue_rms(nb, on);
-        RT_MARK(2);
-        // ---- phase C: 32 dependent steps, one lane per tile --------------------------------------
-        if (!any_work) {            // warp-uniform: nothing moves in this block
-            if (on) {
-#pragma unroll 8
-                for (int k = 0; k < 32; ++k) W.m[lane][k] = a;
-            }
-        } else if (all_exact) {     // warp-uniform: every band of this warp passed the plan-time division check
-            if (on) {
-#pragma unroll 8
-                for (int k = 0; k < 32; ++k) {
-                    const double M = W.m[lane][k];
-                    const double inc = div_const(M, A, rA, true), dec = div_const(M, R, rR, true);
-                    a = recur_step_pos(a, M, inc, dec);
-                    W.m[lane][k] = a;
-                }
-            }
-        } else if (on) {
-#pragma unroll 1
-            for (int k = 0; k < 32; ++k) {
-                const double M = W.m[lane][k];
-                const double inc = div_const(M, A, rA, exact), dec = div_const(M, R, rR, exact);
-                a = recur_step(a, M, inc, dec);
-                W.m[lane][k] = a;
-            }
-        }
-        RT_MARK(3);
-        // ---- phase D: coalesced row stores of the attenuation (main part of the tile only) -------
-        if (any_main) {
-            __syncwarp();
-#pragma unroll 8
-            for (int q = 0; q < 32; ++q) {
-                const ulonglong2 d = W.row[q];
-                if (lane < (int)d.y) reinterpret_cast<double *>(d.x)[lane] = W.m[q][lane];
-            }
-        }
-        if (P.mode == 1 && on && __double_as_longlong(a) == __double_as_longlong(old_last)) merged = true;
-        cb = nb;
-        __syncwarp();
-        RT_MARK(4);
-    }
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
-#ifdef B200M_RECUR_TIMING
-    if (lane == 0 && P.mode == 0) {
-        for (int k = 0; k < 5; ++k) atomicAdd(&counters[8 + k], (unsigned long long)rt_acc[k]);
-        atomicAdd(&counters[13], (unsigned long long)(clock64() - rt_begin));
-        atomicAdd(&counters[14], (unsigned long long)rt_blocks);
-        atomicAdd(&counters[15], 1ull);
-    }
-#endif
-    if (live) {
-        const size_t slot = (size_t)chain * P.tiles + tile;
-        if (P.mode == 0) {
-            ss_out[slot] = a_start;
-            se_out[slot] = a;
-        } else {
-            ss_out[slot] = a_in;
-            se_out[slot] = merged ? se_in[slot] : a;
-        }
-    }
-}
-
-// counters[0] = tiles repaired sequentially, counters[1] = frames re-run sequentially,
-// counters[2] = tiles repaired in the parallel rounds
-__global__ void __launch_bounds__(128)
-k_recur_fix(const StreamDesc *__restrict__ streams, const PlanDev *__restrict__ plans, RecurParams P,
-            BandPtrs bp, const double *__restrict__ spec_start, const double *__restrict__ spec_end,
-            unsigned long long *__restrict__ counters)
-{
-    // one warp per chain: all lanes check the tile joints in parallel (assumed start == predecessor's
-    // end, bit for bit); only a chain with a broken joint is walked, by lane 0, in order
-    const int chain = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-    if (chain >= P.n_streams * P.nbands) return;
-    const int s = chain / P.nbands, band = P.band_base + chain % P.nbands;
-    const StreamDesc sd = streams[s];
-    const PlanDev *__restrict__ pl = plans + sd.plan;
-    if (!pl->multiband || sd.out_frames <= 0) return;
-    const int ntiles = (sd.out_frames + P.tile_len - 1) / P.tile_len;
-    const double *ss = spec_start + (size_t)chain * P.tiles, *se = spec_end + (size_t)chain * P.tiles;
-    bool broken = false;
-    for (int t = 1 + lane; t < ntiles; t += 32)
-        broken |= __double_as_longlong(ss[t]) != __double_as_longlong(se[t - 1]);
-    if (!__any_sync(FULL, broken) || lane != 0) return;
-    const uint16_t *__restrict__ rms = bp.rms[band] + sd.out_off;
-    double *__restrict__ out = bp.att[band] + sd.out_off;
-    const double *__restrict__ curve = pl->curve[band];
-    const BandDev &bd = pl->band[band];
-    const double A = bd.attack_frames, R = bd.release_frames, rA = bd.r_attack, rR = bd.r_release;
-    const bool exact = bd.div_trick != 0;
-    double truth = se[0];                        // tile 0 starts from att = 0 exactly
-    for (int t = 1; t < ntiles; ++t) {
-        if (__double_as_longlong(ss[t]) == __double_as_longlong(truth)) { truth = se[t]; continue; }
-        atomicAdd(&counters[0], 1ull);
-        const int i0 = t * P.tile_len, i1 = min(i0 + P.tile_len, sd.out_frames);
-        double a = truth;
-        bool merged = false;
-        int i = i0;
-        for (; i < i1; ++i) {
-            const unsigned r = rms[i];
-            const double M = r ? curve[r] : 0.0;
-            a = recur_step(a, M, div_const(M, A, rA, exact), div_const(M, R, rR, exact));
-            if (__double_as_longlong(a) == __double_as_longlong(out[i])) { merged = true; break; }
-            out[i] = a;
-        }
-        atomicAdd(&counters[1], (unsigned long long)(i - i0));
-        truth = merged ? se[t] : a;
-    }
-}
-
-// =====================================================================================
-// k_apply: gain = 10^(-att/20) per frame and band, audioop.mul (floor of the clamped
-// product), then low.overlay(mid).overlay(high) = two saturating int16 adds (ENG:210).
-// Two frames per thread (16-byte attenuation loads, 8-byte sample loads): six independent
-// exp10 chains in flight.  grid = (tiles of 512 frames, streams).  NB == 1 backs the
-// single-band helper entry point (band `band_base`); NB == 3 is the crossover (bands 0..2).
-// =====================================================================================
 // 10^x for the gain of an attenuation: x = -att / 20 <= 0 and far from underflow (att is at most
 // slope * 20 log10(32768 / thresh_rms) dB; the caller falls back to the library routine beyond
 // 10^-300).  x log2(10) is split as n + f with the 1.5 * 2^52 trick, r = x - n log10(2) (two-piece
@@ -1255,9 +973,12 @@ __constant__ double c_exp10[18] = {
     0x1.9dc1da994fd21p-59,      // [16] -log10(2), low part
     6755399441055744.0};        // [17] 1.5 * 2^52
 __device__ __noinline__ double exp10_far(double x) { return exp10(x); }
+// FAR = false: the caller knows x > -300 (BandDev::att_bounded) -- no branch, so that several gains of one thread
+// form independent chains the scheduler can interleave.
+template <bool FAR>
 __device__ __forceinline__ double exp10_gain(double x)
 {
-    if (!(x > -300.0)) return exp10_far(x);
+    if (FAR && !(x > -300.0)) return exp10_far(x);
     const double t = fma(x, c_exp10[14], c_exp10[17]);
     const double nf = __dsub_rn(t, c_exp10[17]);
     double r = fma(nf, c_exp10[15], x);
@@ -1268,80 +989,524 @@ __device__ __forceinline__ double exp10_gain(double x)
     return __hiloint2double(__double2hiint(p) + (__double2loint(t) << 20), __double2loint(p));
 }
 
+// pydub: frame * db_to_float(-attenuation), db_to_float(db) = 10 ** (db / 20).  The quotient att / 20 is
+// rounded like CPython's true division (one Markstein correction of att * fl(1/20): exact for every att,
+// checked over 4e8 values on the host), so the exponent handed to 10^x is pydub's, bit for bit.  pydub
+// multiplies only `if attenuation != 0.0`; 10^-0 is exactly 1.0 here (the polynomial at r = 0 is its
+// constant term) and floor(v * 1.0) == v, so the test needs no branch.
+template <bool FAR>
+__device__ __forceinline__ double gain_of_att(double a)
+{
+    const double q = __dmul_rn(a, 0.05);
+    const double r = fma(-q, 20.0, a);
+    return exp10_gain<FAR>(-fma(r, 0.05, q));
+}
+
+// one frame (packed: CH == 2: L | R << 16, CH == 1: the low 16 bits) through audioop.mul
 template <int CH>
-__device__ __forceinline__ void apply_frame(int &acc0, int &acc1, unsigned smp, double a, bool first)
+__device__ __forceinline__ unsigned mul_frame(unsigned smp, double g)
 {
-    int v0 = (int)(short)(smp & 0xffffu), v1 = CH == 2 ? (int)smp >> 16 : 0;
-    // pydub multiplies only `if attenuation != 0.0`; exp10_gain(0) is exactly 1.0 (the polynomial at
-    // r = 0 is its constant term) and floor(v * 1.0) == v, so the test needs no branch
-    const double g = exp10_gain(a * -0.05);         // db_to_float(-att) = 10 ** (-att / 20)
-    v0 = mul_floor16_le1(v0, g);
-    if (CH == 2) v1 = mul_floor16_le1(v1, g);
-    acc0 = first ? v0 : max(-32768, min(32767, acc0 + v0));
-    if (CH == 2) acc1 = first ? v1 : max(-32768, min(32767, acc1 + v1));
+    const int v0 = mul_floor16_le1((int)(short)(smp & 0xffffu), g);
+    if (CH == 2) {
+        const int v1 = mul_floor16_le1((int)smp >> 16, g);
+        return __byte_perm((unsigned)v0, (unsigned)v1, 0x5410);
+    }
+    return (unsigned)v0 & 0xffffu;
 }
 
+// audioop.add on a packed frame: per-sample saturating int16 add (pydub overlay, ENG:210)
+template <int CH>
+__device__ __forceinline__ unsigned add_frame_sat(unsigned x, unsigned y)
+{
+    const int s0 = max(-32768, min(32767, (int)(short)(x & 0xffffu) + (int)(short)(y & 0xffffu)));
+    if (CH == 2) {
+        const int s1 = max(-32768, min(32767, ((int)x >> 16) + ((int)y >> 16)));
+        return __byte_perm((unsigned)s0, (unsigned)s1, 0x5410);
+    }
+    return (unsigned)s0 & 0xffffu;
+}
+
+template <int CH>
+__device__ __forceinline__ unsigned load_frame(const int16_t *__restrict__ p, int64_t f)
+{
+    if (CH == 2) return __ldg(reinterpret_cast<const unsigned *>(p) + f);
+    return (unsigned)(unsigned short)__ldg(p + f);
+}
+
+template <int CH>
+__device__ __forceinline__ void store_frame(int16_t *__restrict__ p, int64_t f, unsigned v)
+{
+    if (CH == 2) reinterpret_cast<unsigned *>(p)[f] = v;
+    else p[f] = (int16_t)v;
+}
+
+// NB = 3: the crossover's bands 0..2, one WARP of the CTA per band (band_base == 0); NB = 1: the single-band helper
+// entry point (band `band_base`), one warp per CTA.  Lane l of every warp of CTA c works on (stream, tile) number 32 c + l.
 template <int CH, int NB>
-__global__ void __launch_bounds__(256)
-k_apply(const StreamDesc *__restrict__ streams, const PlanDev *__restrict__ plans, BandPtrs bp,
-        int band_base, int16_t *__restrict__ proc)
+__global__ void __launch_bounds__(32 * NB)
+k_comp(const StreamDesc *__restrict__ streams, const PlanDev *__restrict__ plans, RecurParams P, BandPtrs bp,
+       int16_t *__restrict__ proc, const double *__restrict__ ss_in, const double *__restrict__ se_in,
+       double *__restrict__ ss_out, double *__restrict__ se_out, unsigned long long *__restrict__ counters)
 {
-    const StreamDesc sd = streams[blockIdx.y];
-    if (!plans[sd.plan].multiband) return;
-    const int f = (blockIdx.x * 256 + threadIdx.x) * 2;
-    if (f >= sd.out_frames) return;
-    const int64_t gi = sd.out_off + f;
-    const bool two = f + 1 < sd.out_frames && (gi & 1) == 0;     // aligned pair
-    int a0 = 0, a1 = 0, b0 = 0, b1 = 0;                          // frame f (L, R), frame f + 1 (L, R)
-    const double *attp[NB];
-    const int16_t *smpp[NB];
-#pragma unroll
-    for (int b = 0; b < NB; ++b) {                               // NB == 3: all bands, band_base == 0 (constant indices: no local copy of bp)
-        attp[b] = NB == 3 ? bp.att[b] : bp.att[band_base];
-        smpp[b] = NB == 3 ? bp.band[b] : bp.band[band_base];
+    extern __shared__ __align__(16) unsigned char recur_smem[];
+    const int wid = NB == 1 ? 0 : (int)(threadIdx.x >> 5), lane = threadIdx.x & 31;
+    RecurWarpSmem *WS = reinterpret_cast<RecurWarpSmem *>(recur_smem);
+    RecurWarpSmem &W = WS[wid];
+    unsigned char (*s_same)[32] = reinterpret_cast<unsigned char (*)[32]>(recur_smem + NB * sizeof(RecurWarpSmem));   // [NB][32]
+    const int band = NB == 3 ? wid : P.band_base;
+    const int gl = blockIdx.x * 32 + lane;
+    const int s = gl / P.tiles, tile = gl % P.tiles;
+    bool live = s < P.n_streams;
+    int start = 0, end = 0;
+    int64_t out_off = 0;
+    const PlanDev *__restrict__ pl = plans;
+    const uint32_t *hold_b = nullptr;
+    const uint16_t *rms_b = nullptr;
+    double *bend_b = nullptr;
+    double a = 0.0;
+    W.base_curve[lane] = 0ull;
+    bool okfast = true;
+    if (live) {
+        const StreamDesc sd = streams[s];
+        pl = plans + sd.plan;
+        start = tile * P.tile_len;
+        live = pl->multiband && start < sd.out_frames;
+        if (live) {
+            end = min(start + P.tile_len, sd.out_frames);
+            out_off = sd.out_off;
+            hold_b = bp.hold[band] + sd.blk_off;
+            rms_b = bp.rms[band] + sd.out_off;
+            bend_b = bp.bend[band] + (size_t)sd.blk_off * 32;
+            W.base_curve[lane] = (unsigned long long)pl->curve[band];
+            okfast = pl->band[band].div_trick != 0 && pl->band[band].att_bounded != 0;
+        }
     }
-    if (two) {
-        // every load of the thread is issued before the first gain is computed: the kernel runs at
-        // the speed its 40 bytes per frame arrive
-        double2 at[NB];
-        unsigned s0[NB], s1[NB];
+    const size_t slot0 = ((size_t)s * NB) * P.tiles + tile;            // band b: slot0 + b * P.tiles
+    const size_t slot = slot0 + (size_t)(NB == 3 ? wid : 0) * P.tiles;
+    double a_in = 0.0;
+    if (P.mode == 1 && live) {
+        // repair round: is ANY band's assumed start state not its predecessor's current end state?  (Every warp of
+        // the CTA looks at all bands and so reaches the same verdict.)
+        bool dirty = false;
 #pragma unroll
         for (int b = 0; b < NB; ++b) {
-            at[b] = *reinterpret_cast<const double2 *>(attp[b] + gi);
-            if (CH == 2) {
-                const uint2 q = *reinterpret_cast<const uint2 *>(smpp[b] + gi * 2);
-                s0[b] = q.x; s1[b] = q.y;
-            } else {
-                const unsigned q = *reinterpret_cast<const unsigned *>(smpp[b] + gi);
-                s0[b] = q & 0xffffu; s1[b] = q >> 16;
+            const size_t sl = slot0 + (size_t)b * P.tiles;
+            const double prev = tile == 0 ? 0.0 : se_in[sl - 1];
+            dirty = dirty || (tile != 0 && __double_as_longlong(ss_in[sl]) != __double_as_longlong(prev));
+        }
+        if (!dirty) {
+            ss_out[slot] = ss_in[slot]; se_out[slot] = se_in[slot];     // consistent: nothing to do
+            live = false;
+        } else {
+            a = tile == 0 ? 0.0 : se_in[slot - 1];    // a band that was consistent reproduces its stored trajectory
+            if (wid == 0) atomicAdd(&counters[2], 1ull);
+        }
+        a_in = a;
+    }
+    // warp-uniform: this band passed the plan-time checks in every plan of the warp (exact constant division, curve
+    // finite and >= +0, attenuation bounded): the branch-free step and gain
+    const bool fast = __all_sync(FULL, okfast || !live);
+    const int sb = start >> 5, eb = (end + 31) >> 5;
+    const BandDev &bd = pl->band[band];
+    const double A = bd.attack_frames, R = bd.release_frames, rA = bd.r_attack, rR = bd.r_release;
+    const bool ex = bd.div_trick != 0;
+    __syncwarp();
+
+    // the hold word of blocks 32w .. 32w+31, kept while the cursor stays inside it
+    int hw_idx = -1;
+    unsigned hw_val = 0u;
+    auto hold_word = [&](int w) { if (w != hw_idx) { hw_idx = w; hw_val = hold_b[w]; } return hw_val; };
+
+    // The RMS rows of every lane's block `cbn` -> W.rms: 64 bytes per row, moved as 16-byte cp.async
+    // pieces, eight rows per instruction (lane l: row q0 + l / 4, piece l % 4, so every 32-byte sector is
+    // asked for once and the shared-memory side is one contiguous 512-byte span).  The source address
+    // of a row travels by shuffle from the lane that owns it.  Rows of held blocks, of lanes without
+    // work and the ragged last block of a stream are written by their owner: zeros (r = 0 gives
+    // M = 0, a hold, i.e. an identity step, so partial rows need no branches later) plus whatever
+    // valid elements there are.  Returns whether this lane's block can change its state.
+    auto issue_rms = [&](int cbn, bool valid) -> bool {
+        const bool on_n = valid && cbn < eb;
+        const int i0n = cbn << 5;
+        const int cntn = on_n ? min(32, end - i0n) : 0;
+        const bool heldn = on_n && ((hold_word(cbn >> 5) >> (cbn & 31)) & 1u);
+        const bool work_n = on_n && !heldn;
+        const bool rms16 = (reinterpret_cast<unsigned long long>(rms_b) & 15ull) == 0;    // chunk starts at odd rates may not be
+        const uint16_t *srcp = (work_n && cntn == 32 && rms16) ? rms_b + i0n : nullptr;
+        if (srcp == nullptr) {
+            uint16_t *row = &W.rms[lane][0];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) reinterpret_cast<uint4 *>(row)[j] = make_uint4(0u, 0u, 0u, 0u);
+            if (work_n) {
+#pragma unroll 1
+                for (int k = 0; k < cntn; ++k) row[k] = rms_b[i0n + k];
             }
         }
+        const int sub = lane >> 2, piece = lane & 3;
 #pragma unroll
-        for (int b = 0; b < NB; ++b) {
-            apply_frame<CH>(a0, a1, s0[b], at[b].x, b == 0);
-            apply_frame<CH>(b0, b1, s1[b], at[b].y, b == 0);
-        }
-        if (CH == 2)
-            *reinterpret_cast<uint2 *>(proc + gi * 2) = make_uint2((unsigned)(a0 & 0xffff) | ((unsigned)a1 << 16),
-                                                                   (unsigned)(b0 & 0xffff) | ((unsigned)b1 << 16));
-        else
-            *reinterpret_cast<unsigned *>(proc + gi) = (unsigned)(a0 & 0xffff) | ((unsigned)b0 << 16);
-    } else {
-        for (int k = 0; k < 2 && f + k < sd.out_frames; ++k) {
-#pragma unroll
-            for (int b = 0; b < NB; ++b) {
-                const double at = attp[b][gi + k];
-                unsigned s0;
-                if (CH == 2) s0 = *reinterpret_cast<const unsigned *>(smpp[b] + (gi + k) * 2);
-                else s0 = (unsigned)(unsigned short)smpp[b][gi + k];
-                apply_frame<CH>(a0, a1, s0, at, b == 0);
+        for (int q0 = 0; q0 < 32; q0 += 8) {
+            const unsigned long long p = __shfl_sync(FULL, (unsigned long long)srcp, q0 + sub);
+            if (p != 0ull) {
+                const unsigned sa = (unsigned)__cvta_generic_to_shared(&W.rms[q0 + sub][piece * 8]);
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(p + 16ull * piece) : "memory");
             }
-            if (CH == 2) *reinterpret_cast<unsigned *>(proc + (gi + k) * 2) = (unsigned)(a0 & 0xffff) | ((unsigned)a1 << 16);
-            else proc[gi + k] = (int16_t)a0;
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        return work_n;
+    };
+    // The band samples of every lane's block `cbn` -> W.smp (main part of the tile only), the same way: 64 * CH
+    // bytes per row as 16-byte cp.async pieces; unaligned or ragged rows are copied by their owner (whole row
+    // zeroed first).  A warp's time is the length of its serial path (all lanes of the grid are resident at once),
+    // so the samples land in shared memory one block ahead and nothing below waits for DRAM.
+    const int16_t *__restrict__ band_smp = bp.band[band];
+    auto issue_smp = [&](int cbn, bool valid) {
+        constexpr int PIECES = 4 * CH;                 // 16-byte pieces per row
+        const bool on_n = valid && cbn < eb;
+        const int i0n = cbn << 5;
+        const int cntn = on_n ? min(32, end - i0n) : 0;
+        const int16_t *base = band_smp + (out_off + i0n) * CH;
+        const bool al = (reinterpret_cast<unsigned long long>(base) & 15ull) == 0;
+        const int16_t *srcp = (on_n && cntn == 32 && al) ? base : nullptr;
+        if (srcp == nullptr && on_n) {
+#pragma unroll
+            for (int j = 0; j < PIECES; ++j) reinterpret_cast<uint4 *>(W.smp[lane])[j] = make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll 1
+            for (int k = 0; k < cntn; ++k) {
+                if (CH == 2) W.smp[lane][k] = reinterpret_cast<const unsigned *>(base)[k];
+                else reinterpret_cast<uint16_t *>(W.smp[lane])[k] = (uint16_t)base[k];
+            }
+        }
+        const int sub = lane / PIECES, piece = lane % PIECES;
+#pragma unroll
+        for (int q0 = 0; q0 < 32; q0 += 32 / PIECES) {
+            const unsigned long long p = __shfl_sync(FULL, (unsigned long long)srcp, q0 + sub);
+            if (p != 0ull) {
+                const unsigned sa = (unsigned)__cvta_generic_to_shared(&W.smp[q0 + sub][piece * 4]);
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(p + 16ull * piece) : "memory");
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    // phase B: RMS rows -> M rows through the static curve (row-wise: consecutive frames have neighbouring
+    // RMS values, so a row's gathers touch a few cache lines); B200M_RECUR_GB rows of gathers in flight together
+    auto phase_b = [&]() {
+#pragma unroll
+        for (int q0 = 0; q0 < 32; q0 += B200M_RECUR_GB) {
+            double v[B200M_RECUR_GB];
+#pragma unroll
+            for (int j = 0; j < B200M_RECUR_GB; ++j) {
+                const ulonglong2 cp2 = *reinterpret_cast<const ulonglong2 *>(&W.base_curve[(q0 + j) & ~1]);   // one load serves two rows
+                const double *curve = reinterpret_cast<const double *>((j & 1) ? cp2.y : cp2.x);
+                const unsigned r = W.rms[q0 + j][lane];
+                v[j] = (curve != nullptr && r != 0u) ? __ldg(curve + r) : 0.0;
+            }
+#pragma unroll
+            for (int j = 0; j < B200M_RECUR_GB; ++j) W.m[q0 + j][lane] = v[j];
+        }
+    };
+
+    // ---- mode 0: warm up over the preceding frames until `warm` ACTIVE frames have been seen -------------------
+    // Walk the hold words (32 blocks = 1024 frames each) backwards; a held stretch carries the state
+    // unchanged, so it neither helps nor costs anything.  Every lane then walks its own cursor over the
+    // blocks [wstart, sb), skipping held blocks outright, so the warp iterates max-over-lanes of the
+    // blocks that need work, not the span.  Only the recurrence runs here: no gains, no samples, no stores.
+    if (P.mode == 0) {
+        int cb = sb;
+        if (live) {
+            int need = P.warm >> 5, wb = sb;
+            while (wb > 0 && need > 0) {
+                const int w = (wb - 1) >> 5, lo = w << 5, nbits = wb - lo;
+                const unsigned mask = nbits == 32 ? 0xffffffffu : ((1u << nbits) - 1u);
+                need -= nbits - __popc(hold_b[w] & mask);
+                wb = lo;
+            }
+            cb = wb;
+        }
+        auto skip_held = [&](int c0) {           // first block >= c0 that needs work, or sb
+            if (live) {
+                while (c0 < sb) {
+                    const unsigned wv = hold_word(c0 >> 5) >> (c0 & 31);
+                    if (!(wv & 1u)) break;
+                    const int run = (~wv) ? __ffs(~wv) - 1 : 32;     // run of held blocks (shifted-in zeros end it)
+                    c0 = min(c0 + run, sb);
+                }
+            }
+            return c0;
+        };
+        cb = skip_held(cb);
+        issue_rms(cb, live && cb < sb);
+        for (;;) {
+            const bool on = live && cb < sb;
+            if (!__any_sync(FULL, on)) break;
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+            __syncwarp();
+            phase_b();                                            // skip_held left only blocks with work
+            __syncwarp();
+            const int nb = on ? skip_held(cb + 1) : cb;
+            issue_rms(nb, on && nb < sb);
+            if (on) {
+                const double2 *mrow = reinterpret_cast<const double2 *>(W.m[lane]);
+                if (fast) {
+#pragma unroll 4
+                    for (int k2 = 0; k2 < 16; ++k2) {
+                        const double2 M = mrow[k2];
+                        a = recur_step_pos(a, M.x, div_const(M.x, A, rA, true), div_const(M.x, R, rR, true));
+                        a = recur_step_pos(a, M.y, div_const(M.y, A, rA, true), div_const(M.y, R, rR, true));
+                    }
+                } else {
+#pragma unroll 1
+                    for (int k2 = 0; k2 < 16; ++k2) {
+                        const double2 M = mrow[k2];
+                        a = recur_step(a, M.x, div_const(M.x, A, rA, ex), div_const(M.x, R, rR, ex));
+                        a = recur_step(a, M.y, div_const(M.y, A, rA, ex), div_const(M.y, R, rR, ex));
+                    }
+                }
+            }
+            cb = nb;
+            __syncwarp();
+        }
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncwarp();
+    }
+    const double a_start = a;
+
+    // ---- the tile itself: the CTA's bands in lockstep over its 32-frame blocks ---------------------------------
+    // Per block: phase B (row-wise: one lane per frame) turns the RMS rows into M rows; then every lane walks ITS
+    // OWN row: 32 recurrence steps, and right behind each step -- off the dependent chain, so the 10^x polynomials
+    // of neighbouring frames interleave freely -- the gain and audioop.mul on the frame's samples; the compressed
+    // frames go back into the bytes of the lane's M row that the walk has already consumed (16 bytes per four
+    // frames against 32 bytes of M).  Then (CTA barrier) the bands' compressed rows are overlaid row-wise, one
+    // lane per frame, every warp of the CTA taking a third of the rows: two saturating adds in band order
+    // (ENG:210) and a coalesced 128-byte store of `proc`; a second barrier frees the rows for the next block.
+    int cb = sb;
+    bool merged = false;
+    bool work = issue_rms(cb, live);
+    issue_smp(cb, live);
+    double *__restrict__ att_dbg = bp.att[band];
+    for (;;) {
+        const bool on = live && !merged && cb < eb;
+        if (!__any_sync(FULL, on)) break;
+        const int i0 = cb << 5;
+        const int cnt = on ? min(32, end - i0) : 0;
+        const double old_end = (P.mode == 1 && on) ? bend_b[cb] : 0.0;     // what this tile stored earlier at the end of this block
+        W.row[lane] = make_ulonglong2((unsigned long long)(out_off + i0), (unsigned long long)cnt);
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncwarp();
+        const bool any_work = __any_sync(FULL, on && work);       // else every lane's block is held: att stays put
+        // nothing moves and nothing is attenuated: the band passes through (a band that stays under its threshold)
+        const bool quiet = !__any_sync(FULL, on && (work || __double_as_longlong(a) != 0ll));
+        if (any_work) phase_b();
+        __syncwarp();
+        work = issue_rms(cb + 1, on);                               // the RMS rows of the next block start moving now
+        {
+            uint4 *crow = reinterpret_cast<uint4 *>(W.m[lane]);      // compressed frames: word w overwrites M[2w], M[2w+1] (consumed)
+            const double2 *mrow = reinterpret_cast<const double2 *>(W.m[lane]);
+            const uint4 *srow = reinterpret_cast<const uint4 *>(W.smp[lane]);
+            constexpr int NW = 8 * CH / 2;                          // 128-bit words per row: 8 stereo (4 frames each), 4 mono (8 frames each)
+            if (on) {
+                if (quiet) {
+#pragma unroll
+                    for (int w = 0; w < NW; ++w) crow[w] = srow[w];
+                } else {
+                    if (!any_work) {
+#pragma unroll
+                        for (int k2 = 0; k2 < 16; ++k2) reinterpret_cast<double2 *>(W.m[lane])[k2] = make_double2(0.0, 0.0);   // held throughout: identity steps
+                    }
+                    const int64_t fdbg = out_off + i0;
+                    if (fast) {
+#pragma unroll 2
+                        for (int w = 0; w < NW; ++w) {
+                            const uint4 sw = srow[w];
+                            const unsigned sv[4] = {sw.x, sw.y, sw.z, sw.w};
+                            unsigned v[4];
+                            if (CH == 2) {
+                                const double2 Ma = mrow[2 * w], Mb = mrow[2 * w + 1];
+                                const double Mv[4] = {Ma.x, Ma.y, Mb.x, Mb.y};
+#pragma unroll
+                                for (int i = 0; i < 4; ++i) {
+                                    a = recur_step_pos(a, Mv[i], div_const(Mv[i], A, rA, true), div_const(Mv[i], R, rR, true));
+                                    if (att_dbg != nullptr && 4 * w + i < cnt) att_dbg[fdbg + 4 * w + i] = a;
+                                    v[i] = mul_frame<2>(sv[i], gain_of_att<false>(a));
+                                }
+                            } else {                                 // mono: two frames per 32-bit word
+#pragma unroll
+                                for (int i = 0; i < 4; ++i) {
+                                    const double2 M = mrow[4 * w + i];
+                                    a = recur_step_pos(a, M.x, div_const(M.x, A, rA, true), div_const(M.x, R, rR, true));
+                                    if (att_dbg != nullptr && 8 * w + 2 * i < cnt) att_dbg[fdbg + 8 * w + 2 * i] = a;
+                                    const unsigned lo = mul_frame<1>(sv[i] & 0xffffu, gain_of_att<false>(a));
+                                    a = recur_step_pos(a, M.y, div_const(M.y, A, rA, true), div_const(M.y, R, rR, true));
+                                    if (att_dbg != nullptr && 8 * w + 2 * i + 1 < cnt) att_dbg[fdbg + 8 * w + 2 * i + 1] = a;
+                                    const unsigned hi = mul_frame<1>(sv[i] >> 16, gain_of_att<false>(a));
+                                    v[i] = lo | (hi << 16);
+                                }
+                            }
+                            crow[w] = make_uint4(v[0], v[1], v[2], v[3]);
+                        }
+                    } else {
+#pragma unroll 1
+                        for (int w = 0; w < NW; ++w) {
+                            const uint4 sw = srow[w];
+                            const unsigned sv[4] = {sw.x, sw.y, sw.z, sw.w};
+                            unsigned v[4];
+                            if (CH == 2) {
+                                const double2 Ma = mrow[2 * w], Mb = mrow[2 * w + 1];
+                                const double Mv[4] = {Ma.x, Ma.y, Mb.x, Mb.y};
+#pragma unroll 1
+                                for (int i = 0; i < 4; ++i) {
+                                    a = recur_step(a, Mv[i], div_const(Mv[i], A, rA, ex), div_const(Mv[i], R, rR, ex));
+                                    if (att_dbg != nullptr && 4 * w + i < cnt) att_dbg[fdbg + 4 * w + i] = a;
+                                    v[i] = mul_frame<2>(sv[i], gain_of_att<true>(a));
+                                }
+                            } else {
+#pragma unroll 1
+                                for (int i = 0; i < 4; ++i) {
+                                    const double2 M = mrow[4 * w + i];
+                                    a = recur_step(a, M.x, div_const(M.x, A, rA, ex), div_const(M.x, R, rR, ex));
+                                    if (att_dbg != nullptr && 8 * w + 2 * i < cnt) att_dbg[fdbg + 8 * w + 2 * i] = a;
+                                    const unsigned lo = mul_frame<1>(sv[i] & 0xffffu, gain_of_att<true>(a));
+                                    a = recur_step(a, M.y, div_const(M.y, A, rA, ex), div_const(M.y, R, rR, ex));
+                                    if (att_dbg != nullptr && 8 * w + 2 * i + 1 < cnt) att_dbg[fdbg + 8 * w + 2 * i + 1] = a;
+                                    const unsigned hi = mul_frame<1>(sv[i] >> 16, gain_of_att<true>(a));
+                                    v[i] = lo | (hi << 16);
+                                }
+                            }
+                            crow[w] = make_uint4(v[0], v[1], v[2], v[3]);
+                        }
+                    }
+                }
+                if (quiet && att_dbg != nullptr)
+                    for (int k = 0; k < cnt; ++k) att_dbg[out_off + i0 + k] = a;
+                s_same[wid][lane] = (unsigned char)(__double_as_longlong(a) == __double_as_longlong(old_end));
+                bend_b[cb] = a;
+            }
+        }
+        __syncwarp();
+        issue_smp(cb + 1, on);                                      // the samples of the next block (W.smp is consumed)
+        if (NB > 1) __syncthreads();                                // every band's compressed rows are in place
+        // ---- overlay + store, row-wise: one lane per frame, rows dealt round-robin to the CTA's warps ------------
+#pragma unroll 2
+        for (int q = wid; q < 32; q += NB) {
+            const ulonglong2 d = W.row[q];
+            if (lane < (int)d.y) {
+                const int64_t f = (int64_t)d.x + lane;
+                if (CH == 2) {
+                    unsigned v = reinterpret_cast<const unsigned *>(WS[0].m[q])[lane];
+#pragma unroll
+                    for (int b = 1; b < NB; ++b) v = add_frame_sat<2>(v, reinterpret_cast<const unsigned *>(WS[b].m[q])[lane]);
+                    reinterpret_cast<unsigned *>(proc)[f] = v;
+                } else {
+                    unsigned v = reinterpret_cast<const uint16_t *>(WS[0].m[q])[lane];
+#pragma unroll
+                    for (int b = 1; b < NB; ++b) v = add_frame_sat<1>(v, reinterpret_cast<const uint16_t *>(WS[b].m[q])[lane]);
+                    proc[f] = (int16_t)v;
+                }
+            }
+        }
+        if (P.mode == 1 && on) {
+            bool same = true;
+#pragma unroll
+            for (int b = 0; b < NB; ++b) same = same && s_same[b][lane] != 0;
+            if (same) merged = true;
+        }
+        ++cb;
+        if (NB > 1) __syncthreads();                                // rows and flags consumed: the next block may overwrite them
+        else __syncwarp();
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    if (live) {
+        if (P.mode == 0) {
+            ss_out[slot] = a_start;
+            se_out[slot] = a;
+        } else {
+            ss_out[slot] = a_in;
+            se_out[slot] = merged ? se_in[slot] : a;
         }
     }
 }
 
+// counters[0] = tiles repaired sequentially, counters[1] = frames re-run sequentially,
+// counters[2] = tiles repaired in the parallel rounds
+// One warp per stream: all lanes check the tile joints of every band in parallel (assumed start ==
+// predecessor's end, bit for bit); only a stream with a broken joint is walked, tile by tile in order:
+// lane b carries band b's true state, a broken tile is re-run block by block (lanes 0 .. NB-1 step
+// their band through the block, then all 32 lanes apply the gains, one frame each) until every band
+// meets its stored block-end state.
+template <int CH, int NB>
+__global__ void __launch_bounds__(128)
+k_comp_fix(const StreamDesc *__restrict__ streams, const PlanDev *__restrict__ plans, RecurParams P, BandPtrs bp,
+           int16_t *__restrict__ proc, const double *__restrict__ spec_start, const double *__restrict__ spec_end,
+           unsigned long long *__restrict__ counters)
+{
+    __shared__ double s_att[4][NB][32];
+    const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int s = blockIdx.x * 4 + wid;
+    if (s >= P.n_streams) return;
+    const StreamDesc sd = streams[s];
+    const PlanDev *__restrict__ pl = plans + sd.plan;
+    if (!pl->multiband || sd.out_frames <= 0) return;
+    const int ntiles = (sd.out_frames + P.tile_len - 1) / P.tile_len;
+    bool broken = false;
+#pragma unroll
+    for (int b = 0; b < NB; ++b) {
+        const double *ss = spec_start + ((size_t)s * NB + b) * P.tiles, *se = spec_end + ((size_t)s * NB + b) * P.tiles;
+        for (int t = 1 + lane; t < ntiles; t += 32)
+            broken |= __double_as_longlong(ss[t]) != __double_as_longlong(se[t - 1]);
+    }
+    if (!__any_sync(FULL, broken)) return;
+    // lane b < NB: band b
+    const int myb = lane < NB ? lane : 0, band = NB == 3 ? myb : P.band_base;
+    const double *ss = spec_start + ((size_t)s * NB + myb) * P.tiles, *se = spec_end + ((size_t)s * NB + myb) * P.tiles;
+    const uint16_t *__restrict__ rms = bp.rms[band] + sd.out_off;
+    double *__restrict__ bend = bp.bend[band] + (size_t)sd.blk_off * 32;
+    const double *__restrict__ curve = pl->curve[band];
+    const BandDev bd = pl->band[band];
+    const bool exact = bd.div_trick != 0;
+    double truth = se[0];                        // tile 0 starts from att = 0 exactly
+    for (int t = 1; t < ntiles; ++t) {
+        const bool ok = lane >= NB || __double_as_longlong(ss[t]) == __double_as_longlong(truth);
+        if (__all_sync(FULL, ok)) { truth = se[t]; continue; }
+        if (lane == 0) atomicAdd(&counters[0], 1ull);
+        const int i0 = t * P.tile_len, i1 = min(i0 + P.tile_len, sd.out_frames);
+        double a = truth;
+        bool merged = false;
+        int done = 0;
+        for (int blk = i0 >> 5; (blk << 5) < i1 && !merged; ++blk) {
+            const int f0 = blk << 5, cnt = min(32, i1 - f0);
+            if (lane < NB) {
+                for (int k = 0; k < cnt; ++k) {
+                    const unsigned r = rms[f0 + k];
+                    const double M = r ? curve[r] : 0.0;
+                    a = recur_step(a, M, div_const(M, bd.attack_frames, bd.r_attack, exact), div_const(M, bd.release_frames, bd.r_release, exact));
+                    s_att[wid][myb][k] = a;
+                }
+            }
+            __syncwarp();
+            if (lane < cnt) {
+                const int64_t f = sd.out_off + f0 + lane;
+                unsigned acc = 0u;
+#pragma unroll
+                for (int b = 0; b < NB; ++b) {
+                    const double at = s_att[wid][b][lane];
+                    const int bb = NB == 3 ? b : P.band_base;
+                    const unsigned v = mul_frame<CH>(load_frame<CH>(bp.band[bb], f), gain_of_att<true>(at));
+                    if (bp.att[bb] != nullptr) bp.att[bb][f] = at;
+                    acc = b == 0 ? v : add_frame_sat<CH>(acc, v);
+                }
+                store_frame<CH>(proc, f, acc);
+            }
+            bool same = true;
+            if (lane < NB) {
+                same = __double_as_longlong(a) == __double_as_longlong(bend[blk]);
+                bend[blk] = a;
+            }
+            merged = __all_sync(FULL, same);
+            done += cnt;
+            __syncwarp();
+        }
+        if (lane == 0) atomicAdd(&counters[1], (unsigned long long)done);
+        truth = merged ? se[t] : a;
+    }
+}
 // =====================================================================================
 // k_kweight: pyloudnorm K-weighting of the (L+R)/2 mean of the processed track
 // (ENG:214-218): shelf then high-pass, float64 DF2T (scipy lfilter), each stage stored

@@ -103,7 +103,7 @@ def main():
         eng.set_profiling(True); eng.reset_profile()
         step(); eng.synchronize()
         if rank == 0:
-            for k in ["k_stage_s24", "k_chain", "k_detect", "k_recur_tiles", "k_recur_repair", "k_recur_fix", "k_apply", "k_kweight", "k_hops",
+            for k in ["k_stage_s24", "k_chain", "k_detect", "k_comp", "k_comp_repair", "k_comp_fix", "k_kweight", "k_hops",
                       "k_blocks", "k_gate", "k_final"]:
                 t, c = eng.kernel_time_ms(k)
                 print(f"{k:16s} {t:8.3f} ms ({c} launches)", file=sys.stderr)

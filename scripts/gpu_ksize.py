@@ -22,7 +22,7 @@ for nt in [1, 2, 4, 6, 8, 12, 16, 24, 32]:
     e0.record()
     for _ in range(K): step()
     eng.synchronize(); e1.record(); torch.cuda.synchronize()
-    ks = {k: eng.kernel_time_ms(k)[0] / K for k in ["k_chain", "k_detect", "k_recur_tiles", "k_apply", "k_kweight", "k_final"]}
+    ks = {k: eng.kernel_time_ms(k)[0] / K for k in ["k_chain", "k_detect", "k_comp", "k_kweight", "k_final"]}
     eng.set_profiling(False)
     ms = e0.elapsed_time(e1) / K
     print(f"tracks {nt:3d}: {ms:8.3f} ms/step = {ms / nt:6.3f} ms/track | " + " ".join(f"{k[2:]} {v:6.2f}" for k, v in ks.items()), flush=True)

@@ -28,7 +28,7 @@ t0 = time.time()
 for _ in range(K): step()
 eng.synchronize(); dt = (time.time() - t0) / K
 tot = 0
-for k in ["k_chain", "k_detect", "k_recur_tiles", "k_recur_repair", "k_recur_fix", "k_apply", "k_kweight", "k_hops", "k_blocks", "k_gate", "k_final"]:
+for k in ["k_chain", "k_detect", "k_comp", "k_comp_repair", "k_comp_fix", "k_kweight", "k_hops", "k_blocks", "k_gate", "k_final"]:
     ms, cnt = eng.kernel_time_ms(k); tot += ms / K
     print(f"{k:10s} {ms / K:9.3f} ms/step  ({cnt} launches)")
 print(f"sum {tot:.3f} ms ; wall {dt * 1e3:.3f} ms/step ; RTF {ntracks * seconds / dt:.0f} ; frames {ntracks * n} ; "

@@ -137,7 +137,7 @@ def test_compressor_trajectory_bit_exact(eng):
 
 
 def test_recurrence_tiling_is_exact_for_any_tile_length(eng):
-    """k_recur_tiles speculates every time tile from a warm-up and k_recur_fix repairs wrong guesses:
+    """k_comp speculates every time tile from a warm-up and k_comp_fix repairs wrong guesses:
     the trajectory must be bit-identical to the sequential oracle for ANY tile / warm-up length,
     including ones so short that most guesses are wrong."""
     from b200master import synth
@@ -215,6 +215,24 @@ def test_errors(eng):
     assert out[0].shape == (8820, 2)
     with pytest.raises(ZeroDivisionError):
         eng.master([synth.make_track(62, 0.5, 44100)], 44100, dict(multiband=True, low_ratio=0))
+
+
+def test_failed_plan_upload_does_not_poison_the_cache(eng):
+    """A plan set that fails validation half-way (after the host tables were rebuilt) must not leave the
+    previous set's cache key behind: the previous good plans, sent again, are rebuilt and give the same bytes."""
+    from b200master import make_plan, synth
+    rate = 44100
+    pcm = synth.make_track(65, 1.0, rate)
+    st = dict(bass_boost=3.0, treble_boost=2.0, saturation=10, width=1.2, multiband=True, lufs=-14.0)
+    good, _ = eng.master([pcm], rate, st)
+    n = pcm.shape[0]
+    bad = make_plan(st, rate, 2)
+    bad.band[2].look_frames = 1 << 20                       # rejected in the middle of the rebuild
+    out = np.empty_like(pcm)
+    with pytest.raises(ValueError):
+        eng.master_raw(np.ascontiguousarray(pcm).reshape(-1), False, [0], [n], [n], [make_plan(dict(st, width=1.0), rate, 2), bad], [0], out.reshape(-1), False)
+    again, _ = eng.master([pcm], rate, st)
+    assert np.array_equal(again[0], good[0])
 
 
 def test_device_resident_buffers(eng):
