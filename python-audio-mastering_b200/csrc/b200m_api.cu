@@ -726,10 +726,10 @@ extern "C" int b200m_create(int device, b200m_handle **out)
     if (e == cudaSuccess) e = allow_smem(k_chainw<2, false, false>, ChainW<2>::SMEM);
     if (e == cudaSuccess) e = allow_smem(k_detect<1>, detect_smem_bytes(8192));
     if (e == cudaSuccess) e = allow_smem(k_detect<2>, detect_smem_bytes(8192));
-    if (e == cudaSuccess) e = allow_smem(k_comp<1, 1>, recur_smem_bytes(1));
-    if (e == cudaSuccess) e = allow_smem(k_comp<2, 1>, recur_smem_bytes(1));
-    if (e == cudaSuccess) e = allow_smem(k_comp<1, 3>, recur_smem_bytes(3));
-    if (e == cudaSuccess) e = allow_smem(k_comp<2, 3>, recur_smem_bytes(3));
+    if (e == cudaSuccess) e = allow_smem(k_comp<1, 1, true>, recur_smem_bytes(1));
+    if (e == cudaSuccess) e = allow_smem(k_comp<2, 1, true>, recur_smem_bytes(1));
+    if (e == cudaSuccess) e = allow_smem(k_comp<1, 3, false>, recur_smem_bytes(3));
+    if (e == cudaSuccess) e = allow_smem(k_comp<2, 3, false>, recur_smem_bytes(3));
     if (e == cudaSuccess) e = allow_smem(k_kweight<1, int16_t, true>, kweight_smem_bytes());
     if (e == cudaSuccess) e = allow_smem(k_kweight<2, int16_t, true>, kweight_smem_bytes());
     if (e == cudaSuccess) e = allow_smem(k_kweight<1, float, true>, kweight_smem_bytes());
@@ -985,10 +985,10 @@ static int launch_compressor(b200m_handle *h, const Group &g, const BandPtrs &bp
     double *ss[2] = {d_spec, d_spec + 2 * slots}, *se[2] = {d_spec + slots, d_spec + 3 * slots};
     const unsigned gr = (unsigned)((lanes + 31) / 32);
 #define LAUNCH_COMP(NAME, PP, SSI, SEI, SSO, SEO) do { \
-        if (nbands == 3) { if (g.ch == 2) LAUNCH(NAME, k_comp<2, 3><<<gr, 96, recur_smem_bytes(3), h->stream>>>(g.d_streams, h->d_plans, PP, bp, d_proc, SSI, SEI, SSO, SEO, h->d_counters)); \
-                           else           LAUNCH(NAME, k_comp<1, 3><<<gr, 96, recur_smem_bytes(3), h->stream>>>(g.d_streams, h->d_plans, PP, bp, d_proc, SSI, SEI, SSO, SEO, h->d_counters)); } \
-        else             { if (g.ch == 2) LAUNCH(NAME, k_comp<2, 1><<<gr, 32, recur_smem_bytes(1), h->stream>>>(g.d_streams, h->d_plans, PP, bp, d_proc, SSI, SEI, SSO, SEO, h->d_counters)); \
-                           else           LAUNCH(NAME, k_comp<1, 1><<<gr, 32, recur_smem_bytes(1), h->stream>>>(g.d_streams, h->d_plans, PP, bp, d_proc, SSI, SEI, SSO, SEO, h->d_counters)); } } while (0)
+        if (nbands == 3) { if (g.ch == 2) LAUNCH(NAME, k_comp<2, 3, false><<<gr, 96, recur_smem_bytes(3), h->stream>>>(g.d_streams, h->d_plans, PP, bp, d_proc, SSI, SEI, SSO, SEO, h->d_counters)); \
+                           else           LAUNCH(NAME, k_comp<1, 3, false><<<gr, 96, recur_smem_bytes(3), h->stream>>>(g.d_streams, h->d_plans, PP, bp, d_proc, SSI, SEI, SSO, SEO, h->d_counters)); } \
+        else             { if (g.ch == 2) LAUNCH(NAME, k_comp<2, 1, true><<<gr, 32, recur_smem_bytes(1), h->stream>>>(g.d_streams, h->d_plans, PP, bp, d_proc, SSI, SEI, SSO, SEO, h->d_counters)); \
+                           else           LAUNCH(NAME, k_comp<1, 1, true><<<gr, 32, recur_smem_bytes(1), h->stream>>>(g.d_streams, h->d_plans, PP, bp, d_proc, SSI, SEI, SSO, SEO, h->d_counters)); } } while (0)
     LAUNCH_COMP("k_comp", P0, nullptr, nullptr, ss[0], se[0]);
     int cur = 0;
     if (P.tiles > 1) {

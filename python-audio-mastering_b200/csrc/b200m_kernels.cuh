@@ -891,6 +891,10 @@ k_detect(const StreamDesc *__restrict__ streams, const PlanDev *__restrict__ pla
 // samples in (plus warm-up re-reads of the RMS), 4 B out, 0.75 B of block-end states -- the fp64
 // attenuation rows (24 B written + 24 B read per frame when k_apply was a kernel of its own) never exist.
 // =====================================================================================
+#ifndef B200M_COMP_UNROLL
+#define B200M_COMP_UNROLL 2         // 128-bit sample words (4 stereo frames each) per iteration of the lane-serial walk
+#endif
+constexpr int COMP_UNROLL = B200M_COMP_UNROLL;
 #ifndef B200M_RECUR_GB
 #define B200M_RECUR_GB 32           // rows of curve gathers in flight per batch (phase B): 32 beats 16 by 1.4 ms per 64-track step
 #endif
@@ -1014,16 +1018,12 @@ __device__ __forceinline__ unsigned mul_frame(unsigned smp, double g)
     return (unsigned)v0 & 0xffffu;
 }
 
-// audioop.add on a packed frame: per-sample saturating int16 add (pydub overlay, ENG:210)
+// audioop.add on a packed frame: per-sample saturating int16 add (pydub overlay, ENG:210).  The SIMD-in-a-word
+// intrinsic is six instructions for both samples (VIADD.16x2 + fix-up); min / max on unpacked halves cost 25.
 template <int CH>
 __device__ __forceinline__ unsigned add_frame_sat(unsigned x, unsigned y)
 {
-    const int s0 = max(-32768, min(32767, (int)(short)(x & 0xffffu) + (int)(short)(y & 0xffffu)));
-    if (CH == 2) {
-        const int s1 = max(-32768, min(32767, ((int)x >> 16) + ((int)y >> 16)));
-        return __byte_perm((unsigned)s0, (unsigned)s1, 0x5410);
-    }
-    return (unsigned)s0 & 0xffffu;
+    return __vaddss2(x, y);          // mono: the upper halves are zero and stay zero
 }
 
 template <int CH>
@@ -1042,7 +1042,7 @@ __device__ __forceinline__ void store_frame(int16_t *__restrict__ p, int64_t f, 
 
 // NB = 3: the crossover's bands 0..2, one WARP of the CTA per band (band_base == 0); NB = 1: the single-band helper
 // entry point (band `band_base`), one warp per CTA.  Lane l of every warp of CTA c works on (stream, tile) number 32 c + l.
-template <int CH, int NB>
+template <int CH, int NB, bool DBG>
 __global__ void __launch_bounds__(32 * NB)
 k_comp(const StreamDesc *__restrict__ streams, const PlanDev *__restrict__ plans, RecurParams P, BandPtrs bp,
        int16_t *__restrict__ proc, const double *__restrict__ ss_in, const double *__restrict__ se_in,
@@ -1281,7 +1281,7 @@ k_comp(const StreamDesc *__restrict__ streams, const PlanDev *__restrict__ plans
     bool merged = false;
     bool work = issue_rms(cb, live);
     issue_smp(cb, live);
-    double *__restrict__ att_dbg = bp.att[band];
+    double *__restrict__ att_dbg = DBG ? bp.att[band] : nullptr;     // DBG: the helper entry point wants the trajectory itself
     for (;;) {
         const bool on = live && !merged && cb < eb;
         if (!__any_sync(FULL, on)) break;
@@ -1313,7 +1313,7 @@ k_comp(const StreamDesc *__restrict__ streams, const PlanDev *__restrict__ plans
                     }
                     const int64_t fdbg = out_off + i0;
                     if (fast) {
-#pragma unroll 2
+#pragma unroll COMP_UNROLL
                         for (int w = 0; w < NW; ++w) {
                             const uint4 sw = srow[w];
                             const unsigned sv[4] = {sw.x, sw.y, sw.z, sw.w};
@@ -1324,7 +1324,7 @@ k_comp(const StreamDesc *__restrict__ streams, const PlanDev *__restrict__ plans
 #pragma unroll
                                 for (int i = 0; i < 4; ++i) {
                                     a = recur_step_pos(a, Mv[i], div_const(Mv[i], A, rA, true), div_const(Mv[i], R, rR, true));
-                                    if (att_dbg != nullptr && 4 * w + i < cnt) att_dbg[fdbg + 4 * w + i] = a;
+                                    if (DBG && att_dbg != nullptr && 4 * w + i < cnt) att_dbg[fdbg + 4 * w + i] = a;
                                     v[i] = mul_frame<2>(sv[i], gain_of_att<false>(a));
                                 }
                             } else {                                 // mono: two frames per 32-bit word
@@ -1332,10 +1332,10 @@ k_comp(const StreamDesc *__restrict__ streams, const PlanDev *__restrict__ plans
                                 for (int i = 0; i < 4; ++i) {
                                     const double2 M = mrow[4 * w + i];
                                     a = recur_step_pos(a, M.x, div_const(M.x, A, rA, true), div_const(M.x, R, rR, true));
-                                    if (att_dbg != nullptr && 8 * w + 2 * i < cnt) att_dbg[fdbg + 8 * w + 2 * i] = a;
+                                    if (DBG && att_dbg != nullptr && 8 * w + 2 * i < cnt) att_dbg[fdbg + 8 * w + 2 * i] = a;
                                     const unsigned lo = mul_frame<1>(sv[i] & 0xffffu, gain_of_att<false>(a));
                                     a = recur_step_pos(a, M.y, div_const(M.y, A, rA, true), div_const(M.y, R, rR, true));
-                                    if (att_dbg != nullptr && 8 * w + 2 * i + 1 < cnt) att_dbg[fdbg + 8 * w + 2 * i + 1] = a;
+                                    if (DBG && att_dbg != nullptr && 8 * w + 2 * i + 1 < cnt) att_dbg[fdbg + 8 * w + 2 * i + 1] = a;
                                     const unsigned hi = mul_frame<1>(sv[i] >> 16, gain_of_att<false>(a));
                                     v[i] = lo | (hi << 16);
                                 }
@@ -1354,7 +1354,7 @@ k_comp(const StreamDesc *__restrict__ streams, const PlanDev *__restrict__ plans
 #pragma unroll 1
                                 for (int i = 0; i < 4; ++i) {
                                     a = recur_step(a, Mv[i], div_const(Mv[i], A, rA, ex), div_const(Mv[i], R, rR, ex));
-                                    if (att_dbg != nullptr && 4 * w + i < cnt) att_dbg[fdbg + 4 * w + i] = a;
+                                    if (DBG && att_dbg != nullptr && 4 * w + i < cnt) att_dbg[fdbg + 4 * w + i] = a;
                                     v[i] = mul_frame<2>(sv[i], gain_of_att<true>(a));
                                 }
                             } else {
@@ -1362,10 +1362,10 @@ k_comp(const StreamDesc *__restrict__ streams, const PlanDev *__restrict__ plans
                                 for (int i = 0; i < 4; ++i) {
                                     const double2 M = mrow[4 * w + i];
                                     a = recur_step(a, M.x, div_const(M.x, A, rA, ex), div_const(M.x, R, rR, ex));
-                                    if (att_dbg != nullptr && 8 * w + 2 * i < cnt) att_dbg[fdbg + 8 * w + 2 * i] = a;
+                                    if (DBG && att_dbg != nullptr && 8 * w + 2 * i < cnt) att_dbg[fdbg + 8 * w + 2 * i] = a;
                                     const unsigned lo = mul_frame<1>(sv[i] & 0xffffu, gain_of_att<true>(a));
                                     a = recur_step(a, M.y, div_const(M.y, A, rA, ex), div_const(M.y, R, rR, ex));
-                                    if (att_dbg != nullptr && 8 * w + 2 * i + 1 < cnt) att_dbg[fdbg + 8 * w + 2 * i + 1] = a;
+                                    if (DBG && att_dbg != nullptr && 8 * w + 2 * i + 1 < cnt) att_dbg[fdbg + 8 * w + 2 * i + 1] = a;
                                     const unsigned hi = mul_frame<1>(sv[i] >> 16, gain_of_att<true>(a));
                                     v[i] = lo | (hi << 16);
                                 }
@@ -1374,7 +1374,7 @@ k_comp(const StreamDesc *__restrict__ streams, const PlanDev *__restrict__ plans
                         }
                     }
                 }
-                if (quiet && att_dbg != nullptr)
+                if (DBG && quiet && att_dbg != nullptr)
                     for (int k = 0; k < cnt; ++k) att_dbg[out_off + i0 + k] = a;
                 s_same[wid][lane] = (unsigned char)(__double_as_longlong(a) == __double_as_longlong(old_end));
                 bend_b[cb] = a;
