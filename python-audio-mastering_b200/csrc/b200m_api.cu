@@ -37,7 +37,7 @@ struct b200m_handle {
     size_t d_plans_cap = 0;
     // device tables keyed by content, least-recently-used entries evicted beyond a bound (a long-lived host --
     // the reference's worker is one -- sees a new slider combination per job; ensure_plans)
-    struct DevTab { void *ptr; uint64_t stamp; };
+    struct DevTab { void *ptr; uint64_t stamp; int flag; };
     std::map<std::tuple<double, double>, DevTab> curves;     // (thresh_rms, slope) -> CURVE_N doubles
     std::map<uint64_t, DevTab> sat_luts;                     // content key -> 65536 floats (2^15 * exciter)
     uint64_t tab_tick = 0;
@@ -59,6 +59,7 @@ struct b200m_handle {
     // time segmentation of k_chain / k_kweight: 0 = automatic, < 0 = off, > 0 = tiles per segment
     int seg_chain = 0, seg_kweight = 0;
     int chain_kernel = 0;            // 0 = automatic, 1 = k_chain (a CTA per segment), 2 = k_chainw (a warp per segment)
+    bool chain_slut_ok = true;       // k_chainw may take its 16-warp shape (B200M_CHAIN_SLUT=0 switches it off: experiments)
     unsigned long long *d_counters = nullptr;
     // host-buffer pipeline: side streams for H2D / D2H and the events that order the groups
     bool pipeline = true;
@@ -357,26 +358,25 @@ static void make_segments(std::vector<SegDesc> &out, int owner, int64_t frames, 
     }
 }
 
-// Warp segments of k_chainw: the stream is cut into a multiple of CW_WARPS equal runs of about `seg_tiles`
-// warp tiles (never shorter than twice the warm-up), so that the eight warps of a CTA share one stream
-// (one plan, one set of tables) and carry the same load; what cannot be filled is padded with empty segments.
+// Warp segments of k_chainw: the stream is cut into equal runs of about `seg_tiles` warp tiles (never shorter than
+// twice the warm-up), one warp each.
 static void make_segments_w(std::vector<SegDesc> &out, int owner, int64_t frames, int tile, double warm_frames, int seg_tiles)
 {
-    const size_t first = out.size();
     if (frames > 0) {
         const int64_t ntiles = (frames + tile - 1) / tile;
         const int64_t warm_tiles = (int64_t)std::ceil(warm_frames / tile);
         const int64_t min_seg = std::max<int64_t>(1, 2 * warm_tiles);
-        int64_t nseg = std::max<int64_t>(CW_WARPS, ((ntiles / std::max(1, seg_tiles) + CW_WARPS / 2) / CW_WARPS) * CW_WARPS);
-        while (nseg > CW_WARPS && (ntiles + nseg - 1) / nseg < min_seg) nseg -= CW_WARPS;
+        int64_t nseg = std::max<int64_t>(1, (ntiles + std::max(1, seg_tiles) / 2) / std::max(1, seg_tiles));
+        while (nseg > 1 && (ntiles + nseg - 1) / nseg < min_seg) --nseg;
         const int64_t seg = std::max(min_seg, (ntiles + nseg - 1) / nseg);
         const int warm = (int)(warm_tiles * tile);
         for (int64_t t = 0; t < ntiles; t += seg) {
             const int64_t b = t * tile, e = std::min<int64_t>(frames, (t + seg) * tile);
             out.push_back({b, e, owner, b == 0 ? 0 : warm});
         }
+    } else {
+        out.push_back({0, 0, owner, 0});
     }
-    while ((out.size() - first) % CW_WARPS != 0 || out.size() == first) out.push_back({0, 0, owner, 0});
 }
 
 static int auto_seg_tiles(int64_t total_tiles, int lo, int hi)
@@ -463,7 +463,7 @@ static int get_curve(b200m_handle *h, const b200m_band &b, const double **out, s
         cudaFree(d);
         return fail(h, B200M_ERR_CUDA, "upload of a compressor curve failed: %s", cudaGetErrorString(cudaGetLastError()));
     }
-    h->curves[key] = {d, h->tab_tick};
+    h->curves[key] = {d, h->tab_tick, 0};
     *out = d;
     return B200M_OK;
 }
@@ -480,7 +480,7 @@ static uint64_t hash_words(const void *p, size_t bytes, uint64_t seed)
 
 // ENG:128-134 tabulated over the 65536 int16 samples (b200m_plan::sat_lut), uploaded pre-scaled by 2^15 (exact):
 // the chain kernels work on 2^15 x up to quantise #1.
-static int get_sat_lut(b200m_handle *h, const b200m_plan &p, const float **out)
+static int get_sat_lut(b200m_handle *h, const b200m_plan &p, const float **out, int *odd = nullptr)
 {
     std::vector<float> own;
     const float *src = p.sat_lut;
@@ -501,17 +501,29 @@ static int get_sat_lut(b200m_handle *h, const b200m_plan &p, const float **out)
         key = hash_words(src, 65536 * sizeof(float), 0);
     }
     auto it = h->sat_luts.find(key);
-    if (it != h->sat_luts.end()) { it->second.stamp = h->tab_tick; *out = (const float *)it->second.ptr; return B200M_OK; }
+    if (it != h->sat_luts.end()) {
+        it->second.stamp = h->tab_tick; *out = (const float *)it->second.ptr;
+        if (odd) *odd = it->second.flag;
+        return B200M_OK;
+    }
     evict_tables(h->sat_luts, MAX_SAT_LUTS, h->tab_tick);
     std::vector<float> scaled(65536);
     for (int i = 0; i < 65536; ++i) scaled[i] = src[i] * 32768.0f;      // exact (power of two; |value| ~ 1)
+    // odd in the sample?  entry(-s) == -entry(s) bit for bit for s = 1 .. 32767 (numpy's tanh and IEEE products are)
+    int sym = 1;
+    for (int m = 1; m < 32768 && sym; ++m) {
+        uint32_t pos, neg;
+        std::memcpy(&pos, &scaled[m], 4); std::memcpy(&neg, &scaled[65536 - m], 4);
+        if ((pos ^ 0x80000000u) != neg) sym = 0;
+    }
+    if (odd) *odd = sym;
     float *d = nullptr;
     CK(cudaMalloc(&d, 65536 * sizeof(float)));
     if (cudaMemcpy(d, scaled.data(), 65536 * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess) {
         cudaFree(d);
         return fail(h, B200M_ERR_CUDA, "upload of an exciter table failed: %s", cudaGetErrorString(cudaGetLastError()));
     }
-    h->sat_luts[key] = {d, h->tab_tick};
+    h->sat_luts[key] = {d, h->tab_tick, sym};
     *out = d;
     return B200M_OK;
 }
@@ -615,7 +627,7 @@ static int ensure_plans(b200m_handle *h, const b200m_plan *plans, int n)
         d.width_on = p.width_on && p.channels == 2; d.multiband = p.multiband; d.has_lufs = p.has_lufs;
         d.sat_clean = p.sat_clean; d.sat_mix = p.sat_mix; d.sat_drive = p.sat_drive;
         d.width = p.width; d.lufs = p.lufs;
-        if (p.sat_on) { int rc = get_sat_lut(h, p, &d.sat_lut); if (rc) return rc; }
+        if (p.sat_on) { int rc = get_sat_lut(h, p, &d.sat_lut, &d.sat_sym); if (rc) return rc; }
         for (int s = 0; s < p.n_eq; ++s) build_sectab(p.eq[s], d.eq[s]);
         build_sectab(p.kw[0], d.kw[0]);
         build_sectab(p.kw[1], d.kw[1]);
@@ -712,6 +724,7 @@ extern "C" int b200m_create(int device, b200m_handle **out)
     h = new b200m_handle();
     h->device = device;
     if (const char *ck = std::getenv("B200M_CHAIN_KERNEL")) h->chain_kernel = std::max(0, std::min(2, std::atoi(ck)));   // test / experiment override
+    if (const char *ck = std::getenv("B200M_CHAIN_SLUT")) h->chain_slut_ok = std::atoi(ck) != 0;
     e = allow_smem(k_chain<1, true>, chain_smem_bytes<1>());
     if (e == cudaSuccess) e = allow_smem(k_chain<2, true>, chain_smem_bytes<2>());
     if (e == cudaSuccess) e = allow_smem(k_chain<1, false>, chain_smem_bytes<1>());
@@ -724,6 +737,10 @@ extern "C" int b200m_create(int device, b200m_handle **out)
     if (e == cudaSuccess) e = allow_smem(k_chainw<1, false, false>, ChainW<1>::SMEM);
     if (e == cudaSuccess) e = allow_smem(k_chainw<2, true, false>, ChainW<2>::SMEM);
     if (e == cudaSuccess) e = allow_smem(k_chainw<2, false, false>, ChainW<2>::SMEM);
+    if (e == cudaSuccess) e = allow_smem(k_chainw<1, true, true, CW_SLUT, true>, ChainW<1>::SMEM_SLUT);
+    if (e == cudaSuccess) e = allow_smem(k_chainw<1, false, true, CW_SLUT, true>, ChainW<1>::SMEM_SLUT);
+    if (e == cudaSuccess) e = allow_smem(k_chainw<2, true, true, CW_SLUT, true>, ChainW<2>::SMEM_SLUT);
+    if (e == cudaSuccess) e = allow_smem(k_chainw<2, false, true, CW_SLUT, true>, ChainW<2>::SMEM_SLUT);
     if (e == cudaSuccess) e = allow_smem(k_detect<1>, detect_smem_bytes(8192));
     if (e == cudaSuccess) e = allow_smem(k_detect<2>, detect_smem_bytes(8192));
     if (e == cudaSuccess) e = allow_smem(k_comp<1, 1, true>, recur_smem_bytes(1));
@@ -919,7 +936,9 @@ struct Group {
     const TrackDesc *d_tracks = nullptr;
     const SegDesc *d_csegs = nullptr, *d_ksegs = nullptr;   // k_chain / k_kweight segments
     int n_csegs = 0, n_ksegs = 0;
-    bool chain_warps = false;        // csegs are warp segments (k_chainw), padded to eight per CTA
+    bool chain_warps = false;        // csegs are warp segments (k_chainw)
+    bool chain_slut = false;         // ... in its 16-warp shape around a shared-memory exciter table (padded to whole CTAs, d_cta_iters)
+    const int32_t *d_cta_iters = nullptr;
     int single_plan = -1;            // >= 0: every stream of the group uses this plan (its tables travel as a kernel parameter)
 };
 
@@ -1074,6 +1093,7 @@ struct GroupPlan {
     std::vector<StreamDesc> streams;
     std::vector<TrackDesc> tracks;
     std::vector<SegDesc> csegs, ksegs;
+    std::vector<int32_t> cta_iters;  // k_chainw's 16-warp shape: tiles every warp of CTA i walks
     int64_t F = 0, Fp = 0, in_total = 0, zoff = 0, out_base = 0;      // F: workspace frames (aligned track starts), Fp: packed output frames
     size_t desc_bytes = 0, res_off = 0, pin_bytes = 0, need = 0;
     int n_targets = 0;               // > 0: loudness sweep (b200m_master_batch_targets): that many outputs per track
@@ -1160,6 +1180,21 @@ static void plan_group(const b200m_handle *h, GroupPlan &gp, bool in_dev, bool o
             const int wseg = (int)std::min<double>(1 << 20, std::max(8.0, std::ceil(run / wt)));
             for (size_t i = 0; i < gp.streams.size(); ++i)
                 make_segments_w(gp.csegs, (int)i, gp.streams[i].out_frames, wt, chain_warm_frames(plans[gp.streams[i].plan]), h->seg_chain > 0 ? h->seg_chain * (TILE / wt) : wseg);
+            // one plan with the exciter on and an odd table: the 16-warp shape keeps the table in shared memory
+            g.chain_slut = g.single_plan >= 0 && (size_t)g.single_plan < h->plans_host.size() && h->plans_host[g.single_plan].sat_on &&
+                           h->plans_host[g.single_plan].sat_sym && h->chain_slut_ok;
+            if (g.chain_slut) {
+                while (gp.csegs.size() % CW_SLUT != 0) gp.csegs.push_back({0, 0, 0, 0});
+                for (size_t c0 = 0; c0 < gp.csegs.size(); c0 += CW_SLUT) {
+                    int64_t it = 0;
+                    for (int w = 0; w < CW_SLUT; ++w) {
+                        const SegDesc &sg = gp.csegs[c0 + w];
+                        const int64_t first = std::max<int64_t>(0, sg.begin - sg.warm);
+                        it = std::max(it, (sg.end - first + wt - 1) / wt);
+                    }
+                    gp.cta_iters.push_back((int32_t)it);
+                }
+            }
         } else {
             for (size_t i = 0; i < gp.streams.size(); ++i)
                 make_segments(gp.csegs, (int)i, gp.streams[i].out_frames, TILE, chain_warm_frames(plans[gp.streams[i].plan]), cs);
@@ -1171,7 +1206,7 @@ static void plan_group(const b200m_handle *h, GroupPlan &gp, bool in_dev, bool o
     }
     gp.F = F; gp.Fp = Fp; gp.in_total = in_total; gp.zoff = zoff;
     gp.desc_bytes = gp.streams.size() * sizeof(StreamDesc) + gp.tracks.size() * sizeof(TrackDesc) +
-                    (gp.csegs.size() + gp.ksegs.size()) * sizeof(SegDesc);
+                    (gp.csegs.size() + gp.ksegs.size()) * sizeof(SegDesc) + gp.cta_iters.size() * sizeof(int32_t);
     gp.res_off = (gp.desc_bytes + 63) & ~(size_t)63;       // double2 results: 16-byte aligned slot after the descriptors
     gp.pin_bytes = (gp.res_off + (size_t)g.n_tracks * 16 * (1 + (size_t)n_targets) + 255) & ~(size_t)255;
     size_t need = 16384 + gp.desc_bytes + (size_t)g.n_tracks * 16 * (1 + (size_t)n_targets) + (size_t)F * ch * 2 /*proc*/ + (size_t)F * 4 /*kw*/ +
@@ -1206,6 +1241,7 @@ static int exec_group(b200m_handle *h, GroupPlan &gp, char *ws, char *pin, const
     TrackDesc *d_tracks = A.take<TrackDesc>(gp.tracks.size());
     SegDesc *d_csegs = A.take<SegDesc>(gp.csegs.size() + 1);
     SegDesc *d_ksegs = A.take<SegDesc>(gp.ksegs.size() + 1);
+    int32_t *d_cta_iters = A.take<int32_t>(gp.cta_iters.size() + 1);
     double2 *d_loud = A.take<double2>((size_t)g.n_tracks * (1 + (size_t)gp.n_targets));     // [0]: k_gate's, [1 + k]: target k
     int16_t *d_proc = ext_proc ? ext_proc : A.take<int16_t>((size_t)F * ch);
     float *d_kw = A.take<float>(F);
@@ -1244,6 +1280,7 @@ static int exec_group(b200m_handle *h, GroupPlan &gp, char *ws, char *pin, const
         CK(up(d_tracks, gp.tracks.data(), gp.tracks.size() * sizeof(TrackDesc)));
         CK(up(d_csegs, gp.csegs.data(), gp.csegs.size() * sizeof(SegDesc)));
         CK(up(d_ksegs, gp.ksegs.data(), gp.ksegs.size() * sizeof(SegDesc)));
+        CK(up(d_cta_iters, gp.cta_iters.data(), gp.cta_iters.size() * sizeof(int32_t)));
     }
     g.d_streams = d_streams; g.d_tracks = d_tracks; g.d_csegs = d_csegs; g.d_ksegs = d_ksegs;
     const int16_t *d_src = pcm_in;
@@ -1265,7 +1302,6 @@ static int exec_group(b200m_handle *h, GroupPlan &gp, char *ws, char *pin, const
 
     // ---- kernels (all on the handle's stream) ------------------------------------------------
     if (g.chain_warps) {
-        const int nb = g.n_csegs / CW_WARPS;
         ChainTabsC ct;                           // 3.6 KB, copied into the launch parameter buffer by the runtime
         const bool pt = g.single_plan >= 0;
         if (pt) {
@@ -1273,17 +1309,27 @@ static int exec_group(b200m_handle *h, GroupPlan &gp, char *ws, char *pin, const
             const SecTab *src[8] = {&pd.eq[0], &pd.eq[1], &pd.eq[2], &pd.eq[3], &pd.lp[0], &pd.lp[1], &pd.hp[0], &pd.hp[1]};
             for (int s8 = 0; s8 < 8; ++s8) fill_tabc(ct.sec[s8], *src[s8]);
         }
-#define LAUNCH_CHAINW(CHN, NAN_, PT_) \
-        LAUNCH("k_chain", k_chainw<CHN, NAN_, PT_><<<nb, 32 * CW_WARPS, (PT_) ? ChainW<CHN>::SMEM_PT : ChainW<CHN>::SMEM, h->stream>>>(d_src, d_streams, d_csegs, g.n_csegs, h->d_plans, d_proc, bp, ct))
         const bool nanchk = !g.chain_stable;
-        if (ch == 2) {
-            if (pt) { if (nanchk) LAUNCH_CHAINW(2, true, true); else LAUNCH_CHAINW(2, false, true); }
-            else    { if (nanchk) LAUNCH_CHAINW(2, true, false); else LAUNCH_CHAINW(2, false, false); }
+        if (g.chain_slut) {
+            const int nb = g.n_csegs / CW_SLUT;
+#define LAUNCH_CHAINS(CHN, NAN_) \
+            LAUNCH("k_chain", k_chainw<CHN, NAN_, true, CW_SLUT, true><<<nb, 32 * CW_SLUT, ChainW<CHN>::SMEM_SLUT, h->stream>>>(d_src, d_streams, d_csegs, g.n_csegs, h->d_plans, d_proc, bp, ct, d_cta_iters))
+            if (ch == 2) { if (nanchk) LAUNCH_CHAINS(2, true); else LAUNCH_CHAINS(2, false); }
+            else         { if (nanchk) LAUNCH_CHAINS(1, true); else LAUNCH_CHAINS(1, false); }
+#undef LAUNCH_CHAINS
         } else {
-            if (pt) { if (nanchk) LAUNCH_CHAINW(1, true, true); else LAUNCH_CHAINW(1, false, true); }
-            else    { if (nanchk) LAUNCH_CHAINW(1, true, false); else LAUNCH_CHAINW(1, false, false); }
-        }
+            const int nb = g.n_csegs;
+#define LAUNCH_CHAINW(CHN, NAN_, PT_) \
+            LAUNCH("k_chain", k_chainw<CHN, NAN_, PT_><<<nb, 32, (PT_) ? ChainW<CHN>::SMEM_PT : ChainW<CHN>::SMEM, h->stream>>>(d_src, d_streams, d_csegs, g.n_csegs, h->d_plans, d_proc, bp, ct, nullptr))
+            if (ch == 2) {
+                if (pt) { if (nanchk) LAUNCH_CHAINW(2, true, true); else LAUNCH_CHAINW(2, false, true); }
+                else    { if (nanchk) LAUNCH_CHAINW(2, true, false); else LAUNCH_CHAINW(2, false, false); }
+            } else {
+                if (pt) { if (nanchk) LAUNCH_CHAINW(1, true, true); else LAUNCH_CHAINW(1, false, true); }
+                else    { if (nanchk) LAUNCH_CHAINW(1, true, false); else LAUNCH_CHAINW(1, false, false); }
+            }
 #undef LAUNCH_CHAINW
+        }
     } else if (ch == 2) {
         if (g.chain_stable) LAUNCH("k_chain", k_chain<2, false><<<g.n_csegs, NSEG * 2, chain_smem_bytes<2>(), h->stream>>>(d_src, d_streams, d_csegs, h->d_plans, d_proc, bp));
         else                LAUNCH("k_chain", k_chain<2, true><<<g.n_csegs, NSEG * 2, chain_smem_bytes<2>(), h->stream>>>(d_src, d_streams, d_csegs, h->d_plans, d_proc, bp));

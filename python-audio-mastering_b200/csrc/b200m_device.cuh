@@ -58,7 +58,8 @@ struct PlanDev {
     const double *curve[3];       // device pointers, CURVE_N doubles each (NULL if !multiband)
     const int32_t *ptree;         // numpy pairwise-sum tree of a full 400 ms block (k_blocks), or NULL
     const int32_t *htree;         // the same for one 100 ms hop when the block tree is four hop trees (k_hops), or NULL
-    int32_t hop, pad2_;           // hop length in samples (0: no hop sharing at this rate)
+    int32_t hop;                  // hop length in samples (0: no hop sharing at this rate)
+    int32_t sat_sym;              // sat_lut is odd: entry(-s) == -entry(s) bit for bit (k_chainw may index a half table by |s|)
     const float *sat_lut;         // sat_on: 2^15 * exciter(s / 2^15) for the 65536 int16 samples s, indexed by (uint16_t)s (ENG:128-134)
     SecTab eq[4], lp[2], hp[2], kw[2];
 };
@@ -210,5 +211,14 @@ __device__ __forceinline__ float exciter(float x, float clean, float mix, float 
 }
 
 __device__ __forceinline__ int pidx(int f) { return f + (f / SEG); }
+
+// prmt.b32 in its generic form: selector nibbles with bit 3 set replicate the SIGN of the byte they name, so
+// 0x9910 / 0xbb32 sign-extend the low / high int16 of a word in one instruction.  (__byte_perm masks that bit.)
+__device__ __forceinline__ int prmt_sx(unsigned x, unsigned sel)
+{
+    int r;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(x), "r"(0u), "r"(sel));
+    return r;
+}
 
 }  // namespace b200m

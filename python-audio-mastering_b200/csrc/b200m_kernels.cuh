@@ -275,17 +275,22 @@ constexpr size_t chain_smem_bytes()
 // Warps never wait for each other, so their fp64-heavy and integer-heavy phases overlap freely.  Segments are joined by overlap-discard exactly like
 // k_chain's; since eight times as many independent segments are needed, the host picks this kernel
 // for batches large enough to keep the warm-up share small (b200m_set_chain_kernel).
-// One warp per CTA (CW_WARPS); with more, the segments of a CTA belong to one stream (the host pads).
+// One warp per CTA, or sixteen around a shared-memory copy of the exciter table (template parameter CW, below).
 // =====================================================================================
-// Warps per CTA of k_chainw.  ONE: everything a warp does then depends on blockIdx and kernel parameters
-// only, the compiler can prove its control flow uniform, and the shuffles lose their divergence guards (the
-// code shrinks from 6400 to 3300 instructions, no spills); with the tables in the constant bank a CTA needs
-// 12 KB of shared memory, so 16 of them fit an SM like two CTAs of eight warps did.  Measured: 10.5 -> 9.5 ms
-// on 64 tracks, 1.49 -> 1.38 ms on 8.  (> 1: segments per stream are padded to a multiple of it.)
-#ifndef B200M_CW_WARPS
-#define B200M_CW_WARPS 1
-#endif
-constexpr int CW_WARPS = B200M_CW_WARPS;
+// Warps per CTA of k_chainw (template parameter CW).  ONE (the default shape): everything a warp does then
+// depends on blockIdx and kernel parameters only, the compiler can prove its control flow uniform, and the
+// shuffles lose their divergence guards (the code shrinks from 6400 to 3300 instructions, no spills); with the
+// tables in the constant bank a CTA needs 12 KB of shared memory, so 16 of them fit an SM like two CTAs of eight
+// warps did.  Measured: 10.5 -> 9.5 ms on 64 tracks, 1.49 -> 1.38 ms on 8.
+// SIXTEEN (SLUT: the launch has one plan and its exciter is on): the CTA fills an SM and keeps the exciter
+// table in shared memory.  ENG:128-134 is a gather per sample; 32 lanes gathering from a 256 KB table in global
+// memory cost the L1 one sector per clock (+3.5 ms per 64-track step, more than the tanhf it replaced), while
+// shared memory serves the same gather in ~3 conflict cycles.  The table is odd (numpy's tanh is; checked at
+// upload), so |s| <= 32768 indexes 128 KB.  Control flow stays provably uniform: the 16 warps of a CTA walk
+// their own segments, but all for the CTA's common number of tiles (cta_iters[blockIdx.x], the host pads with
+// empty segments), a warp past its segment's end filtering zeros into nothing.
+constexpr int CW_SLUT = 16;
+constexpr size_t SLUT_BYTES = 131200;                       // 32769 floats, rounded up to a multiple of 64
 template <int CH> struct ChainW {
     static constexpr int NL = 32 / CH;                      // lanes per channel
     static constexpr int WT = NL * SEG;                     // frames per warp tile
@@ -294,8 +299,9 @@ template <int CH> struct ChainW {
     static constexpr int USTRIDE = 20;                      // floats per lane in the re-floated stash
     static constexpr size_t WARP_BYTES = (size_t)RAW_WORDS * 4 + 32 * USTRIDE * 4 + 8 * CH * 2 * 8;
     static constexpr size_t QTAB_BYTES = 8 * 32 * 4 * 8;  // Q[lane] of the eight sections: all the shared memory the tables need when the rest travels as a parameter
-    static constexpr size_t SMEM = 8 * sizeof(SecTab) + CW_WARPS * WARP_BYTES;     // tables in shared memory (several plans in the launch)
-    static constexpr size_t SMEM_PT = QTAB_BYTES + CW_WARPS * WARP_BYTES;          // tables in the constant bank
+    static constexpr size_t SMEM = 8 * sizeof(SecTab) + WARP_BYTES;               // CW = 1, tables in shared memory (several plans in the launch)
+    static constexpr size_t SMEM_PT = QTAB_BYTES + WARP_BYTES;                    // CW = 1, tables in the constant bank
+    static constexpr size_t SMEM_SLUT = SLUT_BYTES + QTAB_BYTES + CW_SLUT * WARP_BYTES;   // CW = 16, exciter table + Q tables + 16 warps
 };
 
 // The lane-independent tables of the launch's single plan (SecTabC, b200m_device.cuh), by value.
@@ -451,46 +457,62 @@ __device__ __forceinline__ void store_q16_w(int16_t *__restrict__ dst, const int
 #define B200M_CHAINW_OCC 2
 #endif
 // PT: the launch uses ONE plan and its lane-independent tables arrive in `ct` (constant bank).
-template <int CH, bool NANCHK, bool PT>
-__global__ void __launch_bounds__(32 * CW_WARPS, B200M_CHAINW_OCC * 8 / CW_WARPS)
+// CW / SLUT: see above (SLUT implies PT and CW == CW_SLUT; cta_iters is only read when CW > 1).
+template <int CH, bool NANCHK, bool PT, int CW = 1, bool SLUT = false>
+__global__ void __launch_bounds__(32 * CW, CW == 1 ? B200M_CHAINW_OCC * 8 : 1)
 k_chainw(const int16_t *__restrict__ pcm_in, const StreamDesc *__restrict__ streams, const SegDesc *__restrict__ segs, int n_segs,
-         const PlanDev *__restrict__ plans, int16_t *__restrict__ proc, BandPtrs bp, const __grid_constant__ ChainTabsC ct)
+         const PlanDev *__restrict__ plans, int16_t *__restrict__ proc, BandPtrs bp, const __grid_constant__ ChainTabsC ct,
+         const int32_t *__restrict__ cta_iters)
 {
     using W = ChainW<CH>;
     constexpr int NL = W::NL, WT = W::WT;
+    static_assert(!SLUT || (PT && CW == CW_SLUT), "the shared-memory exciter table needs the single-plan, 16-warp shape");
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    SecTab *tabs = reinterpret_cast<SecTab *>(smem_raw);                 // !PT: eq[4] lp[2] hp[2] of the CTA's plan
-    double (*sQ)[32][4] = reinterpret_cast<double (*)[32][4]>(smem_raw); //  PT: only their Q[lane] tables
-    const int warp = CW_WARPS == 1 ? 0 : (int)(threadIdx.x >> 5), lane = threadIdx.x & 31;    // one warp per CTA: everything below is CTA-uniform
-    unsigned char *wbase = smem_raw + (PT ? W::QTAB_BYTES : 8 * sizeof(SecTab)) + (size_t)warp * W::WARP_BYTES;
+    float *slut = reinterpret_cast<float *>(smem_raw);                   // SLUT: 2^15 * exciter(m / 2^15), m = 0 .. 32768
+    unsigned char *smem_tab = smem_raw + (SLUT ? SLUT_BYTES : 0);
+    SecTab *tabs = reinterpret_cast<SecTab *>(smem_tab);                 // !PT: eq[4] lp[2] hp[2] of the CTA's plan
+    double (*sQ)[32][4] = reinterpret_cast<double (*)[32][4]>(smem_tab); //  PT: only their Q[lane] tables
+    const int warp = CW == 1 ? 0 : (int)(threadIdx.x >> 5), lane = threadIdx.x & 31;    // one warp per CTA: everything below is CTA-uniform
+    unsigned char *wbase = smem_tab + (PT ? W::QTAB_BYTES : 8 * sizeof(SecTab)) + (size_t)warp * W::WARP_BYTES;
     unsigned *raw = reinterpret_cast<unsigned *>(wbase);                 // [NL][RSTRIDE] raw PCM of the tile being fetched
     float *su = reinterpret_cast<float *>(wbase + (size_t)W::RAW_WORDS * 4) + lane * W::USTRIDE;   // this lane's 16 re-floated samples
     double *carry = reinterpret_cast<double *>(wbase + (size_t)W::RAW_WORDS * 4 + 32 * W::USTRIDE * 4);   // [8][CH][2]
 
-    const int sidx = blockIdx.x * CW_WARPS + warp;
-    const SegDesc sg0 = segs[blockIdx.x * CW_WARPS];                     // the CTA's first segment names the stream (and so the plan)
+    const int sidx = blockIdx.x * CW + warp;
+    const SegDesc sg0 = segs[blockIdx.x * CW];                           // the CTA's first segment names the plan (CW > 1: the launch has one)
     const PlanDev *__restrict__ pl = plans + streams[sg0.owner].plan;
     if (PT) {
         const SecTab *src = pl->eq;                                      // eq[4] lp[2] hp[2] are contiguous in PlanDev
         double *dst = reinterpret_cast<double *>(sQ);
-        for (int i = threadIdx.x; i < 8 * 128; i += 32 * CW_WARPS) dst[i] = reinterpret_cast<const double *>(src[i >> 7].Q)[i & 127];
+        for (int i = threadIdx.x; i < 8 * 128; i += 32 * CW) dst[i] = reinterpret_cast<const double *>(src[i >> 7].Q)[i & 127];
     } else {
         const double *src = reinterpret_cast<const double *>(pl->eq);
         double *dst = reinterpret_cast<double *>(tabs);
-        for (int i = threadIdx.x; i < 8 * (int)(sizeof(SecTab) / 8); i += 32 * CW_WARPS) dst[i] = src[i];
+        for (int i = threadIdx.x; i < 8 * (int)(sizeof(SecTab) / 8); i += 32 * CW) dst[i] = src[i];
+    }
+    if (SLUT) {
+        // table entry for the int16 sample s lives at (uint16_t)s: [0, 32768) are s >= 0, entry 32768 is s = -32768
+        const float *__restrict__ g = pl->sat_lut;
+        for (int i = threadIdx.x; i < 32768; i += 32 * CW) slut[i] = __ldg(g + i);
+        if (threadIdx.x == 0) slut[32768] = -__ldg(g + 32768);
     }
     if (lane < 8 * CH * 2) carry[lane] = 0.0;
     __syncthreads();                                                     // the only CTA-wide barrier
-    if (sidx >= n_segs) return;
-    const SegDesc sg = segs[sidx];
-    if (sg.begin >= sg.end) return;
+    if (CW == 1) {
+        if (sidx >= n_segs) return;
+    }
+    const SegDesc sg = segs[sidx];                                       // CW > 1: the host pads the list to whole CTAs with empty segments
+    if (CW == 1) {
+        if (sg.begin >= sg.end) return;
+    }
     const StreamDesc sd = streams[sg.owner];
     const int sat_on = pl->sat_on, n_eq = pl->n_eq, width_on = pl->width_on, multiband = pl->multiband;
     const float *__restrict__ lut = pl->sat_lut;
     const double width = pl->width;
     const float widthf = (float)width;
     const int c = CH == 2 ? lane >> 4 : 0, j = CH == 2 ? lane & 15 : lane;
-    const unsigned csel = c ? 0x4432u : 0x4410u;                        // __byte_perm selector: this lane's channel of a packed frame
+    const unsigned csel = c ? 0xbb32u : 0x9910u;                        // __byte_perm selector: this lane's channel of a packed frame, sign-extended
+    const int in_frames = sg.begin < sg.end ? sd.in_frames : 0;         // an empty (padding) segment reads nothing
 
     const int16_t *__restrict__ in = pcm_in + sd.in_off * CH;
     const bool in16 = (reinterpret_cast<unsigned long long>(in) & 15ull) == 0;
@@ -506,24 +528,24 @@ k_chainw(const int16_t *__restrict__ pcm_in, const StreamDesc *__restrict__ stre
             if (CH == 2) {
                 const int gf = t0 + 4 * p;
                 unsigned *d = raw + W::RSTRIDE * (p >> 2) + 4 * (p & 3);
-                if (in16 && gf + 4 <= sd.in_frames) {
+                if (in16 && gf + 4 <= in_frames) {
                     const unsigned sa = (unsigned)__cvta_generic_to_shared(d);
                     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(reinterpret_cast<const unsigned *>(in) + gf) : "memory");
                 } else {
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) d[k] = gf + k < sd.in_frames ? reinterpret_cast<const unsigned *>(in)[gf + k] : 0u;
+                    for (int k = 0; k < 4; ++k) d[k] = gf + k < in_frames ? reinterpret_cast<const unsigned *>(in)[gf + k] : 0u;
                 }
             } else {
                 const int gf = t0 + 8 * p;
                 unsigned *d = raw + W::RSTRIDE * (p >> 1) + 4 * (p & 1);
-                if (in16 && gf + 8 <= sd.in_frames) {
+                if (in16 && gf + 8 <= in_frames) {
                     const unsigned sa = (unsigned)__cvta_generic_to_shared(d);
                     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(in + gf) : "memory");
                 } else {
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
-                        const unsigned lo = gf + 2 * k < sd.in_frames ? (unsigned)(unsigned short)in[gf + 2 * k] : 0u;
-                        const unsigned hi = gf + 2 * k + 1 < sd.in_frames ? (unsigned)(unsigned short)in[gf + 2 * k + 1] : 0u;
+                        const unsigned lo = gf + 2 * k < in_frames ? (unsigned)(unsigned short)in[gf + 2 * k] : 0u;
+                        const unsigned hi = gf + 2 * k + 1 < in_frames ? (unsigned)(unsigned short)in[gf + 2 * k + 1] : 0u;
                         d[k] = lo | (hi << 16);
                     }
                 }
@@ -534,9 +556,12 @@ k_chainw(const int16_t *__restrict__ pcm_in, const StreamDesc *__restrict__ stre
 
     const int seg_begin = (int)sg.begin, seg_end = (int)sg.end;
     const int t_first = max(0, seg_begin - sg.warm);
+    // CW == 1: the warp's own tile count (CTA-uniform: it depends on blockIdx alone); CW > 1: the CTA's common count
+    const int n_iter = CW == 1 ? (seg_end - t_first + WT - 1) / WT : cta_iters[blockIdx.x];
     fetch(t_first);
-    for (int t0 = t_first; t0 < seg_end; t0 += WT) {
-        const bool store = t0 >= seg_begin;          // warm-up tiles only advance the filter states
+    for (int it = 0; it < n_iter; ++it) {
+        const int t0 = t_first + it * WT;
+        const bool store = t0 >= seg_begin && t0 < seg_end;      // warm-up tiles only advance the filter states
         const int nvalid = store ? min(WT, seg_end - t0) : 0;
         asm volatile("cp.async.wait_group 0;" ::: "memory");
         __syncwarp();
@@ -546,7 +571,7 @@ k_chainw(const int16_t *__restrict__ pcm_in, const StreamDesc *__restrict__ stre
         // sample: one gather from the table the host tabulated with numpy (PlanDev::sat_lut, pre-scaled).
         double x[SEG];
         {
-            unsigned s16[SEG];                       // the lane's 16 samples as uint16 bit patterns
+            int sx[SEG];                             // the lane's 16 samples, sign-extended
             if (CH == 2) {
                 const uint4 *rp = reinterpret_cast<const uint4 *>(raw + W::RSTRIDE * j);
 #pragma unroll
@@ -554,7 +579,7 @@ k_chainw(const int16_t *__restrict__ pcm_in, const StreamDesc *__restrict__ stre
                     const uint4 w = rp[i];
                     const unsigned ww[4] = {w.x, w.y, w.z, w.w};
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) s16[4 * i + k] = __byte_perm(ww[k], 0u, csel);
+                    for (int k = 0; k < 4; ++k) sx[4 * i + k] = prmt_sx(ww[k], csel);
                 }
             } else {
                 const uint4 *rp = reinterpret_cast<const uint4 *>(raw + W::RSTRIDE * j);
@@ -564,24 +589,31 @@ k_chainw(const int16_t *__restrict__ pcm_in, const StreamDesc *__restrict__ stre
                     const unsigned ww[4] = {w.x, w.y, w.z, w.w};
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
-                        s16[8 * i + 2 * k] = ww[k] & 0xffffu;
-                        s16[8 * i + 2 * k + 1] = ww[k] >> 16;
+                        sx[8 * i + 2 * k] = prmt_sx(ww[k], 0x9910u);
+                        sx[8 * i + 2 * k + 1] = prmt_sx(ww[k], 0xbb32u);
                     }
                 }
             }
-            if (sat_on) {
+            if (SLUT) {
+                // the table is odd: look up |s| and put the sign back (sat_on is certain: the host chose this shape)
                 float v[SEG];
 #pragma unroll
-                for (int n = 0; n < SEG; ++n) v[n] = __ldg(lut + s16[n]);      // all 16 gathers in flight together
+                for (int n = 0; n < SEG; ++n) v[n] = __uint_as_float(__float_as_uint(slut[abs(sx[n])]) ^ ((unsigned)sx[n] & 0x80000000u));
+#pragma unroll
+                for (int n = 0; n < SEG; ++n) x[n] = (double)v[n];
+            } else if (sat_on) {
+                float v[SEG];
+#pragma unroll
+                for (int n = 0; n < SEG; ++n) v[n] = __ldg(lut + ((unsigned)sx[n] & 0xffffu));      // all 16 gathers in flight together
 #pragma unroll
                 for (int n = 0; n < SEG; ++n) x[n] = (double)v[n];
             } else {
 #pragma unroll
-                for (int n = 0; n < SEG; ++n) x[n] = (double)(int)(short)s16[n];
+                for (int n = 0; n < SEG; ++n) x[n] = (double)sx[n];
             }
         }
         __syncwarp();                                // raw[] is free again
-        if (t0 + WT < seg_end) fetch(t0 + WT);
+        if (CW > 1 || t0 + WT < seg_end) fetch(t0 + WT);        // CW > 1: uniformly (past the input it is a zero fill)
 
         // ---- EQ (bypassed sections were dropped at plan time, ENG:171,186) ---------------------------
 #pragma unroll
