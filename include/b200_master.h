@@ -129,8 +129,9 @@ int b200m_reset_profile(b200m_handle *h);
 /* Compressor recurrence tiling: each (chunk, band) attenuation chain is cut into time tiles that
  * run in parallel after a warm-up over the preceding `warm_frames` (k_recur_tiles), wrong guesses
  * are repaired in `rounds` parallel passes and finally by an exact sequential pass (k_recur_fix).
- * tile_frames = 0: automatic tile length; warm_frames = 0: default 8192 (counted in frames of
- * 32-frame blocks with any activity; silent stretches carry the state unchanged); rounds < 0: default 4.
+ * tile_frames = 0: automatic tile length; warm_frames = 0: automatic: 16384 or 1.75 release times of the band, whichever is more (counted in frames of
+ * 32-frame blocks with any activity; silent stretches carry the state unchanged); rounds < 0: automatic, 6 .. 24 by tile length (each round is a
+ * list-building launch plus a repair launch over the dirty tiles only: a round with nothing to repair costs microseconds).
  * Results never depend on any of the three. */
 int b200m_set_recur_tiling(b200m_handle *h, int tile_frames, int warm_frames, int rounds);
 /* Time segmentation of the filter kernels: k_chain (2048-frame tiles) and k_kweight (4096-sample

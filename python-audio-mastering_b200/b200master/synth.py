@@ -22,7 +22,16 @@ def _db(x):
     return 10.0 ** (x / 20.0)
 
 
-def make_track(index: int, seconds: float, rate: int, channels: int = 2) -> np.ndarray:
+# hi-hat pattern: (period s, decay tau s, level dBFS, hold s): full level for `hold`, then an exponential decay.
+# HAT_SPARSE is the recipe the golden fixtures were written with (one short burst per off-beat: the high band is
+# above its -15 dB RMS threshold ~1.5 % of the time); HAT_DENSE is the benchmark workload's (loud 50 ms bursts on
+# every eighth note: every compressor band is above its threshold for >= 10 % of the frames, SURVEY 8d --
+# bench.py measures and asserts it).
+HAT_SPARSE = (0.5, 0.015, -10.0, 0.0)
+HAT_DENSE = (0.25, 0.020, 9.0, 0.050)
+
+
+def make_track(index: int, seconds: float, rate: int, channels: int = 2, hat_cfg=HAT_SPARSE) -> np.ndarray:
     """int16 array of shape (N, 2) (or (N,) for mono), N = round(seconds * rate)."""
     n = int(round(seconds * rate))
     rng = np.random.Generator(np.random.PCG64(SEED_BASE + index))
@@ -59,9 +68,9 @@ def make_track(index: int, seconds: float, rate: int, channels: int = 2) -> np.n
     hat_spec[(f < 6000.0) | (f > 12000.0)] = 0.0
     hat = np.fft.irfft(hat_spec, n)
     hat /= max(np.max(np.abs(hat)), 1e-12)
-    off = t - 0.25
-    hat_env = np.where(off >= 0, np.exp(-np.mod(off, 0.5) / 0.015), 0.0)
-    hat = _db(-10.0) * hat * hat_env
+    off = t - 0.5 * hat_cfg[0]
+    hat_env = np.where(off >= 0, np.exp(-np.maximum(np.mod(off, hat_cfg[0]) - hat_cfg[3], 0.0) / hat_cfg[1]), 0.0)
+    hat = _db(hat_cfg[2]) * hat * hat_env
 
     left = noise_l + sines_l + kick + click + hat
     right = noise_r + sines_r + kick + click + 0.8 * hat
@@ -73,7 +82,7 @@ def make_track(index: int, seconds: float, rate: int, channels: int = 2) -> np.n
     return pcm
 
 
-def make_tracks_torch(first_index: int, n_tracks: int, seconds: float, rate: int, device):
+def make_tracks_torch(first_index: int, n_tracks: int, seconds: float, rate: int, device, hat_cfg=HAT_SPARSE):
     """(n_tracks, N, 2) int16 tensor on ``device`` built with torch ops (benchmark input
     only -- generating 10^2..10^3 three-minute tracks with numpy would take minutes)."""
     import torch
@@ -89,8 +98,8 @@ def make_tracks_torch(first_index: int, n_tracks: int, seconds: float, rate: int
     kick = _db(-3.0) * torch.exp(-beat / 0.040) * torch.sin(2 * np.pi * 60.0 * beat)
     click = torch.zeros(n, device=device)
     click[torch.arange(0, n, int(round(0.5 * rate)), device=device)] = _db(-3.0)
-    off = t - 0.25
-    hat_env = torch.where(off >= 0, torch.exp(-torch.remainder(off, 0.5) / 0.015), torch.zeros_like(off))
+    off = t - 0.5 * hat_cfg[0]
+    hat_env = torch.where(off >= 0, torch.exp(-torch.clamp_min(torch.remainder(off, hat_cfg[0]) - hat_cfg[3], 0.0) / hat_cfg[1]), torch.zeros_like(off))
     t64 = torch.arange(n, dtype=torch.float64, device=device) / rate
     sines_l = torch.zeros(n, device=device)
     sines_r = torch.zeros(n, device=device)
@@ -111,7 +120,7 @@ def make_tracks_torch(first_index: int, n_tracks: int, seconds: float, rate: int
         nl = nl * (_db(-20.0) / nl.square().mean().sqrt())
         nr = nr * (_db(-20.0) / nr.square().mean().sqrt())
         hat = torch.fft.irfft(torch.fft.rfft(torch.randn(n, generator=g, device=device)) * band, n)
-        hat = _db(-10.0) * hat / hat.abs().max().clamp_min(1e-12) * hat_env
+        hat = _db(hat_cfg[2]) * hat / hat.abs().max().clamp_min(1e-12) * hat_env
         left = nl + sines_l + kick + click + hat
         right = nr + sines_r + kick + click + 0.8 * hat
         peak = torch.maximum(left.abs().max(), right.abs().max())

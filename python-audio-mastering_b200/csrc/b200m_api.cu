@@ -55,7 +55,7 @@ struct b200m_handle {
     std::map<std::string, std::pair<double, int64_t>> prof_acc;
     int64_t launches = 0;
     // recurrence tiling (0 = automatic) and its verification counters
-    int recur_tile = 0, recur_warm = 8192, recur_rounds = 4;
+    int recur_tile = 0, recur_warm = 0, recur_rounds = -1;
     // time segmentation of k_chain / k_kweight: 0 = automatic, < 0 = off, > 0 = tiles per segment
     int seg_chain = 0, seg_kweight = 0;
     int chain_kernel = 0;            // 0 = automatic, 1 = k_chain (a CTA per segment), 2 = k_chainw (a warp per segment)
@@ -64,6 +64,7 @@ struct b200m_handle {
     // host-buffer pipeline: side streams for H2D / D2H and the events that order the groups
     bool pipeline = true;
     int pipe_groups = 8, pipe_streams = 1;      // groups per batch; compute streams the groups alternate over
+    double pipe_max_frames = 280e6;             // ... and the most frames a pipelined group takes (B200M_PIPE_MAX_FRAMES)
     cudaStream_t s_in = nullptr, s_out = nullptr, s_comp2 = nullptr;
     std::vector<cudaEvent_t> sync_events;
 };
@@ -725,6 +726,7 @@ extern "C" int b200m_create(int device, b200m_handle **out)
     h->device = device;
     if (const char *ck = std::getenv("B200M_CHAIN_KERNEL")) h->chain_kernel = std::max(0, std::min(2, std::atoi(ck)));   // test / experiment override
     if (const char *ck = std::getenv("B200M_CHAIN_SLUT")) h->chain_slut_ok = std::atoi(ck) != 0;
+    if (const char *ck = std::getenv("B200M_PIPE_MAX_FRAMES")) h->pipe_max_frames = std::max(8e6, std::atof(ck));
     e = allow_smem(k_chain<1, true>, chain_smem_bytes<1>());
     if (e == cudaSuccess) e = allow_smem(k_chain<2, true>, chain_smem_bytes<2>());
     if (e == cudaSuccess) e = allow_smem(k_chain<1, false>, chain_smem_bytes<1>());
@@ -841,8 +843,8 @@ extern "C" int b200m_set_recur_tiling(b200m_handle *h, int tile_frames, int warm
 {
     if (!h || tile_frames < 0 || warm_frames < 0 || rounds > 64) return B200M_ERR_INVALID;
     h->recur_tile = tile_frames;
-    h->recur_warm = warm_frames > 0 ? warm_frames : 8192;
-    h->recur_rounds = rounds < 0 ? 4 : rounds;
+    h->recur_warm = warm_frames > 0 ? warm_frames : 0;
+    h->recur_rounds = rounds < 0 ? -1 : rounds;
     return B200M_OK;
 }
 
@@ -949,7 +951,7 @@ static RecurParams recur_params(const b200m_handle *h, const Group &g, int nband
 {
     RecurParams P;
     P.nbands = nbands; P.band_base = band_base; P.n_streams = g.n_streams;
-    P.warm = std::max(32, (h->recur_warm + 31) & ~31);
+    P.warm = h->recur_warm > 0 ? std::max(32, (h->recur_warm + 31) & ~31) : 0;      // 0: automatic, per band (k_comp)
     if (h->recur_tile > 0) {
         P.tile_len = std::max(32, (h->recur_tile + 31) & ~31);
     } else {
@@ -958,17 +960,19 @@ static RecurParams recur_params(const b200m_handle *h, const Group &g, int nband
         // (`warm` active frames, level detector -> curve -> recurrence only), so long tiles waste less
         // work and short tiles give a small batch enough lanes.
         const double want_tiles = 148.0 * B200M_COMP_CTAS * 32 / std::max(1, g.n_streams);
-        const double len = std::min(65536.0, std::max(2048.0, g.max_stream_frames / want_tiles));
+        const double len = std::min(65536.0, std::max(4096.0, g.max_stream_frames / want_tiles));
         P.tile_len = ((int)len + 1023) & ~1023;
     }
     P.tiles = std::max(1, (g.max_stream_frames + P.tile_len - 1) / P.tile_len);
     return P;
 }
 
+constexpr int MAX_REPAIR_ROUNDS = 64;
 static size_t recur_spec_doubles(const b200m_handle *h, const Group &g, int nbands)
 {
     const RecurParams P = recur_params(h, g, nbands, 0);
-    return 4 * (size_t)g.n_streams * nbands * P.tiles;       // ss / se ping-pong
+    const size_t lanes = (size_t)g.n_streams * P.tiles;
+    return 4 * lanes * nbands /* ss / se ping-pong */ + (lanes + 1) / 2 /* dirty list (uint32) */ + MAX_REPAIR_ROUNDS / 2 + 2 /* one counter per round */;
 }
 
 // debug_att: the per-frame attenuation trajectory is materialised too (b200m_compress_dynamic_range's att_out)
@@ -1003,18 +1007,29 @@ static int launch_compressor(b200m_handle *h, const Group &g, const BandPtrs &bp
     P0.mode = 0;
     double *ss[2] = {d_spec, d_spec + 2 * slots}, *se[2] = {d_spec + slots, d_spec + 3 * slots};
     const unsigned gr = (unsigned)((lanes + 31) / 32);
-#define LAUNCH_COMP(NAME, PP, SSI, SEI, SSO, SEO) do { \
-        if (nbands == 3) { if (g.ch == 2) LAUNCH(NAME, k_comp<2, 3, false><<<gr, 96, recur_smem_bytes(3), h->stream>>>(g.d_streams, h->d_plans, PP, bp, d_proc, SSI, SEI, SSO, SEO, h->d_counters)); \
-                           else           LAUNCH(NAME, k_comp<1, 3, false><<<gr, 96, recur_smem_bytes(3), h->stream>>>(g.d_streams, h->d_plans, PP, bp, d_proc, SSI, SEI, SSO, SEO, h->d_counters)); } \
-        else             { if (g.ch == 2) LAUNCH(NAME, k_comp<2, 1, true><<<gr, 32, recur_smem_bytes(1), h->stream>>>(g.d_streams, h->d_plans, PP, bp, d_proc, SSI, SEI, SSO, SEO, h->d_counters)); \
-                           else           LAUNCH(NAME, k_comp<1, 1, true><<<gr, 32, recur_smem_bytes(1), h->stream>>>(g.d_streams, h->d_plans, PP, bp, d_proc, SSI, SEI, SSO, SEO, h->d_counters)); } } while (0)
-    LAUNCH_COMP("k_comp", P0, nullptr, nullptr, ss[0], se[0]);
+#define LAUNCH_COMP(NAME, PP, SSI, SEI, SSO, SEO, DL, DC) do { \
+        if (nbands == 3) { if (g.ch == 2) LAUNCH(NAME, k_comp<2, 3, false><<<gr, 96, recur_smem_bytes(3), h->stream>>>(g.d_streams, h->d_plans, PP, bp, d_proc, SSI, SEI, SSO, SEO, DL, DC)); \
+                           else           LAUNCH(NAME, k_comp<1, 3, false><<<gr, 96, recur_smem_bytes(3), h->stream>>>(g.d_streams, h->d_plans, PP, bp, d_proc, SSI, SEI, SSO, SEO, DL, DC)); } \
+        else             { if (g.ch == 2) LAUNCH(NAME, k_comp<2, 1, true><<<gr, 32, recur_smem_bytes(1), h->stream>>>(g.d_streams, h->d_plans, PP, bp, d_proc, SSI, SEI, SSO, SEO, DL, DC)); \
+                           else           LAUNCH(NAME, k_comp<1, 1, true><<<gr, 32, recur_smem_bytes(1), h->stream>>>(g.d_streams, h->d_plans, PP, bp, d_proc, SSI, SEI, SSO, SEO, DL, DC)); } } while (0)
+    unsigned *d_list = reinterpret_cast<unsigned *>(d_spec + 4 * slots);
+    unsigned *d_counts = d_list + ((lanes + 1) / 2) * 2;             // [MAX_REPAIR_ROUNDS]
+    LAUNCH_COMP("k_comp", P0, nullptr, nullptr, ss[0], se[0], nullptr, nullptr);
     int cur = 0;
-    if (P.tiles > 1) {
+    if (P.tiles > 1 && h->recur_rounds != 0) {
         RecurParams P1 = P;
         P1.mode = 1;
-        for (int round = 0; round < h->recur_rounds; ++round) {      // parallel repair rounds
-            LAUNCH_COMP("k_comp_repair", P1, ss[cur], se[cur], ss[cur ^ 1], se[cur ^ 1]);
+        // a stretch in which trajectories from different pasts stay apart (a slow release: up to ~2 release times)
+        // may span several short tiles, and a Jacobi round carries the truth one tile further: short tiles get more
+        // rounds (an empty round costs two empty launches)
+        const int auto_rounds = std::max(6, std::min(24, 2 + 40000 / std::max(1, P.tile_len)));
+        const int rounds = std::min(h->recur_rounds >= 0 ? h->recur_rounds : auto_rounds, MAX_REPAIR_ROUNDS);
+        CK(cudaMemsetAsync(d_counts, 0, MAX_REPAIR_ROUNDS * sizeof(unsigned), h->stream));
+        const unsigned gdirty = (unsigned)((lanes + 255) / 256);
+        for (int round = 0; round < rounds; ++round) {               // parallel repair rounds (Jacobi), dirty tiles only
+            if (nbands == 3) LAUNCH("k_comp_dirty", k_comp_dirty<3><<<gdirty, 256, 0, h->stream>>>(g.d_streams, h->d_plans, P1, ss[cur], se[cur], ss[cur ^ 1], se[cur ^ 1], d_list, d_counts + round, h->d_counters));
+            else             LAUNCH("k_comp_dirty", k_comp_dirty<1><<<gdirty, 256, 0, h->stream>>>(g.d_streams, h->d_plans, P1, ss[cur], se[cur], ss[cur ^ 1], se[cur ^ 1], d_list, d_counts + round, h->d_counters));
+            LAUNCH_COMP("k_comp_repair", P1, ss[cur], se[cur], ss[cur ^ 1], se[cur ^ 1], d_list, d_counts + round);
             cur ^= 1;
         }
     }
@@ -1432,7 +1447,15 @@ static int master_batch_impl(b200m_handle *h, const void *pcm_in, int in_on_devi
     // (and at least ~8 M frames) so that copies and kernels of neighbouring groups overlap
     const double per_frame = ch * 2 * (2 + std::max(1, n_targets)) + 4 + 3 * (ch * 2 + 2 + 0.26) + 2;
     const double slot_limit = (double)h->ws_limit / slots;
-    const double pipe_frames = pipelined ? std::max<double>(8e6, (double)total_frames / (double)h->pipe_groups) : 1e300;
+    // host buffers: ~1/8 of the batch per group, but no more than `pipe_max_frames` (about 32 three-minute tracks): the
+    // first group's H2D and the last group's D2H are not overlapped by anything, so on a large batch smaller groups win.
+    // device buffers: as few groups as the workspace limit allows, of equal size.
+    double pipe_frames = 1e300;
+    if (pipelined) pipe_frames = std::max<double>(8e6, std::min<double>((double)total_frames / (double)h->pipe_groups, h->pipe_max_frames));
+    else {
+        const double ngroups = std::ceil(per_frame * (double)total_frames / slot_limit);
+        if (ngroups > 1) pipe_frames = (double)total_frames / ngroups * 1.02 + 1;
+    }
     std::vector<GroupPlan> gps;
     {
         int t0 = 0;

@@ -923,6 +923,9 @@ k_detect(const StreamDesc *__restrict__ streams, const PlanDev *__restrict__ pla
 // samples in (plus warm-up re-reads of the RMS), 4 B out, 0.75 B of block-end states -- the fp64
 // attenuation rows (24 B written + 24 B read per frame when k_apply was a kernel of its own) never exist.
 // =====================================================================================
+#ifndef B200M_WARM_RELEASES
+#define B200M_WARM_RELEASES 1.75
+#endif
 #ifndef B200M_COMP_UNROLL
 #define B200M_COMP_UNROLL 2         // 128-bit sample words (4 stereo frames each) per iteration of the lane-serial walk
 #endif
@@ -1078,15 +1081,23 @@ template <int CH, int NB, bool DBG>
 __global__ void __launch_bounds__(32 * NB)
 k_comp(const StreamDesc *__restrict__ streams, const PlanDev *__restrict__ plans, RecurParams P, BandPtrs bp,
        int16_t *__restrict__ proc, const double *__restrict__ ss_in, const double *__restrict__ se_in,
-       double *__restrict__ ss_out, double *__restrict__ se_out, unsigned long long *__restrict__ counters)
+       double *__restrict__ ss_out, double *__restrict__ se_out,
+       const unsigned *__restrict__ dirty_list, const unsigned *__restrict__ dirty_count)
 {
     extern __shared__ __align__(16) unsigned char recur_smem[];
     const int wid = NB == 1 ? 0 : (int)(threadIdx.x >> 5), lane = threadIdx.x & 31;
+    // mode 1 (repair round): the lanes take the (stream, tile) pairs k_comp_dirty listed, densely packed
+    unsigned n_dirty = 0u;
+    if (P.mode == 1) {
+        n_dirty = *dirty_count;
+        if (blockIdx.x * 32u >= n_dirty) return;                         // CTA-uniform
+    }
     RecurWarpSmem *WS = reinterpret_cast<RecurWarpSmem *>(recur_smem);
     RecurWarpSmem &W = WS[wid];
     unsigned char (*s_same)[32] = reinterpret_cast<unsigned char (*)[32]>(recur_smem + NB * sizeof(RecurWarpSmem));   // [NB][32]
     const int band = NB == 3 ? wid : P.band_base;
-    const int gl = blockIdx.x * 32 + lane;
+    const unsigned li = blockIdx.x * 32u + lane;
+    const int gl = P.mode == 1 ? (li < n_dirty ? (int)dirty_list[li] : P.n_streams * P.tiles) : (int)li;
     const int s = gl / P.tiles, tile = gl % P.tiles;
     bool live = s < P.n_streams;
     int start = 0, end = 0;
@@ -1117,22 +1128,10 @@ k_comp(const StreamDesc *__restrict__ streams, const PlanDev *__restrict__ plans
     const size_t slot = slot0 + (size_t)(NB == 3 ? wid : 0) * P.tiles;
     double a_in = 0.0;
     if (P.mode == 1 && live) {
-        // repair round: is ANY band's assumed start state not its predecessor's current end state?  (Every warp of
-        // the CTA looks at all bands and so reaches the same verdict.)
-        bool dirty = false;
-#pragma unroll
-        for (int b = 0; b < NB; ++b) {
-            const size_t sl = slot0 + (size_t)b * P.tiles;
-            const double prev = tile == 0 ? 0.0 : se_in[sl - 1];
-            dirty = dirty || (tile != 0 && __double_as_longlong(ss_in[sl]) != __double_as_longlong(prev));
-        }
-        if (!dirty) {
-            ss_out[slot] = ss_in[slot]; se_out[slot] = se_in[slot];     // consistent: nothing to do
-            live = false;
-        } else {
-            a = tile == 0 ? 0.0 : se_in[slot - 1];    // a band that was consistent reproduces its stored trajectory
-            if (wid == 0) atomicAdd(&counters[2], 1ull);
-        }
+        // repair round: some band's assumed start state was not its predecessor's current end state (k_comp_dirty).
+        // Every band of the tile is re-run from its predecessor's end; one that was consistent reproduces its
+        // stored trajectory.
+        a = tile == 0 ? 0.0 : se_in[slot - 1];
         a_in = a;
     }
     // warp-uniform: this band passed the plan-time checks in every plan of the warp (exact constant division, curve
@@ -1244,7 +1243,14 @@ k_comp(const StreamDesc *__restrict__ streams, const PlanDev *__restrict__ plans
     if (P.mode == 0) {
         int cb = sb;
         if (live) {
-            int need = P.warm >> 5, wb = sb;
+            // automatic: 16384 ACTIVE frames or 1.75 release times, whichever is more.  Two trajectories from different
+            // pasts stay apart while the higher one is still releasing towards the static curve (about one release time
+            // after a transient, longer when the curve value is small).  A tile that starts from a wrong guess costs a
+            // repair pass whose length is that of its slowest lane -- up to a whole tile -- so a longer warm-up for
+            // every lane is the cheaper side: on the benchmark programme (kicks every 0.5 s) 8192 frames leave 36 % of
+            // the tiles dirty (main pass 7.8 ms + repairs 7.6 ms per 64 tracks), 16384 leave 2 % (8.8 + 0.9 ms).
+            const int warm_frames = P.warm > 0 ? P.warm : max(16384, (int)(B200M_WARM_RELEASES * R));
+            int need = (warm_frames + 31) >> 5, wb = sb;
             while (wb > 0 && need > 0) {
                 const int w = (wb - 1) >> 5, lo = w << 5, nbits = wb - lo;
                 const unsigned mask = nbits == 32 ? 0xffffffffu : ((1u << nbits) - 1u);
@@ -1452,6 +1458,40 @@ k_comp(const StreamDesc *__restrict__ streams, const PlanDev *__restrict__ plans
         } else {
             ss_out[slot] = a_in;
             se_out[slot] = merged ? se_in[slot] : a;
+        }
+    }
+}
+
+// k_comp_dirty: ahead of a repair round, one thread per (stream, tile): a tile in which every band's assumed start
+// state is its predecessor's current end state (bit for bit) is carried over to the round's output unchanged; the
+// others are appended to `list` (any order), so that k_comp's repair pass runs on dense warps of dirty tiles and a
+// round with nothing to repair costs two empty launches.
+template <int NB>
+__global__ void __launch_bounds__(256)
+k_comp_dirty(const StreamDesc *__restrict__ streams, const PlanDev *__restrict__ plans, RecurParams P,
+             const double *__restrict__ ss_in, const double *__restrict__ se_in, double *__restrict__ ss_out, double *__restrict__ se_out,
+             unsigned *__restrict__ list, unsigned *__restrict__ count, unsigned long long *__restrict__ counters)
+{
+    const int gl = blockIdx.x * blockDim.x + threadIdx.x;
+    if (gl >= P.n_streams * P.tiles) return;
+    const int s = gl / P.tiles, tile = gl % P.tiles;
+    const StreamDesc sd = streams[s];
+    if (!plans[sd.plan].multiband || tile * P.tile_len >= sd.out_frames) return;
+    const size_t slot0 = ((size_t)s * NB) * P.tiles + tile;
+    bool dirty = false;
+#pragma unroll
+    for (int b = 0; b < NB; ++b) {
+        const size_t sl = slot0 + (size_t)b * P.tiles;
+        dirty = dirty || (tile != 0 && __double_as_longlong(ss_in[sl]) != __double_as_longlong(se_in[sl - 1]));
+    }
+    if (dirty) {
+        list[atomicAdd(count, 1u)] = (unsigned)gl;
+        atomicAdd(&counters[2], 1ull);
+    } else {
+#pragma unroll
+        for (int b = 0; b < NB; ++b) {
+            const size_t sl = slot0 + (size_t)b * P.tiles;
+            ss_out[sl] = ss_in[sl]; se_out[sl] = se_in[sl];
         }
     }
 }

@@ -14,7 +14,8 @@ if os.environ.get("WARM") or os.environ.get("TILE"):
     eng.set_recur_tiling(int(os.environ.get("TILE", 0)), int(os.environ.get("WARM", 0)), int(os.environ.get("ROUNDS", -1)))
 st = dict(bass_boost=4.0, mid_cut=3.0, presence_boost=1.0, treble_boost=3.0, saturation=sat, width=1.2, multiband=True, lufs=-14.0)
 t0 = time.time()
-d_in = synth.make_tracks_torch(0, ntracks, seconds, rate, "cuda")
+hat = synth.HAT_DENSE if os.environ.get("HAT", "dense") == "dense" else synth.HAT_SPARSE
+d_in = torch.cat([synth.make_tracks_torch(k, min(32, ntracks - k), seconds, rate, "cuda", hat_cfg=hat) for k in range(0, ntracks, 32)])
 torch.cuda.synchronize(); print("synth", time.time() - t0)
 n = d_in.shape[1]
 d_out = torch.empty_like(d_in)
