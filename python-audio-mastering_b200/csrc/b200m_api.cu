@@ -59,6 +59,7 @@ struct b200m_handle {
     // time segmentation of k_chain / k_kweight: 0 = automatic, < 0 = off, > 0 = tiles per segment
     int seg_chain = 0, seg_kweight = 0;
     int chain_kernel = 0;            // 0 = automatic, 1 = k_chain (a CTA per segment), 2 = k_chainw (a warp per segment)
+    int detect_kernel = 0;           // 0 = automatic (k_detectw where the look-back fits its ring), 1 = k_detect always (B200M_DETECT_KERNEL: experiments, tests)
     bool chain_slut_ok = true;       // k_chainw may take its 16-warp shape (B200M_CHAIN_SLUT=0 switches it off: experiments)
     unsigned long long *d_counters = nullptr;
     // host-buffer pipeline: side streams for H2D / D2H and the events that order the groups
@@ -726,6 +727,7 @@ extern "C" int b200m_create(int device, b200m_handle **out)
     h->device = device;
     if (const char *ck = std::getenv("B200M_CHAIN_KERNEL")) h->chain_kernel = std::max(0, std::min(2, std::atoi(ck)));   // test / experiment override
     if (const char *ck = std::getenv("B200M_CHAIN_SLUT")) h->chain_slut_ok = std::atoi(ck) != 0;
+    if (const char *ck = std::getenv("B200M_DETECT_KERNEL")) h->detect_kernel = std::atoi(ck);
     if (const char *ck = std::getenv("B200M_PIPE_MAX_FRAMES")) h->pipe_max_frames = std::max(8e6, std::atof(ck));
     e = allow_smem(k_chain<1, true>, chain_smem_bytes<1>());
     if (e == cudaSuccess) e = allow_smem(k_chain<2, true>, chain_smem_bytes<2>());
@@ -996,10 +998,16 @@ static int launch_compressor(b200m_handle *h, const Group &g, const BandPtrs &bp
 {
     if (!((nbands == 3 && band_base == 0) || nbands == 1))
         return fail(h, B200M_ERR_INVALID, "internal: compressor runs on one band or on all three");
-    const dim3 gd((g.max_stream_frames + DT - 1) / DT, g.n_streams, nbands);
-    const size_t smem = detect_smem_bytes(g.max_look);
-    if (g.ch == 2) LAUNCH("k_detect", k_detect<2><<<gd, DNT, smem, h->stream>>>(g.d_streams, h->d_plans, bp, band_base));
-    else           LAUNCH("k_detect", k_detect<1><<<gd, DNT, smem, h->stream>>>(g.d_streams, h->d_plans, bp, band_base));
+    if (g.max_look <= DW_MAX_LOOK && h->detect_kernel != 1) {
+        const dim3 gw((g.max_stream_frames + DW_SPAN * DW_WARPS - 1) / (DW_SPAN * DW_WARPS), g.n_streams, nbands);
+        if (g.ch == 2) LAUNCH("k_detect", k_detectw<2><<<gw, 32 * DW_WARPS, 0, h->stream>>>(g.d_streams, h->d_plans, bp, band_base));
+        else           LAUNCH("k_detect", k_detectw<1><<<gw, 32 * DW_WARPS, 0, h->stream>>>(g.d_streams, h->d_plans, bp, band_base));
+    } else {
+        const dim3 gd((g.max_stream_frames + DT - 1) / DT, g.n_streams, nbands);
+        const size_t smem = detect_smem_bytes(g.max_look);
+        if (g.ch == 2) LAUNCH("k_detect", k_detect<2><<<gd, DNT, smem, h->stream>>>(g.d_streams, h->d_plans, bp, band_base));
+        else           LAUNCH("k_detect", k_detect<1><<<gd, DNT, smem, h->stream>>>(g.d_streams, h->d_plans, bp, band_base));
+    }
     const RecurParams P = recur_params(h, g, nbands, band_base);
     const size_t lanes = (size_t)g.n_streams * P.tiles;              // one lane per (stream, tile), all bands
     const size_t slots = lanes * nbands;

@@ -888,6 +888,151 @@ k_detect(const StreamDesc *__restrict__ streams, const PlanDev *__restrict__ pla
 }
 
 // =====================================================================================
+// k_detectw: the same window RMS (audioop.rms over [i-look, i) of both channels) with every WARP walking a
+// contiguous span of one (stream, band) in steps of 256 frames, eight per lane.  The window sum slides:
+// S(i+1) = S(i) + e(i) - e(i-look), so a step needs only the LOCAL prefix of d = e_lead - e_trail (eight adds per
+// lane and one 64-bit warp scan) on top of the sum carried from the step before -- no far reads of prefix sums,
+// no CTA barriers; the trail energies are the lead energies of `look` frames ago, kept in a per-warp ring in shared
+// memory.  ~35 instructions per frame and band against k_detect's 82 (whose CTA-wide prefix scan moves 40 bytes of
+// shared memory per frame); k_detect stays for look-backs beyond the ring (sample rates above ~170 kHz).
+// grid = (spans / DW_WARPS, streams, bands).
+// =====================================================================================
+constexpr int DW_WARPS = 4;         // warps per CTA
+constexpr int DW_STEP = 256;        // frames per warp step (eight per lane)
+constexpr int DW_SPAN = 8192;       // frames per warp: a multiple of 1024 (whole hold words)
+constexpr int DW_RING = 2048;       // frame energies kept per warp: look + DW_STEP must fit
+constexpr int DW_MAX_LOOK = DW_RING - DW_STEP;
+
+template <int CH>
+__global__ void __launch_bounds__(32 * DW_WARPS)
+k_detectw(const StreamDesc *__restrict__ streams, const PlanDev *__restrict__ plans, BandPtrs bp, int band_base)
+{
+    __shared__ __align__(16) unsigned ring_all[DW_WARPS][DW_RING];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const StreamDesc sd = streams[blockIdx.y];
+    const PlanDev *__restrict__ pl = plans + sd.plan;
+    const int band = band_base + blockIdx.z;
+    const int t0 = (blockIdx.x * DW_WARPS + warp) * DW_SPAN;
+    if (!pl->multiband || t0 >= sd.out_frames) return;             // warps never synchronise with each other
+    const int t1 = min(t0 + DW_SPAN, sd.out_frames);
+    const int H = pl->band[band].look, hold_max = pl->band[band].hold_max;
+    const unsigned nH = (unsigned)CH * (unsigned)H;
+    float rnH = 0.0f;
+    if (nH) asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rnH) : "f"((float)nH));
+    const int16_t *__restrict__ src = bp.band[band] + sd.out_off * CH;
+    uint16_t *__restrict__ dst = bp.rms[band] + sd.out_off;
+    uint32_t *__restrict__ hold = bp.hold[band] + sd.blk_off;
+    unsigned *ring = ring_all[warp];
+    for (int i = lane; i < DW_RING / 4; i += 32) reinterpret_cast<uint4 *>(ring)[i] = make_uint4(0u, 0u, 0u, 0u);
+    __syncwarp();
+    // 16-byte accesses where the stream's buffers allow them (chunk starts at odd rates may not be aligned)
+    const bool src16 = (reinterpret_cast<unsigned long long>(src) & 15ull) == 0;
+    const bool dst16 = (reinterpret_cast<unsigned long long>(dst) & 15ull) == 0;
+    const bool h4 = (H & 3) == 0;                                   // the trail group of a lane is then two aligned 16-byte ring spans
+    // The walk starts `look` frames (rounded up to whole steps) ahead of the span with S = 0 and an empty ring: frames
+    // the ring has not seen read as zero energy, so by frame t0 the sum is exactly that of [t0 - look, t0).
+    long long S_base = 0;
+    unsigned hword = 0xffffffffu;                                   // hold bits of the current 1024-frame word (blocks past the end count as held)
+    const int i_start = t0 == 0 ? 0 : t0 - ((H + DW_STEP - 1) / DW_STEP) * DW_STEP;
+    for (int i0 = i_start; i0 < t1; i0 += DW_STEP) {
+        const int f = i0 + 8 * lane;
+        // ---- lead: this lane's eight frames -> energies -> ring --------------------------------------------------
+        unsigned el[8];
+        {
+            unsigned w[8];                                          // stereo: one packed frame per word; mono: two frames per word (four words)
+            const bool inside = f >= 0 && f + 8 <= sd.out_frames;
+            if (inside && src16) {
+                if (CH == 2) {
+                    const uint4 a = __ldg(reinterpret_cast<const uint4 *>(src + (int64_t)f * 2)), b = __ldg(reinterpret_cast<const uint4 *>(src + (int64_t)f * 2) + 1);
+                    w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w; w[4] = b.x; w[5] = b.y; w[6] = b.z; w[7] = b.w;
+                } else {
+                    const uint4 a = __ldg(reinterpret_cast<const uint4 *>(src + f));
+                    w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w;
+                }
+            } else {
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const bool ok = f + k >= 0 && f + k < sd.out_frames;
+                    if (CH == 2) w[k] = ok ? *reinterpret_cast<const unsigned *>(src + (int64_t)(f + k) * 2) : 0u;
+                    else {
+                        const unsigned v = ok ? (unsigned)(unsigned short)src[f + k] : 0u;
+                        if (k & 1) w[k >> 1] |= v << 16; else w[k >> 1] = v;
+                    }
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                if (CH == 2) {
+                    const int l = prmt_sx(w[k], 0x9910u), r = prmt_sx(w[k], 0xbb32u);
+                    el[k] = (unsigned)(l * l) + (unsigned)(r * r);
+                } else {
+                    const int v = prmt_sx(w[k >> 1], (k & 1) ? 0xbb32u : 0x9910u);
+                    el[k] = (unsigned)(v * v);
+                }
+            }
+            uint4 *rp = reinterpret_cast<uint4 *>(ring + (f & (DW_RING - 1)));     // f is a multiple of 8: one aligned span, no wrap
+            rp[0] = make_uint4(el[0], el[1], el[2], el[3]);
+            rp[1] = make_uint4(el[4], el[5], el[6], el[7]);
+        }
+        __syncwarp();
+        // ---- trail: the energies of `look` frames ago, from the ring ------------------------------------------------
+        unsigned et[8];
+        if (h4) {
+            const uint4 a = *reinterpret_cast<const uint4 *>(ring + ((f - H) & (DW_RING - 1)));
+            const uint4 b = *reinterpret_cast<const uint4 *>(ring + ((f - H + 4) & (DW_RING - 1)));
+            et[0] = a.x; et[1] = a.y; et[2] = a.z; et[3] = a.w; et[4] = b.x; et[5] = b.y; et[6] = b.z; et[7] = b.w;
+        } else {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) et[k] = ring[(f - H + k) & (DW_RING - 1)];
+        }
+        __syncwarp();                                               // the next step's lead writes may land on this step's trail slots
+        // ---- window sums: S(f + k) = S_base + (exclusive prefix of d over the step) ------------------------------
+        long long p[8];
+        long long run = 0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { p[k] = run; run += (long long)el[k] - (long long)et[k]; }
+        long long inc = run;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const long long t = __shfl_up_sync(FULL, inc, d);
+            if (lane >= d) inc += t;
+        }
+        const long long mine = S_base + (inc - run);
+        S_base += __shfl_sync(FULL, inc, 31);
+        if (i0 < t0) continue;                                      // warm-up of the sum: nothing to emit (warp-uniform)
+        // ---- integer RMS, stores, hold bits ---------------------------------------------------------------------
+        unsigned r[8];
+        bool act = false;
+        if (i0 >= H) {                                              // the whole look-back lies inside the stream: n = CH * look (warp-uniform)
+#pragma unroll
+            for (int k = 0; k < 8; ++k) r[k] = nH ? window_rms_rn((unsigned long long)(mine + p[k]), nH, rnH) : 0u;
+        } else {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) r[k] = f + k >= H ? (nH ? window_rms_rn((unsigned long long)(mine + p[k]), nH, rnH) : 0u)
+                                                          : window_rms((unsigned long long)(mine + p[k]), (unsigned)CH * (unsigned)(f + k));
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) act = act || (f + k < sd.out_frames && (int)r[k] > hold_max);
+        if (dst16 && f + 8 <= sd.out_frames) {
+            *reinterpret_cast<uint4 *>(dst + f) = make_uint4(r[0] | (r[1] << 16), r[2] | (r[3] << 16), r[4] | (r[5] << 16), r[6] | (r[7] << 16));
+        } else {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) if (f + k < sd.out_frames) dst[f + k] = (uint16_t)r[k];
+        }
+        // a 32-frame block = four lanes; the step's eight blocks are bits (i0 / 32) % 32 .. + 7 of hold word i0 / 1024
+        const unsigned bal = __ballot_sync(FULL, act);
+        unsigned busy = 0u;
+#pragma unroll
+        for (int b = 0; b < 8; ++b) busy |= ((bal >> (4 * b)) & 0xfu) ? (1u << b) : 0u;
+        hword &= ~(busy << ((i0 >> 5) & 31));
+        if (((i0 + DW_STEP) & 1023) == 0 || i0 + DW_STEP >= t1) {
+            if (lane == 0) hold[i0 >> 10] = hword;
+            hword = 0xffffffffu;
+        }
+    }
+}
+
+// =====================================================================================
 // k_comp / k_comp_fix: pydub compress_dynamic_range after the level detector (ENG:207-209 run per
 // chunk, state reset to 0 at every chunk) for ALL bands of a stream, fused with the gain
 // application and the overlay (ENG:210): static curve, attenuation recurrence, 10^(-att/20),
