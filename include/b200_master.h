@@ -165,7 +165,9 @@ int b200m_plan_from_settings(const b200m_settings *s, int sample_rate, int chann
 /* ---- whole path: replaces the chunk loop + loudness + limiter, ENG:46-89 ---------
  * Masters n_tracks independent tracks in one batch.  All tracks share the sample
  * rate / channel count of their plans.
- *   pcm_in        interleaved PCM of all tracks (format `fmt`), device or host
+ *   pcm_in        interleaved PCM of all tracks (format `fmt`), device or host.  B200M_FMT_S16 is the reference's
+ *                 domain; B200M_FMT_S24 / B200M_FMT_F32 are staged to it first exactly like b200m_stage_pcm
+ *                 (declared extension: ENG:125 handles 16-bit PCM only; the output stays int16)
  *   in_offsets    [n_tracks] first frame of each track inside pcm_in          (host)
  *   in_frames     [n_tracks] frames available for each track                  (host)
  *   out_frames    [n_tracks] frames to produce (pydub's ms framing, ENG:51-54: may be

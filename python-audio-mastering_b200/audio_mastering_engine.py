@@ -59,6 +59,18 @@ def _segment_pcm(seg) -> np.ndarray:
     return pcm.reshape(-1, 2) if seg.channels == 2 else pcm
 
 
+def _job_error(seg, settings):
+    """Why the reference could not master this file (None: it can).  The reference handles one file per call, so a
+    bad file fails alone; a batch checks every file up front and masters the rest."""
+    try:
+        _segment_pcm(seg)
+    except ValueError as e:
+        return str(e)
+    if (settings or {}).get("lufs") is not None and seg.frame_count() < 0.4 * seg.frame_rate:
+        return "Audio must have length greater than the block size."       # pyloudnorm valid_audio (ENG:218)
+    return None
+
+
 def master_segment(seg, settings, device: int = 0):
     """ENG:46-89 on one decoded segment: chunk loop, loudness, limiter -> new segment."""
     outs, infos = get_engine(device).master([_segment_pcm(seg)], seg.frame_rate, settings)
@@ -122,9 +134,11 @@ def process_audio_batch_from_gcs(jobs):
             src.seek(0)
             decoded.append((bucket, blob_name, segment_class().from_file(src)))
         print(f"Decoded {len(decoded)} object(s); mastering on the GPU ...")
+        failed = {i: msg for i, (_b, _n, seg) in enumerate(decoded) if (msg := _job_error(seg, jobs[i][1])) is not None}
         groups = {}
         for i, (_b, _n, seg) in enumerate(decoded):
-            groups.setdefault((seg.frame_rate, seg.channels), []).append(i)
+            if i not in failed:
+                groups.setdefault((seg.frame_rate, seg.channels), []).append(i)
         images = [None] * len(jobs)
         for (rate, _ch), idx in groups.items():
             res, infos = get_engine().master_wav([_segment_pcm(decoded[i][2]) for i in idx], rate, [jobs[i][1] for i in idx])
@@ -134,11 +148,15 @@ def process_audio_batch_from_gcs(jobs):
                     print(f"{decoded[i][1]}: measured {info['loudness']:.2f} LUFS; applied "
                           f"{jobs[i][1].get('lufs') - info['loudness']:.2f} dB of gain.")
         for (bucket, blob_name, _seg), img in zip(decoded, images):
+            if img is None:
+                continue                                     # a job that failed on its own (reported below), like ENG:110-113 for that job
             target = f"processed/mastered_{os.path.basename(blob_name)}"
             print(f"Uploading {target} ...")
             bucket.blob(target).upload_from_file(io.BytesIO(img.tobytes()), content_type="audio/wav")
             bucket.blob(f"{target}.complete").upload_from_string("")
             print(f"Done: {target}.complete written.")
+        if failed:
+            raise ValueError("; ".join(f"{decoded[i][1]}: {msg}" for i, msg in sorted(failed.items())))
     except Exception as e:
         print(f"FATAL ERROR in mastering engine: {e}")
         raise
@@ -181,8 +199,16 @@ def batch_process_audio(settings, input_folder, output_folder, status_callback=N
         say(f"Loading {len(names)} files...")
         cls = segment_class()
         segs = [cls.from_file(os.path.join(input_folder, n)) for n in names]
+        bad = [(n, msg) for n, sg in zip(names, segs) if (msg := _job_error(sg, settings)) is not None]
+        for n, msg in bad:                                   # the reference would have failed on this file alone
+            say(f"Error: {n}: {msg}")
+        keep = [i for i, n in enumerate(names) if n not in {b for b, _ in bad}]
+        total = len(names)
+        names, segs = [names[i] for i in keep], [segs[i] for i in keep]
         say(f"Mastering {len(segs)} files on the GPU...")
-        if all(n.lower().endswith(".wav") for n in names):
+        if not segs:
+            pass
+        elif all(n.lower().endswith(".wav") for n in names):
             # WAV in, WAV out: the GPU returns complete file images
             for n, img in zip(names, master_segments_wav(segs, settings)):
                 with open(os.path.join(output_folder, f"mastered_{n}"), "wb") as f:
@@ -191,7 +217,7 @@ def batch_process_audio(settings, input_folder, output_folder, status_callback=N
             outs = master_segments(segs, settings)
             for n, seg in zip(names, outs):
                 _export(seg, os.path.join(output_folder, f"mastered_{n}"))
-        say(f"Batch processing complete: {len(names)} files.")
+        say(f"Batch processing complete: {len(names)} of {total} files.")
     except Exception as e:
         say(f"Error: {e}")
 

@@ -100,11 +100,13 @@ class Engine:
 
     # -- the whole path ------------------------------------------------------------------
     def master_raw(self, pcm_in, in_on_device, in_offsets, in_frames, out_frames, plans, plan_index,
-                   pcm_out, out_on_device, want_loudness=True, targets=None):
+                   pcm_out, out_on_device, want_loudness=True, targets=None, fmt=L.FMT_S16):
         """Thin wrapper over ``b200m_master_batch`` (``b200m_master_batch_targets`` when ``targets`` is
         given: pcm_out then holds ``len(targets)`` copies of the batch output, target-major, and the
         returned gains have shape (len(targets), n)).  pcm_in / pcm_out: numpy int16 arrays or torch
-        tensors; offsets / frames / plan_index: sequences."""
+        tensors; offsets / frames / plan_index: sequences.  ``fmt``: format of pcm_in (``lib.FMT_S16``; packed
+        s24 and float32 are staged to the reference's 16-bit domain first, see ``b200m_stage_pcm``); the
+        output is always int16 (ENG:125)."""
         n = len(in_frames)
         off = np.ascontiguousarray(in_offsets, dtype=np.int64)
         inf = np.ascontiguousarray(in_frames, dtype=np.int64)
@@ -116,7 +118,7 @@ class Engine:
             tg = np.ascontiguousarray(targets, dtype=np.float64)
             gain = np.empty((len(tg), n), dtype=np.float64) if want_loudness else None
             self._ck(self._lib.b200m_master_batch_targets(
-                self._h, C.c_void_p(_ptr(pcm_in)), int(in_on_device), L.FMT_S16, n,
+                self._h, C.c_void_p(_ptr(pcm_in)), int(in_on_device), int(fmt), n,
                 C.c_void_p(off.ctypes.data), C.c_void_p(inf.ctypes.data), C.c_void_p(outf.ctypes.data),
                 parr, len(plans), C.c_void_p(pidx.ctypes.data), C.c_void_p(tg.ctypes.data), len(tg),
                 C.c_void_p(_ptr(pcm_out)), int(out_on_device),
@@ -125,7 +127,7 @@ class Engine:
             return loud, gain
         gain = np.empty(n, dtype=np.float64) if want_loudness else None
         self._ck(self._lib.b200m_master_batch(
-            self._h, C.c_void_p(_ptr(pcm_in)), int(in_on_device), L.FMT_S16, n,
+            self._h, C.c_void_p(_ptr(pcm_in)), int(in_on_device), int(fmt), n,
             C.c_void_p(off.ctypes.data), C.c_void_p(inf.ctypes.data), C.c_void_p(outf.ctypes.data),
             parr, len(plans), C.c_void_p(pidx.ctypes.data),
             C.c_void_p(_ptr(pcm_out)), int(out_on_device),
@@ -194,6 +196,10 @@ class Engine:
             offs.append(start // fw)
             pos = start + f * fw
         buf = np.zeros(pos, dtype=np.uint8)
+        if sum(out_frames) == 0:                               # nothing for the GPU to do: header-only files (what export() writes for empty audio)
+            for o in offs:
+                buf[o * fw - 44:o * fw] = np.frombuffer(self.wav_header(rate, ch, 0), dtype=np.uint8)
+            return [buf[o * fw - 44:o * fw] for o in offs], [{"loudness": None, "gain": None} for _ in tracks]
         flat = np.ascontiguousarray(np.concatenate([np.ascontiguousarray(t, dtype=np.int16).reshape(-1) for t in tracks]))
         off = np.ascontiguousarray(np.concatenate([[0], np.cumsum(in_frames)[:-1]]), dtype=np.int64)
         inf = np.ascontiguousarray(in_frames, dtype=np.int64)

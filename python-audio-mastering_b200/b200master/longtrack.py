@@ -48,14 +48,19 @@ def partition(track_frames: int, rate: int, world: int) -> List[Slice]:
     """Contiguous, chunk-aligned time ranges, as even as the 30-s chunk grid allows.  Ranks
     beyond the number of chunks get an empty slice."""
     out_total = ms_framing(track_frames, rate)
-    chunk = int(CHUNK_MS * (rate / 1000.0))                  # exact for the usual rates (SURVEY D.4)
-    n_chunks = (out_total + chunk - 1) // chunk if out_total > 0 else 0
+
+    def chunk_start(k):                                      # pydub's own ms -> frame conversion (ENG:48-54), chunk by chunk
+        return int((CHUNK_MS * k) * (rate / 1000.0))
+
+    n_chunks = 0
+    while chunk_start(n_chunks) < out_total:
+        n_chunks += 1
     base, rem = divmod(n_chunks, world)
     slices, c = [], 0
     for r in range(world):
         n = base + (1 if r < rem else 0)
         c0, c1 = c, c + n
-        a, b = min(c0 * chunk, out_total), min(c1 * chunk, out_total)
+        a, b = min(chunk_start(c0), out_total), min(chunk_start(c1), out_total)
         slices.append(Slice(r, c0, c1, a, max(0, min(b, track_frames) - a) if b > a else 0, b - a))
         c = c1
     return slices

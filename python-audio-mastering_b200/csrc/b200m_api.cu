@@ -65,7 +65,7 @@ struct b200m_handle {
     // host-buffer pipeline: side streams for H2D / D2H and the events that order the groups
     bool pipeline = true;
     int pipe_groups = 8, pipe_streams = 1;      // groups per batch; compute streams the groups alternate over
-    double pipe_max_frames = 280e6;             // ... and the most frames a pipelined group takes (B200M_PIPE_MAX_FRAMES)
+    double pipe_max_frames = 140e6;             // ... and the most frames a pipelined group takes (B200M_PIPE_MAX_FRAMES)
     cudaStream_t s_in = nullptr, s_out = nullptr, s_comp2 = nullptr;
     std::vector<cudaEvent_t> sync_events;
 };
@@ -1119,6 +1119,7 @@ struct GroupPlan {
     std::vector<int32_t> cta_iters;  // k_chainw's 16-warp shape: tiles every warp of CTA i walks
     int64_t F = 0, Fp = 0, in_total = 0, zoff = 0, out_base = 0;      // F: workspace frames (aligned track starts), Fp: packed output frames
     size_t desc_bytes = 0, res_off = 0, pin_bytes = 0, need = 0;
+    int fmt = B200M_FMT_S16;         // PCM format of the caller's input (s24 / f32: staged to the 16-bit domain first, declared extension)
     int n_targets = 0;               // > 0: loudness sweep (b200m_master_batch_targets): that many outputs per track
     bool wav = false;                // b200m_master_batch_wav: a 44-byte RIFF header ahead of every track's samples
 };
@@ -1126,16 +1127,24 @@ struct GroupPlan {
 static void plan_group(const b200m_handle *h, GroupPlan &gp, bool in_dev, bool out_dev, int t_begin, int t_end,
                        const int64_t *in_offsets, const int64_t *in_frames, const int64_t *out_frames,
                        const b200m_plan *plans, const int32_t *plan_index, int64_t out_base, int n_targets = 0,
-                       const int64_t *out_offsets = nullptr)
+                       const int64_t *out_offsets = nullptr, int fmt = B200M_FMT_S16)
 {
     gp.n_targets = n_targets;
+    gp.fmt = fmt;
+    const bool packed_in = !in_dev || fmt != B200M_FMT_S16;      // the kernels read a packed copy of the group's tracks (H2D staging or format staging)
+    const int bps = fmt == B200M_FMT_S16 ? 2 : fmt == B200M_FMT_S24 ? 3 : 4;
     gp.wav = out_offsets != nullptr;
     // WAV images: the group's span of the output starts at the header of its first track
     const int64_t hdr = out_offsets ? 44 / (plans[0].channels * 2) : 0;
     if (out_offsets) out_base = out_offsets[t_begin] - hdr;
     const size_t outs = (size_t)std::max(1, n_targets);
     const int ch = plans[0].channels, rate = plans[0].sample_rate;
-    const int64_t chunk = 30LL * rate;          // ENG:48: 30 000 ms -> int(ms * rate / 1000) frames
+    // ENG:48-54 `audio[start_ms:start_ms + 30000]`: pydub turns a millisecond position into a frame index as
+    // int(ms * (rate / 1000.0)) -- for about one integer rate in seven (11 024, 18 900, 37 800 ... Hz) the product for some
+    // chunk k lands one frame short of 30 * rate * k, and filters and compressors restart there, so chunk k starts at
+    // the frame pydub computes, operation for operation (all the usual rates are exact either way).
+    const double frames_per_ms = (double)rate / 1000.0;
+    auto chunk_start = [&](int64_t k) { return (int64_t)((double)(30000 * k) * frames_per_ms); };
     Group &g = gp.g;
     gp.t_begin = t_begin; gp.t_end = t_end; gp.out_base = out_base;
     g.ch = ch;
@@ -1156,11 +1165,12 @@ static void plan_group(const b200m_handle *h, GroupPlan &gp, bool in_dev, bool o
         g.any_lufs |= p.has_lufs != 0;
         if (!(chain_warm_frames(p) < 1e29)) g.chain_stable = false;
         if (p.multiband) for (int b = 0; b < 3; ++b) g.max_look = std::max(g.max_look, p.band[b].look_frames);
-        const int64_t in_base = in_dev ? in_offsets[t] : in_total;
-        for (int64_t s = 0; s < out_frames[t]; s += chunk) {
+        const int64_t in_base = packed_in ? in_total : in_offsets[t];
+        for (int64_t k = 0; chunk_start(k) < out_frames[t]; ++k) {
+            const int64_t s = chunk_start(k);
             StreamDesc sd;
             sd.in_off = in_base + s; sd.out_off = F + s;
-            sd.out_frames = (int32_t)std::min(chunk, out_frames[t] - s);
+            sd.out_frames = (int32_t)(std::min(chunk_start(k + 1), out_frames[t]) - s);
             sd.in_frames = (int32_t)std::max<int64_t>(0, std::min<int64_t>(sd.out_frames, in_frames[t] - s));
             sd.plan = plan_index[t]; sd.track = t - t_begin;
             sd.blk_off = (int32_t)g.total_blocks; sd.pad_ = 0;
@@ -1234,7 +1244,8 @@ static void plan_group(const b200m_handle *h, GroupPlan &gp, bool in_dev, bool o
     gp.pin_bytes = (gp.res_off + (size_t)g.n_tracks * 16 * (1 + (size_t)n_targets) + 255) & ~(size_t)255;
     size_t need = 16384 + gp.desc_bytes + (size_t)g.n_tracks * 16 * (1 + (size_t)n_targets) + (size_t)F * ch * 2 /*proc*/ + (size_t)F * 4 /*kw*/ +
                   (size_t)zoff * 16 + 25 * 256;
-    if (!in_dev) need += (size_t)in_total * ch * 2;
+    if (!in_dev) need += (size_t)in_total * ch * bps + 256;
+    if (fmt != B200M_FMT_S16) need += (size_t)in_total * ch * 2 + 256;
     if (!out_dev) need += (size_t)Fp * ch * 2 * outs + 256 * outs + 256;
     if (g.any_multiband) need += (size_t)F * 3 * ch * 2 + 3 * 256 + compressor_ws_bytes(h, g, F, 3);
     gp.need = (need + 1023) & ~(size_t)1023;
@@ -1271,7 +1282,11 @@ static int exec_group(b200m_handle *h, GroupPlan &gp, char *ws, char *pin, const
     double *d_z = A.take<double>(gp.zoff + 1);
     double *d_zsel = A.take<double>(gp.zoff + 1);
     int16_t *d_in = nullptr, *d_out = nullptr;
-    if (!in_dev) d_in = A.take<int16_t>((size_t)gp.in_total * ch);
+    const int fmt = gp.fmt, bps = fmt == B200M_FMT_S16 ? 2 : fmt == B200M_FMT_S24 ? 3 : 4;
+    unsigned char *d_raw = nullptr;                      // host input: the group's tracks in the caller's format, packed
+    if (!in_dev) d_raw = A.take<unsigned char>((size_t)gp.in_total * ch * bps + 16);
+    if (fmt != B200M_FMT_S16) d_in = A.take<int16_t>((size_t)gp.in_total * ch);     // ... and staged to the 16-bit domain
+    else d_in = reinterpret_cast<int16_t *>(d_raw);
     const size_t out_stride = ((size_t)gp.Fp * ch + 127) & ~(size_t)127;                    // samples between the staged copies (256-byte aligned)
     if (!out_dev) {
         d_out = A.take<int16_t>(out_stride * n_out + 8);
@@ -1314,13 +1329,33 @@ static int exec_group(b200m_handle *h, GroupPlan &gp, char *ws, char *pin, const
             int64_t run = in_frames[t];
             while (t2 < gp.t_end && in_offsets[t2] == in_offsets[t2 - 1] + in_frames[t2 - 1]) { run += in_frames[t2]; ++t2; }
             if (run > 0)
-                CK(cudaMemcpyAsync(d_in + pos * ch, pcm_in + in_offsets[t] * ch, (size_t)run * ch * 2, cudaMemcpyHostToDevice, X.in));
+                CK(cudaMemcpyAsync(d_raw + (size_t)pos * ch * bps, reinterpret_cast<const unsigned char *>(pcm_in) + (size_t)in_offsets[t] * ch * bps,
+                                   (size_t)run * ch * bps, cudaMemcpyHostToDevice, X.in));
             pos += run;
             t = t2;
         }
         d_src = d_in;
     }
     if (X.h2d_done) { CK(cudaEventRecord(X.h2d_done, X.in)); CK(cudaStreamWaitEvent(X.comp, X.h2d_done, 0)); }
+    if (fmt != B200M_FMT_S16) {
+        // declared extension (b200m_stage_pcm): s24 keeps its high-order 16 bits, f32 goes through ENG:123-126
+        auto stage = [&](const unsigned char *src, int64_t n_samples, int16_t *dst) {
+            if (n_samples <= 0) return;
+            const int grid = (int)std::min<int64_t>((n_samples / 4 + 255) / 256 + 1, 148 * 16);
+            if (fmt == B200M_FMT_S24) LAUNCH("k_stage_s24", k_stage_s24<<<grid, 256, 0, h->stream>>>(src, n_samples, dst));
+            else                      LAUNCH("k_stage_f32", k_stage_f32<<<grid, 256, 0, h->stream>>>(reinterpret_cast<const float *>(src), n_samples, dst));
+        };
+        if (!in_dev) stage(d_raw, gp.in_total * ch, d_in);
+        else {
+            int64_t pos = 0;
+            for (int t = gp.t_begin; t < gp.t_end; ++t) {
+                stage(reinterpret_cast<const unsigned char *>(pcm_in) + (size_t)in_offsets[t] * ch * bps, in_frames[t] * ch, d_in + pos * ch);
+                pos += in_frames[t];
+            }
+        }
+        CK(cudaGetLastError());
+        d_src = d_in;
+    }
     int16_t *d_dst = out_dev ? pcm_out + gp.out_base * ch : d_out;
 
     // ---- kernels (all on the handle's stream) ------------------------------------------------
@@ -1412,7 +1447,7 @@ static int master_batch_impl(b200m_handle *h, const void *pcm_in, int in_on_devi
     if (!h) return B200M_ERR_INVALID;
     if (!pcm_in || !pcm_out || n_tracks <= 0 || !in_offsets || !in_frames || !out_frames || !plans || n_plans <= 0 || !plan_index)
         return fail(h, B200M_ERR_INVALID, "b200m_master_batch: null or empty argument");
-    if (fmt != B200M_FMT_S16) return fail(h, B200M_ERR_INVALID, "b200m_master_batch: only B200M_FMT_S16 is implemented");
+    if (fmt != B200M_FMT_S16 && fmt != B200M_FMT_S24 && fmt != B200M_FMT_F32) return fail(h, B200M_ERR_INVALID, "b200m_master_batch: unknown PCM format %d", fmt);
     CK(cudaSetDevice(h->device));
     const int ch = plans[0].channels, rate = plans[0].sample_rate;
     for (int i = 0; i < n_plans; ++i)
@@ -1455,7 +1490,7 @@ static int master_batch_impl(b200m_handle *h, const void *pcm_in, int in_on_devi
     // (and at least ~8 M frames) so that copies and kernels of neighbouring groups overlap
     const double per_frame = ch * 2 * (2 + std::max(1, n_targets)) + 4 + 3 * (ch * 2 + 2 + 0.26) + 2;
     const double slot_limit = (double)h->ws_limit / slots;
-    // host buffers: ~1/8 of the batch per group, but no more than `pipe_max_frames` (about 32 three-minute tracks): the
+    // host buffers: ~1/8 of the batch per group, but no more than `pipe_max_frames` (about 16 three-minute tracks): the
     // first group's H2D and the last group's D2H are not overlapped by anything, so on a large batch smaller groups win.
     // device buffers: as few groups as the workspace limit allows, of equal size.
     double pipe_frames = 1e300;
@@ -1479,7 +1514,7 @@ static int master_batch_impl(b200m_handle *h, const void *pcm_in, int in_on_devi
             }
             gps.emplace_back();
             plan_group(h, gps.back(), in_dev, out_dev, t0, t1, in_offsets, in_frames, out_frames, plans, plan_index, out_base, targets ? n_targets : 0,
-                       out_offsets);
+                       out_offsets, fmt);
             out_base += frames;
             t0 = t1;
         }

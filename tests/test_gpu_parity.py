@@ -517,3 +517,96 @@ def test_full_size_batch_properties(eng):
     # (4) the target is met (gain applied to the float32 re-float of the processed track, ENG:82-86,219-222)
     assert np.all(np.isfinite(loud)) and np.all(gain > 0)
     assert np.allclose(20 * np.log10(gain), -14.0 - loud, atol=1e-9)
+
+
+@pytest.mark.parametrize("cfg", ["cfg1", "cfg2"])
+def test_baseline_cfg1_cfg2_full_length_vs_oracle(eng, cfg):
+    """BASELINE configs[0] / configs[1] at full length: one 180-s 44.1 kHz s16 stereo track, Pop preset; cfg1 with
+    multiband off and -14 LUFS (the reference's own CPU-runnable case), cfg2 the full chain.  Against the oracle
+    (compressor loop in C) on the same bytes; full-length tolerance of the module docstring."""
+    from b200master import synth
+    from oracle import port
+    rate = 44100
+    pcm = synth.make_track(0, 180.0, rate, hat_cfg=synth.HAT_DENSE)
+    pop = dict(bass_boost=2.0, mid_cut=0.0, presence_boost=3.5, treble_boost=2.5)
+    st = dict(pop, saturation=0, width=1.0, multiband=False, lufs=-14.0) if cfg == "cfg1" else \
+        dict(pop, saturation=25, width=1.2, multiband=True, lufs=-14.0)
+    outs, infos = eng.master([pcm], rate, st)
+    ref, info = port.master(pcm, rate, st)
+    d = np.abs(outs[0].astype(np.int32) - ref.astype(np.int32))
+    print(f"{cfg}: {int((d != 0).sum())} of {d.size} samples differ from the oracle, max {int(d.max())} LSB")
+    assert d.max() <= 1 and np.mean(d != 0) <= 1e-5
+    assert abs(infos[0]["loudness"] - info["loudness"]) <= 1e-9
+
+
+def test_master_batch_stages_s24_and_f32_input(eng):
+    """b200m_master_batch with B200M_FMT_S24 / B200M_FMT_F32 input (declared extension, ENG:125 handles 16 bit only):
+    the batch equals the s16 batch on the staged tracks (s24: high-order 16 bits = audioop.lin2lin; f32: the
+    reference's own quantiser), host and device buffers, several tracks."""
+    import torch
+    from b200master import lib as L
+    from b200master import make_plan, ms_framing, synth
+    from oracle import port
+    rate = 48000
+    st = dict(bass_boost=4.0, mid_cut=3.0, treble_boost=3.0, saturation=10, width=1.2, multiband=True, lufs=-14.0)
+    tracks16 = [synth.make_track(70 + i, s, rate) for i, s in enumerate([31.0, 2.25])]
+    ref, rinfo = eng.master(tracks16, rate, st)
+    plan = make_plan(st, rate, 2)
+    fr = [t.shape[0] for t in tracks16]
+    offs = [0, fr[0]]
+    of = [ms_framing(f, rate) for f in fr]
+    # packed little-endian s24 with the 16-bit programme in the high bytes and noise in the low byte
+    rng = np.random.default_rng(3)
+    flat16 = np.concatenate([t.reshape(-1) for t in tracks16])
+    raw24 = np.stack([rng.integers(0, 256, flat16.size).astype(np.uint8), (flat16.view(np.uint16) & 0xff).astype(np.uint8),
+                      (flat16.view(np.uint16) >> 8).astype(np.uint8)], axis=-1).reshape(-1)
+    # float32 whose quantisation (ENG:123-126) gives the same int16 programme
+    f32 = (flat16.astype(np.float32) + np.float32(0.25) * np.sign(flat16).astype(np.float32)) / np.float32(32768.0)
+    assert np.array_equal(port.float_to_pcm16(f32), flat16)
+    for fmt, raw in ((L.FMT_S24, raw24), (L.FMT_F32, f32)):
+        out = np.empty(sum(of) * 2, dtype=np.int16)
+        loud, gain = eng.master_raw(np.ascontiguousarray(raw), False, offs, fr, of, [plan], [0, 0], out, False, fmt=fmt)
+        assert np.array_equal(out, np.concatenate([r.reshape(-1) for r in ref])), f"host buffers, fmt {fmt}"
+        assert loud[0] == rinfo[0]["loudness"] and loud[1] == rinfo[1]["loudness"]
+        d_raw = torch.from_numpy(np.ascontiguousarray(raw)).cuda()
+        d_out = torch.empty(sum(of) * 2, dtype=torch.int16, device="cuda")
+        eng.master_raw(d_raw, True, offs, fr, of, [plan], [0, 0], d_out, True, fmt=fmt)
+        torch.cuda.synchronize()
+        assert np.array_equal(d_out.cpu().numpy(), out), f"device buffers, fmt {fmt}"
+
+
+def test_chunk_starts_follow_pydubs_ms_arithmetic(eng):
+    """ENG:48-54 slices by milliseconds, and pydub turns a millisecond into a frame as int(ms * (rate / 1000.0)): at
+    some integer rates a chunk then starts one frame short of 30 * rate * k.  Filters and compressors restart at
+    THAT frame; three chunks at such rates against the oracle (whose chunking is pydub's arithmetic)."""
+    from b200master import synth
+    from oracle import port
+    st = dict(bass_boost=3.0, mid_cut=1.0, saturation=10, width=1.1, multiband=True, lufs=-15.0)
+    for rate in (37800, 11024):
+        starts = [int(30000 * k * (rate / 1000.0)) for k in range(1, 4)]
+        assert starts[2] == 90 * rate - 1                              # chunk 3 starts one frame early at these rates
+        pcm = synth.make_track(71, 95.0, rate)
+        outs, infos = eng.master([pcm], rate, st)
+        ref, info = port.master(pcm, rate, st)
+        assert [b[0] for b in port.chunk_bounds(pcm.shape[0], rate)][1:] == starts
+        assert np.array_equal(outs[0], ref), f"rate {rate}: chunk starts {starts} vs {[30 * rate, 60 * rate, 90 * rate]}"
+        assert abs(infos[0]["loudness"] - info["loudness"]) <= 1e-12
+
+
+def test_a_bad_file_fails_alone(eng, tmp_path):
+    """The reference masters one file per call, so a file it cannot handle fails on its own (GUI:226-232 shows an
+    "error" status, WRK:46-50 drops that job): in a folder batch the other files are still written."""
+    import audio_mastering_engine as ame
+    from b200master import synth
+    from b200master.segment import PcmSegment
+    rate = 44100
+    src = tmp_path / "in"; dst = tmp_path / "out"; src.mkdir()
+    PcmSegment(synth.make_track(72, 1.0, rate).tobytes(), 2, rate, 2).export(str(src / "good.wav"))
+    PcmSegment(synth.make_track(73, 0.2, rate).tobytes(), 2, rate, 2).export(str(src / "short.wav"))     # < 400 ms with a loudness target
+    msgs = []
+    ame.batch_process_audio(dict(ame.EQ_PRESETS["pop"], lufs=-14.0), str(src), str(dst), msgs.append)
+    assert any("error" in m.lower() and "short.wav" in m for m in msgs)
+    assert "complete" in msgs[-1].lower() and "1 of 2" in msgs[-1]
+    assert (dst / "mastered_good.wav").exists() and not (dst / "mastered_short.wav").exists()
+    images, infos = eng.master_wav([np.zeros((0, 2), np.int16), np.zeros((0, 2), np.int16)], rate, dict(lufs=None))
+    assert [bytes(i) for i in images] == [eng.wav_header(rate, 2, 0)] * 2      # empty audio: header-only files, no device work
