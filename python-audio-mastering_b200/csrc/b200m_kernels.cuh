@@ -509,6 +509,7 @@ k_chainw(const int16_t *__restrict__ pcm_in, const StreamDesc *__restrict__ stre
     const int sat_on = pl->sat_on, n_eq = pl->n_eq, width_on = pl->width_on, multiband = pl->multiband;
     const float *__restrict__ lut = pl->sat_lut;
     const double width = pl->width;
+    const double half_width = 0.5 * width;                              // exact
     const float widthf = (float)width;
     const int c = CH == 2 ? lane >> 4 : 0, j = CH == 2 ? lane & 15 : lane;
     const unsigned csel = c ? 0xbb32u : 0x9910u;                        // __byte_perm selector: this lane's channel of a packed frame, sign-extended
@@ -628,10 +629,12 @@ k_chainw(const int16_t *__restrict__ pcm_in, const StreamDesc *__restrict__ stre
             if (n_eq > 0) {     // float64 arithmetic (EQ output is float64)
 #pragma unroll
                 for (int n = 0; n < SEG; ++n) {
+                    // mid = (me + o) / 2, side = (me - o) / 2 * w, me' = mid + side (seen from R, (R - L) / 2 * w is exactly
+                    // -side).  Halving is exact, so fl(fl(me - o) * 0.5 * w) == fl(fl(me - o) * (0.5 w)) and
+                    // fl(fl(me + o) * 0.5 + side) is one FMA: four fp64 instructions instead of six, the same roundings.
                     const double o = __shfl_xor_sync(FULL, x[n], 16);
-                    const double mid = __dmul_rn(__dadd_rn(x[n], o), 0.5);
-                    const double side = __dmul_rn(__dmul_rn(__dsub_rn(x[n], o), 0.5), width);
-                    x[n] = __dadd_rn(mid, side);
+                    const double side = __dmul_rn(__dsub_rn(x[n], o), half_width);
+                    x[n] = fma(__dadd_rn(x[n], o), 0.5, side);
                 }
             } else {            // EQ fully bypassed: the reference stays in float32
 #pragma unroll
@@ -934,32 +937,41 @@ k_detectw(const StreamDesc *__restrict__ streams, const PlanDev *__restrict__ pl
     long long S_base = 0;
     unsigned hword = 0xffffffffu;                                   // hold bits of the current 1024-frame word (blocks past the end count as held)
     const int i_start = t0 == 0 ? 0 : t0 - ((H + DW_STEP - 1) / DW_STEP) * DW_STEP;
+    // the lane's eight frames of a step, as packed words (stereo: one frame per word; mono: two): issued one step
+    // ahead, so the loads of step i + 1 are in flight while step i is being worked on
+    auto load_lead = [&](int fl, unsigned (&w)[8]) {
+        const bool inside = fl >= 0 && fl + 8 <= sd.out_frames;
+        if (inside && src16) {
+            if (CH == 2) {
+                const uint4 a = __ldg(reinterpret_cast<const uint4 *>(src + (int64_t)fl * 2)), b = __ldg(reinterpret_cast<const uint4 *>(src + (int64_t)fl * 2) + 1);
+                w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w; w[4] = b.x; w[5] = b.y; w[6] = b.z; w[7] = b.w;
+            } else {
+                const uint4 a = __ldg(reinterpret_cast<const uint4 *>(src + fl));
+                w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w;
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const bool ok = fl + k >= 0 && fl + k < sd.out_frames;
+                if (CH == 2) w[k] = ok ? *reinterpret_cast<const unsigned *>(src + (int64_t)(fl + k) * 2) : 0u;
+                else {
+                    const unsigned v = ok ? (unsigned)(unsigned short)src[fl + k] : 0u;
+                    if (k & 1) w[k >> 1] |= v << 16; else w[k >> 1] = v;
+                }
+            }
+        }
+    };
+    unsigned wn[8];
+    load_lead(i_start + 8 * lane, wn);
     for (int i0 = i_start; i0 < t1; i0 += DW_STEP) {
         const int f = i0 + 8 * lane;
         // ---- lead: this lane's eight frames -> energies -> ring --------------------------------------------------
         unsigned el[8];
         {
-            unsigned w[8];                                          // stereo: one packed frame per word; mono: two frames per word (four words)
-            const bool inside = f >= 0 && f + 8 <= sd.out_frames;
-            if (inside && src16) {
-                if (CH == 2) {
-                    const uint4 a = __ldg(reinterpret_cast<const uint4 *>(src + (int64_t)f * 2)), b = __ldg(reinterpret_cast<const uint4 *>(src + (int64_t)f * 2) + 1);
-                    w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w; w[4] = b.x; w[5] = b.y; w[6] = b.z; w[7] = b.w;
-                } else {
-                    const uint4 a = __ldg(reinterpret_cast<const uint4 *>(src + f));
-                    w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w;
-                }
-            } else {
+            unsigned w[8];
 #pragma unroll
-                for (int k = 0; k < 8; ++k) {
-                    const bool ok = f + k >= 0 && f + k < sd.out_frames;
-                    if (CH == 2) w[k] = ok ? *reinterpret_cast<const unsigned *>(src + (int64_t)(f + k) * 2) : 0u;
-                    else {
-                        const unsigned v = ok ? (unsigned)(unsigned short)src[f + k] : 0u;
-                        if (k & 1) w[k >> 1] |= v << 16; else w[k >> 1] = v;
-                    }
-                }
-            }
+            for (int k = 0; k < 8; ++k) w[k] = wn[k];
+            if (i0 + DW_STEP < t1) load_lead(f + DW_STEP, wn);
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
                 if (CH == 2) {
