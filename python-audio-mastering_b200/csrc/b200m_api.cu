@@ -745,6 +745,10 @@ extern "C" int b200m_create(int device, b200m_handle **out)
     if (e == cudaSuccess) e = allow_smem(k_chainw<1, false, true, CW_SLUT, true>, ChainW<1>::SMEM_SLUT);
     if (e == cudaSuccess) e = allow_smem(k_chainw<2, true, true, CW_SLUT, true>, ChainW<2>::SMEM_SLUT);
     if (e == cudaSuccess) e = allow_smem(k_chainw<2, false, true, CW_SLUT, true>, ChainW<2>::SMEM_SLUT);
+    if (e == cudaSuccess) e = allow_smem(k_chainw<1, true, false, CW_SLUT, true>, ChainW<1>::SMEM_SLUT_MP);
+    if (e == cudaSuccess) e = allow_smem(k_chainw<1, false, false, CW_SLUT, true>, ChainW<1>::SMEM_SLUT_MP);
+    if (e == cudaSuccess) e = allow_smem(k_chainw<2, true, false, CW_SLUT, true>, ChainW<2>::SMEM_SLUT_MP);
+    if (e == cudaSuccess) e = allow_smem(k_chainw<2, false, false, CW_SLUT, true>, ChainW<2>::SMEM_SLUT_MP);
     if (e == cudaSuccess) e = allow_smem(k_detect<1>, detect_smem_bytes(8192));
     if (e == cudaSuccess) e = allow_smem(k_detect<2>, detect_smem_bytes(8192));
     if (e == cudaSuccess) e = allow_smem(k_comp<1, 1, true>, recur_smem_bytes(1));
@@ -1213,11 +1217,31 @@ static void plan_group(const b200m_handle *h, GroupPlan &gp, bool in_dev, bool o
             const int wseg = (int)std::min<double>(1 << 20, std::max(8.0, std::ceil(run / wt)));
             for (size_t i = 0; i < gp.streams.size(); ++i)
                 make_segments_w(gp.csegs, (int)i, gp.streams[i].out_frames, wt, chain_warm_frames(plans[gp.streams[i].plan]), h->seg_chain > 0 ? h->seg_chain * (TILE / wt) : wseg);
-            // one plan with the exciter on and an odd table: the 16-warp shape keeps the table in shared memory
-            g.chain_slut = g.single_plan >= 0 && (size_t)g.single_plan < h->plans_host.size() && h->plans_host[g.single_plan].sat_on &&
-                           h->plans_host[g.single_plan].sat_sym && h->chain_slut_ok;
+            // every plan has the exciter on with the SAME odd table: the 16-warp shape keeps the table in shared memory
+            // (one plan: its filter tables travel as a kernel parameter; several: the segments are grouped by plan, a
+            // CTA's sixteen belong to one plan and its tables sit in shared memory next to the exciter table)
+            g.chain_slut = h->chain_slut_ok && !gp.streams.empty();
+            const float *lut0 = nullptr;
+            for (auto &sd : gp.streams) {
+                if ((size_t)sd.plan >= h->plans_host.size()) { g.chain_slut = false; break; }
+                const PlanDev &pd = h->plans_host[sd.plan];
+                if (!pd.sat_on || !pd.sat_sym || (lut0 && pd.sat_lut != lut0)) { g.chain_slut = false; break; }
+                lut0 = pd.sat_lut;
+            }
             if (g.chain_slut) {
-                while (gp.csegs.size() % CW_SLUT != 0) gp.csegs.push_back({0, 0, 0, 0});
+                if (g.single_plan < 0) {
+                    std::vector<SegDesc> grouped;
+                    std::vector<int> plan_ids;
+                    for (auto &sd : gp.streams) if (std::find(plan_ids.begin(), plan_ids.end(), sd.plan) == plan_ids.end()) plan_ids.push_back(sd.plan);
+                    for (int pid : plan_ids) {
+                        for (auto &sg : gp.csegs) if (gp.streams[sg.owner].plan == pid) grouped.push_back(sg);
+                        int owner0 = 0;
+                        for (size_t i = 0; i < gp.streams.size(); ++i) if (gp.streams[i].plan == pid) { owner0 = (int)i; break; }
+                        while (grouped.size() % CW_SLUT != 0) grouped.push_back({0, 0, owner0, 0});     // padding names a stream of the same plan
+                    }
+                    gp.csegs.swap(grouped);
+                }
+                while (gp.csegs.size() % CW_SLUT != 0) gp.csegs.push_back({0, 0, gp.csegs.empty() ? 0 : gp.csegs.back().owner, 0});
                 for (size_t c0 = 0; c0 < gp.csegs.size(); c0 += CW_SLUT) {
                     int64_t it = 0;
                     for (int w = 0; w < CW_SLUT; ++w) {
@@ -1370,10 +1394,15 @@ static int exec_group(b200m_handle *h, GroupPlan &gp, char *ws, char *pin, const
         const bool nanchk = !g.chain_stable;
         if (g.chain_slut) {
             const int nb = g.n_csegs / CW_SLUT;
-#define LAUNCH_CHAINS(CHN, NAN_) \
-            LAUNCH("k_chain", k_chainw<CHN, NAN_, true, CW_SLUT, true><<<nb, 32 * CW_SLUT, ChainW<CHN>::SMEM_SLUT, h->stream>>>(d_src, d_streams, d_csegs, g.n_csegs, h->d_plans, d_proc, bp, ct, d_cta_iters))
-            if (ch == 2) { if (nanchk) LAUNCH_CHAINS(2, true); else LAUNCH_CHAINS(2, false); }
-            else         { if (nanchk) LAUNCH_CHAINS(1, true); else LAUNCH_CHAINS(1, false); }
+#define LAUNCH_CHAINS(CHN, NAN_, PT_) \
+            LAUNCH("k_chain", k_chainw<CHN, NAN_, PT_, CW_SLUT, true><<<nb, 32 * CW_SLUT, (PT_) ? ChainW<CHN>::SMEM_SLUT : ChainW<CHN>::SMEM_SLUT_MP, h->stream>>>(d_src, d_streams, d_csegs, g.n_csegs, h->d_plans, d_proc, bp, ct, d_cta_iters))
+            if (ch == 2) {
+                if (pt) { if (nanchk) LAUNCH_CHAINS(2, true, true); else LAUNCH_CHAINS(2, false, true); }
+                else    { if (nanchk) LAUNCH_CHAINS(2, true, false); else LAUNCH_CHAINS(2, false, false); }
+            } else {
+                if (pt) { if (nanchk) LAUNCH_CHAINS(1, true, true); else LAUNCH_CHAINS(1, false, true); }
+                else    { if (nanchk) LAUNCH_CHAINS(1, true, false); else LAUNCH_CHAINS(1, false, false); }
+            }
 #undef LAUNCH_CHAINS
         } else {
             const int nb = g.n_csegs;

@@ -302,6 +302,7 @@ template <int CH> struct ChainW {
     static constexpr size_t SMEM = 8 * sizeof(SecTab) + WARP_BYTES;               // CW = 1, tables in shared memory (several plans in the launch)
     static constexpr size_t SMEM_PT = QTAB_BYTES + WARP_BYTES;                    // CW = 1, tables in the constant bank
     static constexpr size_t SMEM_SLUT = SLUT_BYTES + QTAB_BYTES + CW_SLUT * WARP_BYTES;   // CW = 16, exciter table + Q tables + 16 warps
+    static constexpr size_t SMEM_SLUT_MP = SLUT_BYTES + 8 * sizeof(SecTab) + CW_SLUT * WARP_BYTES;   // ... several plans sharing one exciter table: the CTA's plan's tables in shared memory
 };
 
 // The lane-independent tables of the launch's single plan (SecTabC, b200m_device.cuh), by value.
@@ -457,7 +458,8 @@ __device__ __forceinline__ void store_q16_w(int16_t *__restrict__ dst, const int
 #define B200M_CHAINW_OCC 2
 #endif
 // PT: the launch uses ONE plan and its lane-independent tables arrive in `ct` (constant bank).
-// CW / SLUT: see above (SLUT implies PT and CW == CW_SLUT; cta_iters is only read when CW > 1).
+// CW / SLUT: see above (SLUT implies CW == CW_SLUT; cta_iters is only read when CW > 1; without PT the segments of a CTA
+// belong to one plan -- the host pads per plan -- and every plan of the launch has the same exciter table).
 template <int CH, bool NANCHK, bool PT, int CW = 1, bool SLUT = false>
 __global__ void __launch_bounds__(32 * CW, CW == 1 ? B200M_CHAINW_OCC * 8 : 1)
 k_chainw(const int16_t *__restrict__ pcm_in, const StreamDesc *__restrict__ streams, const SegDesc *__restrict__ segs, int n_segs,
@@ -466,7 +468,7 @@ k_chainw(const int16_t *__restrict__ pcm_in, const StreamDesc *__restrict__ stre
 {
     using W = ChainW<CH>;
     constexpr int NL = W::NL, WT = W::WT;
-    static_assert(!SLUT || (PT && CW == CW_SLUT), "the shared-memory exciter table needs the single-plan, 16-warp shape");
+    static_assert(!SLUT || CW == CW_SLUT, "the shared-memory exciter table needs the 16-warp shape");
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float *slut = reinterpret_cast<float *>(smem_raw);                   // SLUT: 2^15 * exciter(m / 2^15), m = 0 .. 32768
     unsigned char *smem_tab = smem_raw + (SLUT ? SLUT_BYTES : 0);

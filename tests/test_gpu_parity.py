@@ -610,3 +610,26 @@ def test_a_bad_file_fails_alone(eng, tmp_path):
     assert (dst / "mastered_good.wav").exists() and not (dst / "mastered_short.wav").exists()
     images, infos = eng.master_wav([np.zeros((0, 2), np.int16), np.zeros((0, 2), np.int16)], rate, dict(lufs=None))
     assert [bytes(i) for i in images] == [eng.wav_header(rate, 2, 0)] * 2      # empty audio: header-only files, no device work
+
+
+def test_several_plans_sharing_one_exciter_table(eng):
+    """cfg5's shape: clips with different presets / targets (different filter tables) but the same saturation in ONE
+    batch.  k_chainw's 16-warp shape then groups the segments by plan around one shared-memory exciter table; a
+    batch whose plans have different saturations falls back to gathers from global memory.  Both against the oracle."""
+    from b200master import synth
+    from oracle import port
+    rate = 48000
+    presets = [dict(bass_boost=4.0, mid_cut=3.0, presence_boost=1.0, treble_boost=3.0), dict(bass_boost=5.0, mid_cut=4.0, presence_boost=2.0, treble_boost=3.5),
+               dict(bass_boost=2.0, mid_cut=0.0, presence_boost=3.5, treble_boost=2.5), dict(bass_boost=1.5, mid_cut=-2.0, presence_boost=2.5, treble_boost=1.0)]
+    tracks = [synth.make_track(110 + i, 30.0 if i % 3 else 7.3, rate) for i in range(7)]
+    try:
+        eng.set_chain_kernel(2)
+        for sats in ([25] * 7, [25, 10, 25, 0, 10, 25, 40]):
+            sts = [dict(presets[i % 4], saturation=s, width=1.2, multiband=(i % 2 == 0), lufs=[-9.0, -14.0, -23.0][i % 3]) for i, s in enumerate(sats)]
+            outs, infos = eng.master(tracks, rate, sts)
+            for t, st, o, info in zip(tracks, sts, outs, infos):
+                ref, rinfo = port.master(t, rate, st)
+                assert np.array_equal(o, ref)
+                assert abs(info["loudness"] - rinfo["loudness"]) <= 1e-12
+    finally:
+        eng.set_chain_kernel(0)
