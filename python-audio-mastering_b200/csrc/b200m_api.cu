@@ -962,11 +962,12 @@ static RecurParams recur_params(const b200m_handle *h, const Group &g, int nband
         P.tile_len = std::max(32, (h->recur_tile + 31) & ~31);
     } else {
         // One lane per (stream, tile), one warp per band: about one resident wave of lanes (148 SMs x
-        // B200M_COMP_CTAS CTAs x 32); tiles of 2048 .. 65536 frames.  Every lane also runs the warm-up
+        // B200M_COMP_CTAS CTAs x 32); tiles of 4096 .. 262144 frames.  Every lane also runs the warm-up
         // (`warm` active frames, level detector -> curve -> recurrence only), so long tiles waste less
         // work and short tiles give a small batch enough lanes.
-        const double want_tiles = 148.0 * B200M_COMP_CTAS * 32 / std::max(1, g.n_streams);
-        const double len = std::min(65536.0, std::max(4096.0, g.max_stream_frames / want_tiles));
+        // (the tile count is rounded DOWN: a few CTAs beyond the resident wave would cost a whole second pass)
+        const double want_tiles = std::max(1.0, std::floor(148.0 * B200M_COMP_CTAS * 32 / std::max(1, g.n_streams)));
+        const double len = std::min(262144.0, std::max(4096.0, std::ceil(g.max_stream_frames / want_tiles)));
         P.tile_len = ((int)len + 1023) & ~1023;
     }
     P.tiles = std::max(1, (g.max_stream_frames + P.tile_len - 1) / P.tile_len);
