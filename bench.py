@@ -230,7 +230,7 @@ def run_reference_arm(args):
     cores = os.cpu_count() or 1
     total_steps = args.steps + args.warmup
     budget = max(4.0, 150.0 / total_steps)                  # seconds of wall per step
-    tracks, note = workload_tracks_host(list(range(cores)), 30.0 if args.seconds >= 30.0 else args.seconds)
+    tracks, note = workload_tracks_host(list(range(cores)), args.seconds)      # whole tracks: the first seconds of THE workload's tracks
     _CPU_TRACKS["probe"] = tracks[0][:RATE]
     probe = _cpu_job(("probe", "py"))                       # wall per audio-second on one core
     sample = float(min(30.0, max(1.0, budget / max(probe, 1e-3))))
@@ -411,7 +411,9 @@ def run_b200_arm(args):
         tpath = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tpath):
             tj = json.load(open(tpath))
-            key = "k_chainw" if dom == "k_chain" and "k_chainw" in tj else dom
+            # the library times a kernel family under one name; ncu lists the variant that ran at this batch size
+            key = {"k_chain": "k_chainw", "k_detect": "k_detectw"}.get(dom, dom)
+            key = key if key in tj else dom
             if key in tj:
                 traffic = tj[key]["dram_bytes_per_frame"] * frames_per_launch
             traffic_total = sum(v["dram_bytes_per_frame"] for v in tj.values() if isinstance(v, dict) and "dram_bytes_per_frame" in v)
