@@ -1,6 +1,7 @@
 // b200m_api.cu -- C-ABI of libb200master.so (include/b200_master.h): handle, host-side
 // filter design, plan upload, batch orchestration and the stage-level entry points.
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>       // header-only NVTX 3: a range per kernel launch and per batch call (nsys / ncu --nvtx)
 
 #include <algorithm>
 #include <cmath>
@@ -113,9 +114,10 @@ struct LaunchScope {
     LaunchScope(b200m_handle *h_, const char *name) : h(h_), on(h_->profiling)
     {
         ++h->launches;
+        nvtxRangePushA(name);
         if (on) { r.name = prof_name_id(h, name); r.a = prof_event(h); r.b = prof_event(h); cudaEventRecord(r.a, h->stream); }
     }
-    ~LaunchScope() { if (on) { cudaEventRecord(r.b, h->stream); h->prof_recs.push_back(r); } }
+    ~LaunchScope() { if (on) { cudaEventRecord(r.b, h->stream); h->prof_recs.push_back(r); } nvtxRangePop(); }
 };
 #define LAUNCH(name, ...) do { LaunchScope ls_(h, name); __VA_ARGS__; } while (0)
 
@@ -1475,6 +1477,7 @@ static int master_batch_impl(b200m_handle *h, const void *pcm_in, int in_on_devi
                              void *pcm_out, int out_on_device, double *loudness_out, double *gain_out)
 {
     if (!h) return B200M_ERR_INVALID;
+    struct Range { Range() { nvtxRangePushA("b200m_master_batch"); } ~Range() { nvtxRangePop(); } } nvtx_range;
     if (!pcm_in || !pcm_out || n_tracks <= 0 || !in_offsets || !in_frames || !out_frames || !plans || n_plans <= 0 || !plan_index)
         return fail(h, B200M_ERR_INVALID, "b200m_master_batch: null or empty argument");
     if (fmt != B200M_FMT_S16 && fmt != B200M_FMT_S24 && fmt != B200M_FMT_F32) return fail(h, B200M_ERR_INVALID, "b200m_master_batch: unknown PCM format %d", fmt);
