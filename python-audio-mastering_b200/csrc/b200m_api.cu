@@ -1495,6 +1495,23 @@ static int master_batch_impl(b200m_handle *h, const void *pcm_in, int in_on_devi
         if (plans[plan_index[t]].has_lufs && (double)out_frames[t] < 0.4 * rate)
             return fail(h, B200M_ERR_TOO_SHORT, "track %d: audio must have length greater than the block size (400 ms)", t);
         total_frames += std::max(out_frames[t], in_frames[t]);
+        if (plans[plan_index[t]].multiband) {
+            // ENG:210: pydub's overlay re-derives a chunk's length from its ROUNDED millisecond length.  At the usual
+            // rates that is the chunk itself; at the few integer rates where 30 000 ms is not a whole number of frames as
+            // pydub computes it (11 024, 18 900, 37 800 ... Hz) the reference drops or inserts a frame at every chunk seam,
+            // shifting everything behind it.  That is not reproduced: such a track is refused, not mastered differently.
+            const double fpm = (double)rate / 1000.0;
+            for (int64_t k = 0;; ++k) {
+                const int64_t s0 = (int64_t)((double)(30000 * k) * fpm);
+                if (s0 >= out_frames[t]) break;
+                const int64_t n = std::min((int64_t)((double)(30000 * (k + 1)) * fpm), out_frames[t]) - s0;
+                const int64_t e = (int64_t)(std::nearbyint(1000.0 * ((double)n / (double)rate)) * fpm);
+                if (e != n)
+                    return fail(h, B200M_ERR_INVALID, "track %d: at %d Hz chunk %lld (%lld frames) is not a whole number of milliseconds as pydub counts them "
+                                "(its overlay would re-frame it to %lld); the multiband stage is not supported at this sample rate -- resample first",
+                                t, rate, (long long)k, (long long)n, (long long)e);
+            }
+        }
         if (targets && !plans[plan_index[t]].has_lufs)
             return fail(h, B200M_ERR_INVALID, "track %d: a loudness sweep needs a plan with a loudness target (has_lufs)", t);
     }

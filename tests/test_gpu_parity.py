@@ -577,11 +577,13 @@ def test_master_batch_stages_s24_and_f32_input(eng):
 
 def test_chunk_starts_follow_pydubs_ms_arithmetic(eng):
     """ENG:48-54 slices by milliseconds, and pydub turns a millisecond into a frame as int(ms * (rate / 1000.0)): at
-    some integer rates a chunk then starts one frame short of 30 * rate * k.  Filters and compressors restart at
-    THAT frame; three chunks at such rates against the oracle (whose chunking is pydub's arithmetic)."""
+    some integer rates a chunk then starts one frame short of 30 * rate * k.  Filters restart at THAT frame; four
+    chunks at such rates against the oracle (whose chunking is pydub's arithmetic).  With the multiband stage on,
+    pydub's overlay additionally re-frames every chunk to its rounded millisecond length at these rates (a frame is
+    dropped or inserted at each seam): that is refused with an explicit error rather than mastered differently."""
     from b200master import synth
     from oracle import port
-    st = dict(bass_boost=3.0, mid_cut=1.0, saturation=10, width=1.1, multiband=True, lufs=-15.0)
+    st = dict(bass_boost=3.0, mid_cut=1.0, saturation=10, width=1.1, multiband=False, lufs=-15.0)
     for rate in (37800, 11024):
         starts = [int(30000 * k * (rate / 1000.0)) for k in range(1, 4)]
         assert starts[2] == 90 * rate - 1                              # chunk 3 starts one frame early at these rates
@@ -591,6 +593,9 @@ def test_chunk_starts_follow_pydubs_ms_arithmetic(eng):
         assert [b[0] for b in port.chunk_bounds(pcm.shape[0], rate)][1:] == starts
         assert np.array_equal(outs[0], ref), f"rate {rate}: chunk starts {starts} vs {[30 * rate, 60 * rate, 90 * rate]}"
         assert abs(infos[0]["loudness"] - info["loudness"]) <= 1e-12
+        with pytest.raises(ValueError, match="not supported at this sample rate"):
+            eng.master([pcm], rate, dict(st, multiband=True))
+    # the usual rates are frame-exact: multiband across chunk seams is covered by test_oracle_multi_chunk
 
 
 def test_a_bad_file_fails_alone(eng, tmp_path):
