@@ -1085,6 +1085,9 @@ k_detectw(const StreamDesc *__restrict__ streams, const PlanDev *__restrict__ pl
 #ifndef B200M_WARM_RELEASES
 #define B200M_WARM_RELEASES 1.75
 #endif
+#ifndef B200M_COMP_MINB
+#define B200M_COMP_MINB 4           // minimum resident CTAs per SM promised to the compiler for k_comp (register cap)
+#endif
 #ifndef B200M_COMP_UNROLL
 #define B200M_COMP_UNROLL 2         // 128-bit sample words (4 stereo frames each) per iteration of the lane-serial walk
 #endif
@@ -1237,7 +1240,7 @@ __device__ __forceinline__ void store_frame(int16_t *__restrict__ p, int64_t f, 
 // NB = 3: the crossover's bands 0..2, one WARP of the CTA per band (band_base == 0); NB = 1: the single-band helper
 // entry point (band `band_base`), one warp per CTA.  Lane l of every warp of CTA c works on (stream, tile) number 32 c + l.
 template <int CH, int NB, bool DBG>
-__global__ void __launch_bounds__(32 * NB)
+__global__ void __launch_bounds__(32 * NB, B200M_COMP_MINB)
 k_comp(const StreamDesc *__restrict__ streams, const PlanDev *__restrict__ plans, RecurParams P, BandPtrs bp,
        int16_t *__restrict__ proc, const double *__restrict__ ss_in, const double *__restrict__ se_in,
        double *__restrict__ ss_out, double *__restrict__ se_out,
