@@ -37,11 +37,12 @@ for r in rows[2:]:
     t, rd, wr = val(r, "time"), val(r, "rd"), val(r, "wr")
     out.append(f"| {name} | {int(val(r, 'grid'))} x {int(val(r, 'block'))} | {t * 1e3:.3f} | {rd / 1e9:.3f} | {wr / 1e9:.3f} | {(rd + wr) / frames:.1f} | "
                f"{val(r, 'dram'):.1f} | {val(r, 'sm'):.1f} | {val(r, 'warps'):.1f} | {val(r, 'fp64'):.1f} | {val(r, 'issue'):.1f} | {int(val(r, 'regs'))} | {val(r, 'inst') / frames:.2f} |")
-    if base not in seen and t > 2e-5:          # first substantial launch of each kernel
-        seen.add(base)
+    if t > 2e-5 and t > traffic.get(base, {}).get("_t", 0.0):          # the longest launch of each kernel (repair rounds re-launch k_comp)
         traffic[base] = {"dram_bytes_per_frame": (rd + wr) / frames, "dram_read_bytes": rd, "dram_write_bytes": wr, "frames": frames,
-                         "source": f"profiles/{tag}_ncu_full.md"}
+                         "source": f"profiles/{tag}_ncu_full.md", "_t": t}
 open(os.path.join(ROOT, "profiles", f"{tag}_ncu_full.md"), "w").write("\n".join(out) + "\n")
+for v in traffic.values():
+    v.pop("_t", None)
 json.dump(traffic, open(tpath, "w"), indent=1)
 if len(sys.argv) > 4:
     shutil.copy(sys.argv[4], os.path.join(ROOT, "profiles", f"{tag}_launches.csv"))
