@@ -61,6 +61,7 @@ struct b200m_handle {
     int seg_chain = 0, seg_kweight = 0;
     int chain_kernel = 0;            // 0 = automatic, 1 = k_chain (a CTA per segment), 2 = k_chainw (a warp per segment)
     int detect_kernel = 0;           // 0 = automatic (k_detectw where the look-back fits its ring), 1 = k_detect always (B200M_DETECT_KERNEL: experiments, tests)
+    int chain_waves = 4;             // k_chainw: the most resident waves of warps a group is cut into (B200M_CHAIN_WAVES)
     bool chain_slut_ok = true;       // k_chainw may take its 16-warp shape (B200M_CHAIN_SLUT=0 switches it off: experiments)
     unsigned long long *d_counters = nullptr;
     // host-buffer pipeline: side streams for H2D / D2H and the events that order the groups
@@ -362,15 +363,15 @@ static void make_segments(std::vector<SegDesc> &out, int owner, int64_t frames, 
     }
 }
 
-// Warp segments of k_chainw: the stream is cut into equal runs of about `seg_tiles` warp tiles (never shorter than
-// twice the warm-up), one warp each.
+// Warp segments of k_chainw: the stream is cut into the fewest equal runs of at most `seg_tiles` warp tiles (never
+// shorter than twice the warm-up), one warp each.
 static void make_segments_w(std::vector<SegDesc> &out, int owner, int64_t frames, int tile, double warm_frames, int seg_tiles)
 {
     if (frames > 0) {
         const int64_t ntiles = (frames + tile - 1) / tile;
         const int64_t warm_tiles = (int64_t)std::ceil(warm_frames / tile);
         const int64_t min_seg = std::max<int64_t>(1, 2 * warm_tiles);
-        int64_t nseg = std::max<int64_t>(1, (ntiles + std::max(1, seg_tiles) / 2) / std::max(1, seg_tiles));
+        int64_t nseg = std::max<int64_t>(1, (ntiles + std::max(1, seg_tiles) - 1) / std::max(1, seg_tiles));
         while (nseg > 1 && (ntiles + nseg - 1) / nseg < min_seg) --nseg;
         const int64_t seg = std::max(min_seg, (ntiles + nseg - 1) / nseg);
         const int warm = (int)(warm_tiles * tile);
@@ -730,6 +731,7 @@ extern "C" int b200m_create(int device, b200m_handle **out)
     if (const char *ck = std::getenv("B200M_CHAIN_KERNEL")) h->chain_kernel = std::max(0, std::min(2, std::atoi(ck)));   // test / experiment override
     if (const char *ck = std::getenv("B200M_CHAIN_SLUT")) h->chain_slut_ok = std::atoi(ck) != 0;
     if (const char *ck = std::getenv("B200M_DETECT_KERNEL")) h->detect_kernel = std::atoi(ck);
+    if (const char *ck = std::getenv("B200M_CHAIN_WAVES")) h->chain_waves = std::max(1, std::min(16, std::atoi(ck)));
     if (const char *ck = std::getenv("B200M_PIPE_MAX_FRAMES")) h->pipe_max_frames = std::max(8e6, std::atof(ck));
     e = allow_smem(k_chain<1, true>, chain_smem_bytes<1>());
     if (e == cudaSuccess) e = allow_smem(k_chain<2, true>, chain_smem_bytes<2>());
@@ -1198,10 +1200,12 @@ static void plan_group(const b200m_handle *h, GroupPlan &gp, bool in_dev, bool o
         for (auto &td : gp.tracks) ktiles += (td.frames + KTILE - 1) / KTILE;
         const int cs = h->seg_chain == 0 ? auto_seg_tiles(ctiles, 8, 48) : h->seg_chain;
         const int ks = h->seg_kweight == 0 ? auto_seg_tiles(ktiles, 8, 32) : h->seg_kweight;
-        // k_chainw needs eight times as many independent segments as k_chain.  It runs w = 4, 3, 2 or 1
-        // resident waves of warps (148 SMs x 16), the most for which a warp's run is still >= 4 warm-ups
-        // (warm-up share <= 20 %; measured on B200: 13.0 vs 13.9 ms on 64 tracks, 1.82 vs 1.98 ms on 8);
-        // smaller groups stay with k_chain, whose eight warps share one warm-up.
+        // k_chainw: every warp walks its own segment; 148 SMs x 16 warps are resident at a time and all segments of a
+        // group have (nearly) the same length, so the kernel's time is waves x (segment + warm-up).  The cut is chosen
+        // to minimise exactly that: for w = 1 .. chain_waves waves, the longest segments whose count still fits w
+        // resident waves (a few segments beyond a wave cost a whole extra pass: 600 CTAs of 16 warps on 148 SMs ran
+        // 9.4 ms per 64 tracks, 144 CTAs run 7.3 ms), never shorter than four warm-ups; smaller groups stay with
+        // k_chain, whose eight warps share one warm-up.
         double max_warm = 0;
         bool bounded = true;
         for (auto &sd : gp.streams) {
@@ -1210,16 +1214,34 @@ static void plan_group(const b200m_handle *h, GroupPlan &gp, bool in_dev, bool o
             max_warm = std::max(max_warm, w);
         }
         const int wt = ch == 2 ? ChainW<2>::WT : ChainW<1>::WT;
-        const double frames_total = (double)ctiles * TILE;
-        double run = 0;
-        for (int w = 4; w >= 1 && run == 0; --w)
-            if (frames_total / (148.0 * 16 * w) >= 4.0 * std::max(max_warm, 256.0)) run = frames_total / (148.0 * 16 * w);
-        g.chain_warps = bounded && h->seg_chain >= 0 && (h->chain_kernel == 2 || (h->chain_kernel == 0 && run > 0));
-        if (run == 0) run = 4.0 * std::max(max_warm, 256.0);
+        std::vector<int64_t> wtiles(gp.streams.size());
+        int64_t total_wtiles = 0;
+        for (size_t i = 0; i < gp.streams.size(); ++i) { wtiles[i] = (gp.streams[i].out_frames + wt - 1) / wt; total_wtiles += wtiles[i]; }
+        const double warm_tiles = std::ceil(std::max(max_warm, 1.0) / wt);
+        const double min_len = std::max(8.0, 4.0 * std::max(warm_tiles, 1.0));      // segment length in warp tiles
+        double best_len = 0, best_cost = 1e300;
+        for (int w = 1; w <= h->chain_waves && bounded; ++w) {
+            const double cap = 148.0 * 16 * w;
+            double len = std::max(min_len, std::ceil((double)total_wtiles / cap));
+            for (int it = 0; it < 200; ++it) {
+                double total = 0;
+                for (int64_t nt : wtiles) total += nt > 0 ? std::ceil((double)nt / len) : 0;
+                if (total <= cap) break;
+                len = std::ceil(len * std::max(1.003, total / cap));
+            }
+            double total = 0, longest = 0;
+            for (int64_t nt : wtiles) if (nt > 0) { const double n = std::ceil((double)nt / len); total += n; longest = std::max(longest, std::ceil((double)nt / n)); }
+            if (total > cap) continue;
+            const double cost = w * (longest + warm_tiles);
+            if (cost < best_cost) { best_cost = cost; best_len = len; }
+        }
+        const bool enough = (double)total_wtiles / min_len >= 148.0 * 16;     // a resident wave of warps, each with a run of >= 4 warm-ups
+        g.chain_warps = bounded && h->seg_chain >= 0 && (h->chain_kernel == 2 || (h->chain_kernel == 0 && enough));
+        if (best_len == 0) best_len = min_len;
         if (g.chain_warps) {
-            const int wseg = (int)std::min<double>(1 << 20, std::max(8.0, std::ceil(run / wt)));
+            const int wseg = h->seg_chain > 0 ? h->seg_chain * (TILE / wt) : (int)std::min<double>(1 << 20, best_len);
             for (size_t i = 0; i < gp.streams.size(); ++i)
-                make_segments_w(gp.csegs, (int)i, gp.streams[i].out_frames, wt, chain_warm_frames(plans[gp.streams[i].plan]), h->seg_chain > 0 ? h->seg_chain * (TILE / wt) : wseg);
+                make_segments_w(gp.csegs, (int)i, gp.streams[i].out_frames, wt, chain_warm_frames(plans[gp.streams[i].plan]), wseg);
             // every plan has the exciter on with the SAME odd table: the 16-warp shape keeps the table in shared memory
             // (one plan: its filter tables travel as a kernel parameter; several: the segments are grouped by plan, a
             // CTA's sixteen belong to one plan and its tables sit in shared memory next to the exciter table)
