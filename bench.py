@@ -303,6 +303,13 @@ def run_b200_arm(args):
     fr = [n] * B
     of = [ms_framing(n, RATE)] * B
     pidx = [0] * B
+    # A device-resident batch is cut into as few groups as the library's workspace limit allows (64 GB unless told
+    # otherwise); longer groups mean longer compressor tiles behind the same warm-up, so hand it what this GPU has free.
+    torch.cuda.empty_cache()
+    free_b, _ = torch.cuda.mem_get_info(local)
+    ws_limit = min(int(free_b) - (24 << 30), 112 << 30)
+    if ws_limit > (64 << 30):
+        eng.set_workspace_limit(ws_limit)
 
     def barrier():
         if world > 1:

@@ -142,7 +142,9 @@ int b200m_set_segment_tiles(b200m_handle *h, int chain_tiles, int kweight_tiles)
 /* Which kernel runs ENG:117-206: 1 = k_chain (one CTA of eight warps per time segment), 2 = k_chainw (every
  * warp on its own segment: no CTA barriers, shuffle-only exchanges; needs eight times as many segments, so
  * its warm-up share is only small on large batches), 0 = automatic (k_chainw when every warp still gets
- * a run of >= 8 warm-up lengths; environment variable B200M_CHAIN_KERNEL presets it).  Results do not depend on it. */
+ * a run of >= 4 warm-up lengths; environment variable B200M_CHAIN_KERNEL presets it).  The K-weighting ahead of the
+ * loudness measurement (ENG:214-218) has the same two shapes, k_kweight and k_kweightw, and follows the same setting
+ * (B200M_KWEIGHT_KERNEL presets it alone).  Results do not depend on it. */
 int b200m_set_chain_kernel(b200m_handle *h, int mode);
 /* Host-buffer pipeline of b200m_master_batch: with host PCM the batch is cut into groups of
  * tracks and the H2D copy of group g+1 / D2H copy of group g-1 run on side streams while the

@@ -60,6 +60,7 @@ struct b200m_handle {
     // time segmentation of k_chain / k_kweight: 0 = automatic, < 0 = off, > 0 = tiles per segment
     int seg_chain = 0, seg_kweight = 0;
     int chain_kernel = 0;            // 0 = automatic, 1 = k_chain (a CTA per segment), 2 = k_chainw (a warp per segment)
+    int kweight_kernel = 0;          // the same choice for k_kweight / k_kweightw (b200m_set_chain_kernel sets both)
     int detect_kernel = 0;           // 0 = automatic (k_detectw where the look-back fits its ring), 1 = k_detect always (B200M_DETECT_KERNEL: experiments, tests)
     int chain_waves = 4;             // k_chainw: the most resident waves of warps a group is cut into (B200M_CHAIN_WAVES)
     bool chain_slut_ok = true;       // k_chainw may take its 16-warp shape (B200M_CHAIN_SLUT=0 switches it off: experiments)
@@ -382,6 +383,33 @@ static void make_segments_w(std::vector<SegDesc> &out, int owner, int64_t frames
     } else {
         out.push_back({0, 0, owner, 0});
     }
+}
+
+// Segment length (in warp tiles) for a kernel whose warps each walk one segment, `resident` of them at a time: the
+// kernel's time is waves x (longest segment + warm-up), so for w = 1 .. max_waves take the shortest length whose
+// segment count still fits w resident waves and keep the cheapest (a few segments beyond a wave cost a whole extra
+// pass).  0 when nothing fits.
+static double plan_warp_segments(const std::vector<int64_t> &wtiles, double warm_tiles, double min_len, int max_waves, double resident)
+{
+    int64_t total_wtiles = 0;
+    for (int64_t nt : wtiles) total_wtiles += nt;
+    double best_len = 0, best_cost = 1e300;
+    for (int w = 1; w <= max_waves; ++w) {
+        const double cap = resident * w;
+        double len = std::max(min_len, std::ceil((double)total_wtiles / cap));
+        for (int it = 0; it < 200; ++it) {
+            double total = 0;
+            for (int64_t nt : wtiles) total += nt > 0 ? std::ceil((double)nt / len) : 0;
+            if (total <= cap) break;
+            len = std::ceil(len * std::max(1.003, total / cap));
+        }
+        double total = 0, longest = 0;
+        for (int64_t nt : wtiles) if (nt > 0) { const double n = std::ceil((double)nt / len); total += n; longest = std::max(longest, std::ceil((double)nt / n)); }
+        if (total > cap) continue;
+        const double cost = w * (longest + warm_tiles);
+        if (cost < best_cost) { best_cost = cost; best_len = len; }
+    }
+    return best_len;
 }
 
 static int auto_seg_tiles(int64_t total_tiles, int lo, int hi)
@@ -729,6 +757,7 @@ extern "C" int b200m_create(int device, b200m_handle **out)
     h = new b200m_handle();
     h->device = device;
     if (const char *ck = std::getenv("B200M_CHAIN_KERNEL")) h->chain_kernel = std::max(0, std::min(2, std::atoi(ck)));   // test / experiment override
+    if (const char *ck = std::getenv("B200M_KWEIGHT_KERNEL")) h->kweight_kernel = std::max(0, std::min(2, std::atoi(ck)));
     if (const char *ck = std::getenv("B200M_CHAIN_SLUT")) h->chain_slut_ok = std::atoi(ck) != 0;
     if (const char *ck = std::getenv("B200M_DETECT_KERNEL")) h->detect_kernel = std::atoi(ck);
     if (const char *ck = std::getenv("B200M_CHAIN_WAVES")) h->chain_waves = std::max(1, std::min(16, std::atoi(ck)));
@@ -877,6 +906,7 @@ extern "C" int b200m_set_chain_kernel(b200m_handle *h, int mode)
 {
     if (!h || mode < 0 || mode > 2) return B200M_ERR_INVALID;
     h->chain_kernel = mode;
+    h->kweight_kernel = mode;
     return B200M_OK;
 }
 
@@ -949,13 +979,14 @@ struct Group {
     const SegDesc *d_csegs = nullptr, *d_ksegs = nullptr;   // k_chain / k_kweight segments
     int n_csegs = 0, n_ksegs = 0;
     bool chain_warps = false;        // csegs are warp segments (k_chainw)
+    bool kw_warps = false;           // ksegs are warp segments (k_kweightw)
     bool chain_slut = false;         // ... in its 16-warp shape around a shared-memory exciter table (padded to whole CTAs, d_cta_iters)
     const int32_t *d_cta_iters = nullptr;
     int single_plan = -1;            // >= 0: every stream of the group uses this plan (its tables travel as a kernel parameter)
 };
 
 #ifndef B200M_COMP_CTAS
-#define B200M_COMP_CTAS 4           // resident CTAs per SM (48 KB of shared memory each) k_comp's automatic tile length aims at
+#define B200M_COMP_CTAS B200M_COMP_MINB   // resident CTAs per SM (42 KB of shared memory each) k_comp's automatic tile length aims at
 #endif
 static RecurParams recur_params(const b200m_handle *h, const Group &g, int nbands, int band_base)
 {
@@ -1085,7 +1116,11 @@ static int launch_loudness(b200m_handle *h, const Group &g, const int16_t *d_pro
 #define LAUNCH_KW(CHN, INT, SRC) do { \
         if (pt) LAUNCH("k_kweight", k_kweight<CHN, INT, true><<<g.n_ksegs, KNT, kweight_smem_bytes(), h->stream>>>(SRC, g.d_tracks, g.d_ksegs, h->d_plans, d_kw, kt)); \
         else    LAUNCH("k_kweight", k_kweight<CHN, INT, false><<<g.n_ksegs, KNT, kweight_smem_bytes(), h->stream>>>(SRC, g.d_tracks, g.d_ksegs, h->d_plans, d_kw, kt)); } while (0)
-        if (d_mono)         LAUNCH_KW(1, float, d_mono);
+        if (g.kw_warps && pt && !d_mono) {
+            if (g.ch == 2) LAUNCH("k_kweight", k_kweightw<2><<<g.n_ksegs, 32, KwW<2>::SMEM, h->stream>>>(d_proc, g.d_tracks, g.d_ksegs, h->d_plans, d_kw, kt));
+            else           LAUNCH("k_kweight", k_kweightw<1><<<g.n_ksegs, 32, KwW<1>::SMEM, h->stream>>>(d_proc, g.d_tracks, g.d_ksegs, h->d_plans, d_kw, kt));
+        }
+        else if (d_mono)    LAUNCH_KW(1, float, d_mono);
         else if (g.ch == 2) LAUNCH_KW(2, int16_t, d_proc);
         else                LAUNCH_KW(1, int16_t, d_proc);
 #undef LAUNCH_KW
@@ -1219,22 +1254,7 @@ static void plan_group(const b200m_handle *h, GroupPlan &gp, bool in_dev, bool o
         for (size_t i = 0; i < gp.streams.size(); ++i) { wtiles[i] = (gp.streams[i].out_frames + wt - 1) / wt; total_wtiles += wtiles[i]; }
         const double warm_tiles = std::ceil(std::max(max_warm, 1.0) / wt);
         const double min_len = std::max(8.0, 4.0 * std::max(warm_tiles, 1.0));      // segment length in warp tiles
-        double best_len = 0, best_cost = 1e300;
-        for (int w = 1; w <= h->chain_waves && bounded; ++w) {
-            const double cap = 148.0 * 16 * w;
-            double len = std::max(min_len, std::ceil((double)total_wtiles / cap));
-            for (int it = 0; it < 200; ++it) {
-                double total = 0;
-                for (int64_t nt : wtiles) total += nt > 0 ? std::ceil((double)nt / len) : 0;
-                if (total <= cap) break;
-                len = std::ceil(len * std::max(1.003, total / cap));
-            }
-            double total = 0, longest = 0;
-            for (int64_t nt : wtiles) if (nt > 0) { const double n = std::ceil((double)nt / len); total += n; longest = std::max(longest, std::ceil((double)nt / n)); }
-            if (total > cap) continue;
-            const double cost = w * (longest + warm_tiles);
-            if (cost < best_cost) { best_cost = cost; best_len = len; }
-        }
+        double best_len = bounded ? plan_warp_segments(wtiles, warm_tiles, min_len, h->chain_waves, 148.0 * 16) : 0;
         const bool enough = (double)total_wtiles / min_len >= 148.0 * 16;     // a resident wave of warps, each with a run of >= 4 warm-ups
         g.chain_warps = bounded && h->seg_chain >= 0 && (h->chain_kernel == 2 || (h->chain_kernel == 0 && enough));
         if (best_len == 0) best_len = min_len;
@@ -1281,9 +1301,37 @@ static void plan_group(const b200m_handle *h, GroupPlan &gp, bool in_dev, bool o
             for (size_t i = 0; i < gp.streams.size(); ++i)
                 make_segments(gp.csegs, (int)i, gp.streams[i].out_frames, TILE, chain_warm_frames(plans[gp.streams[i].plan]), cs);
         }
-        for (size_t i = 0; i < gp.tracks.size(); ++i)
-            if (plans[gp.tracks[i].plan].has_lufs)
-                make_segments(gp.ksegs, (int)i, gp.tracks[i].frames, KTILE, kweight_warm_frames(plans[gp.tracks[i].plan]), ks);
+        // k_kweightw: the same idea for the K-weighting (one warp per segment of a track, 148 x B200M_KWW_OCC resident)
+        {
+            constexpr int kwt = KwW<2>::WT;
+            std::vector<int64_t> ktl(gp.tracks.size(), 0);
+            int64_t ktotal = 0;
+            double kwarm = 0;
+            bool kbounded = true;
+            for (size_t i = 0; i < gp.tracks.size(); ++i) {
+                if (!plans[gp.tracks[i].plan].has_lufs) continue;
+                ktl[i] = (gp.tracks[i].frames + kwt - 1) / kwt; ktotal += ktl[i];
+                const double w = kweight_warm_frames(plans[gp.tracks[i].plan]);
+                if (!(w < 1e6)) kbounded = false;
+                kwarm = std::max(kwarm, w);
+            }
+            const double kwarm_tiles = std::ceil(std::max(kwarm, 1.0) / kwt);
+            const double kmin_len = std::max(8.0, 4.0 * kwarm_tiles);
+            const double resident = 148.0 * B200M_KWW_OCC;
+            const bool kenough = (double)ktotal / kmin_len >= resident;
+            g.kw_warps = kbounded && h->seg_kweight >= 0 && (h->kweight_kernel == 2 || (h->kweight_kernel == 0 && kenough));
+            if (g.kw_warps) {
+                double len = h->seg_kweight > 0 ? (double)h->seg_kweight * (KTILE / kwt) : plan_warp_segments(ktl, kwarm_tiles, kmin_len, h->chain_waves, resident);
+                if (len == 0) len = kmin_len;
+                for (size_t i = 0; i < gp.tracks.size(); ++i)
+                    if (plans[gp.tracks[i].plan].has_lufs && gp.tracks[i].frames > 0)
+                        make_segments_w(gp.ksegs, (int)i, gp.tracks[i].frames, kwt, kweight_warm_frames(plans[gp.tracks[i].plan]), (int)std::min<double>(1 << 20, len));
+            } else {
+                for (size_t i = 0; i < gp.tracks.size(); ++i)
+                    if (plans[gp.tracks[i].plan].has_lufs)
+                        make_segments(gp.ksegs, (int)i, gp.tracks[i].frames, KTILE, kweight_warm_frames(plans[gp.tracks[i].plan]), ks);
+            }
+        }
         g.n_csegs = (int)gp.csegs.size(); g.n_ksegs = (int)gp.ksegs.size();
     }
     gp.F = F; gp.Fp = Fp; gp.in_total = in_total; gp.zoff = zoff;

@@ -707,31 +707,36 @@ constexpr int DT = B200M_DT;    // frames per tile
 constexpr int DNT = B200M_DNT;
 
 __device__ __forceinline__ unsigned window_rms_rn(unsigned long long S, unsigned n, float rn);
+// rcp.approx(n), scaled down by 2^-20 (see window_rms_rn)
+__device__ __forceinline__ float window_rcp(unsigned n)
+{
+    float rn;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rn) : "f"((float)n));
+    return __fmul_rn(rn, 1.0f - 0x1p-20f);
+}
 __device__ __forceinline__ unsigned window_rms(unsigned long long S, unsigned n)
 {
     if (n == 0) return 0u;
-    // largest r with r*r*n <= S  ==  (unsigned)sqrt((double)S / n): the quotient is a
-    // multiple of 1/n, so it can never sit within double rounding of a perfect square
-    // without being one.
-    // MUFU-grade estimate: (float)S, rcp.approx, the product and sqrt.approx carry at most
-    // 2^-24 + 2^-23 + 2^-24 + 2^-23 < 4e-7 of relative error between them (half of the first three
-    // survives the root), i.e. < 0.01 absolute at r <= 32768, so its floor is off by at most ONE.
-    // One exact, branch-free correction settles it: lo = r^2 n <= S < (r + 1)^2 n = lo + (2r + 1) n.
-    // (n <= 2 * 8192 frames of look-back: (2r + 1) n < 2^31; r^2 <= 2^30; S <= n 2^30 < 2^45.)
-    float rn;
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rn) : "f"((float)n));
-    return window_rms_rn(S, n, rn);
+    return window_rms_rn(S, n, window_rcp(n));
 }
 
-// the same with rn = rcp.approx(n) supplied (n > 0): n is the same for every frame past the look-back
+// largest r with r*r*n <= S  ==  (unsigned)sqrt((double)S / n): the quotient is a multiple of 1/n, so it
+// can never sit within double rounding of a perfect square without being one.  n > 0, rn = window_rcp(n)
+// (n is the same for every frame past the look-back).
+// MUFU-grade estimate from BELOW: (float)S, rcp.approx, the two products and sqrt.approx carry at most
+// 2^-24 + 2^-23 + 2^-24 + 2^-24 of relative error on the radicand (half of it survives the root) and 2^-23 on
+// the root, < 2.8e-7 together; the factor 1 - 2^-20 on the radicand lowers the root by 4.8e-7.  So the estimate
+// is below the true root by between 2.0e-7 and 7.6e-7 of it, < 0.025 absolute at r <= 32768: its floor is r or
+// r - 1, never more (an exact square lands on r - 1), and ONE exact compare settles it: S >= (r + 1)^2 n.
+// The floor itself is an add (round down) of 2^23: F2I goes through the quarter-rate conversion unit.
+// (n <= 2 * 8192 frames of look-back; (r + 1)^2 <= 2^30; S <= n 2^30 < 2^45.)
 __device__ __forceinline__ unsigned window_rms_rn(unsigned long long S, unsigned n, float rn)
 {
     float q;
     asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(q) : "f"(__fmul_rn((float)S, rn)));
-    unsigned r = min((unsigned)q, 32768u);
-    const unsigned long long lo = (unsigned long long)(r * r) * n;
-    const unsigned long long hi = lo + (unsigned long long)((2u * r + 1u) * n);
-    r += (unsigned)(S >= hi) - (unsigned)(S < lo);
+    unsigned r = __float_as_uint(__fadd_rd(q, 8388608.0f)) & 0x7fffffu;
+    const unsigned r1 = r + 1u;
+    r += (unsigned)(S >= (unsigned long long)(r1 * r1) * n);
     return r;
 }
 
@@ -867,7 +872,7 @@ k_detect(const StreamDesc *__restrict__ streams, const PlanDev *__restrict__ pla
     const int nvalid = min(DT, sd.out_frames - t0);
     const unsigned nH = (unsigned)CH * (unsigned)H;
     float rnH = 0.0f;
-    if (nH) asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rnH) : "f"((float)nH));
+    if (nH) rnH = window_rcp(nH);
     for (int c0 = wid * 128; c0 < ((nvalid + 127) & ~127); c0 += (DNT / 32) * 128) {      // whole warps
         unsigned m4 = 0u;
 #pragma unroll
@@ -923,7 +928,7 @@ k_detectw(const StreamDesc *__restrict__ streams, const PlanDev *__restrict__ pl
     const int H = pl->band[band].look, hold_max = pl->band[band].hold_max;
     const unsigned nH = (unsigned)CH * (unsigned)H;
     float rnH = 0.0f;
-    if (nH) asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rnH) : "f"((float)nH));
+    if (nH) rnH = window_rcp(nH);
     const int16_t *__restrict__ src = bp.band[band] + sd.out_off * CH;
     uint16_t *__restrict__ dst = bp.rms[band] + sd.out_off;
     uint32_t *__restrict__ hold = bp.hold[band] + sd.blk_off;
@@ -1086,7 +1091,7 @@ k_detectw(const StreamDesc *__restrict__ streams, const PlanDev *__restrict__ pl
 #define B200M_WARM_RELEASES 1.75
 #endif
 #ifndef B200M_COMP_MINB
-#define B200M_COMP_MINB 4           // minimum resident CTAs per SM promised to the compiler for k_comp (register cap)
+#define B200M_COMP_MINB 4           // resident CTAs per SM k_comp is built for (5 fit since the RMS rows lost their own storage, but on a 64-track group the shorter tiles -- 23 k frames behind a 16 k warm-up -- cost more than the extra warps bring: 10.7 vs 8.7 ms)
 #endif
 #ifndef B200M_COMP_UNROLL
 #define B200M_COMP_UNROLL 2         // 128-bit sample words (4 stereo frames each) per iteration of the lane-serial walk
@@ -1101,8 +1106,11 @@ struct RecurWarpSmem {              // one per warp = per band of the CTA's 32 (
     double m[32][34];               // M rows in (phase B, row-wise), read back lane-wise (128-bit) by the recurrence, which leaves
                                     // the block's compressed frames in the first 128 bytes of each row
     unsigned smp[32][SROW];         // band samples of the block being worked on: one packed frame per word (mono: two)
-    uint16_t rms[32][32];           // RMS rows of the block being worked on
+                                    // RMS rows (64 bytes each) have no storage of their own: during the warm-up they are staged
+                                    // in the (idle) sample rows, afterwards in bytes 128..191 of the M rows, which the walk has
+                                    // consumed by the time the next block's RMS values are asked for (rms_row below)
     unsigned long long base_curve[32];
+    double etab[32];                // 2^(j/32) for the gains (exp10_gain)
     ulonglong2 row[32];             // per lane: {first workspace frame of its current block, frames to produce (0 = none)}:
                                     // one 16-byte broadcast load per row in the row-wise overlay
 };
@@ -1151,43 +1159,58 @@ __device__ __forceinline__ double recur_step_pos(double a, double M, double inc,
 // audioop.mul: floor(fbound(sample * factor)), fbound clipping to [-32768, 32767].  The factor here is a
 // gain in [0, 1] -- the attenuation is never negative (the recurrence clamps at +0) and exp10_gain(x <= 0)
 // <= 1 -- so |v g| <= |v| <= 32768 and the floor is in range without the clip.
+// The floor is an add, rounded down, of 1.5 * 2^52 (the integer then sits in the low word, two's complement):
+// F2I.F64 occupies the fp64 pipe for 6.5 cycles per warp against DADD's 2.5 (scripts/ubench/cvt_rate.cu).
 __device__ __forceinline__ int mul_floor16_le1(int v, double g)
 {
-    return __double2int_rd(__dmul_rn((double)v, g));
+    return __double2loint(__dadd_rd(__dmul_rn((double)v, g), 6755399441055744.0));
 }
 
 // 10^x for the gain of an attenuation: x = -att / 20 <= 0 and far from underflow (att is at most
 // slope * 20 log10(32768 / thresh_rms) dB; the caller falls back to the library routine beyond
-// 10^-300).  x log2(10) is split as n + f with the 1.5 * 2^52 trick, r = x - n log10(2) (two-piece
-// constant, |r| <= 0.1506), 10^r by its degree-13 Taylor polynomial (next term < 5e-18) in Horner
-// form with the coefficients as constant-bank operands (the library routine spends 28 uniform-
-// register moves per call on its immediates), and 2^n goes straight into the exponent field.
-// Max error measured against 60-digit arithmetic: 1.05 ulp, the class of the library's exp10
-// (1 ulp) -- both far inside what floor(sample * gain) can see.
-__constant__ double c_exp10[18] = {
+// 10^-300).  32 x log2(10) is split as m + f with the 1.5 * 2^52 trick, m = 32 n + j;
+// r = x - m log10(2) / 32 (two-piece constant, |r| <= 0.0047); 10^x = 2^n * T[j] * 10^r with
+// T[j] = 2^(j/32) from a 32-entry table (`tab`: shared memory in k_comp, lanes gather) and
+// 10^r - 1 = r q(r), q the degree-5 Taylor quotient (next term < 4e-18), so the result is ONE
+// fused multiply-add T + T * (r q): the table entry's rounding and the final rounding are the only
+// errors of size.  2^n goes straight into the exponent field.  Coefficients are constant-bank
+// operands.  Eleven fp64 operations (the degree-13 polynomial without a table took seventeen).
+// Max error against 60-digit arithmetic: 0.99 ulp (scripts/exp10_check.py simulates this
+// sequence with exact FMA semantics), the class of the library's exp10 -- far inside what
+// floor(sample * gain) can see.
+__constant__ double c_exp10[11] = {
     0x1.0000000000000p+0, 0x1.26bb1bbb55516p+1, 0x1.53524c73cea69p+1, 0x1.0470591de2ca4p+1,
-    0x1.2bd7609fd98c4p+0, 0x1.1429ffd1d4d76p-1, 0x1.a7ed70847c8b6p-3, 0x1.16e4dfc333a87p-4,
-    0x1.4116b05fdaa5dp-6, 0x1.4897c45d93d42p-8, 0x1.2ea52b2d182afp-10, 0x1.facfd5d909d64p-13,
-    0x1.84fe12df80be4p-15, 0x1.1398ad2c41708p-17,
-    0x1.a934f0979a371p+1,       // [14] log2(10)
-    -0x1.34413509f79ffp-2,      // [15] -log10(2), high part
-    0x1.9dc1da994fd21p-59,      // [16] -log10(2), low part
-    6755399441055744.0};        // [17] 1.5 * 2^52
+    0x1.2bd7609fd98c4p+0, 0x1.1429ffd1d4d76p-1, 0x1.a7ed70847c8b6p-3,
+    0x1.a934f0979a371p+6,       // [7] 32 log2(10)
+    -0x1.34413509f79ffp-7,      // [8] -log10(2) / 32, high part
+    0x1.9dc1da994fd21p-64,      // [9] -log10(2) / 32, low part
+    6755399441055744.0};        // [10] 1.5 * 2^52
+__device__ const double g_exp10_tab[32] = {
+    0x1.0000000000000p+0, 0x1.059b0d3158574p+0, 0x1.0b5586cf9890fp+0, 0x1.11301d0125b51p+0, 0x1.172b83c7d517bp+0, 0x1.1d4873168b9aap+0,
+    0x1.2387a6e756238p+0, 0x1.29e9df51fdee1p+0, 0x1.306fe0a31b715p+0, 0x1.371a7373aa9cbp+0, 0x1.3dea64c123422p+0, 0x1.44e086061892dp+0,
+    0x1.4bfdad5362a27p+0, 0x1.5342b569d4f82p+0, 0x1.5ab07dd485429p+0, 0x1.6247eb03a5585p+0, 0x1.6a09e667f3bcdp+0, 0x1.71f75e8ec5f74p+0,
+    0x1.7a11473eb0187p+0, 0x1.82589994cce13p+0, 0x1.8ace5422aa0dbp+0, 0x1.93737b0cdc5e5p+0, 0x1.9c49182a3f090p+0, 0x1.a5503b23e255dp+0,
+    0x1.ae89f995ad3adp+0, 0x1.b7f76f2fb5e47p+0, 0x1.c199bdd85529cp+0, 0x1.cb720dcef9069p+0, 0x1.d5818dcfba487p+0, 0x1.dfc97337b9b5fp+0,
+    0x1.ea4afa2a490dap+0, 0x1.f50765b6e4540p+0};
 __device__ __noinline__ double exp10_far(double x) { return exp10(x); }
 // FAR = false: the caller knows x > -300 (BandDev::att_bounded) -- no branch, so that several gains of one thread
 // form independent chains the scheduler can interleave.
 template <bool FAR>
-__device__ __forceinline__ double exp10_gain(double x)
+__device__ __forceinline__ double exp10_gain(double x, const double *__restrict__ tab)
 {
     if (FAR && !(x > -300.0)) return exp10_far(x);
-    const double t = fma(x, c_exp10[14], c_exp10[17]);
-    const double nf = __dsub_rn(t, c_exp10[17]);
-    double r = fma(nf, c_exp10[15], x);
-    r = fma(nf, c_exp10[16], r);
-    double p = c_exp10[13];
+    const double t = fma(x, c_exp10[7], c_exp10[10]);
+    const double mf = __dsub_rn(t, c_exp10[10]);
+    double r = fma(mf, c_exp10[8], x);
+    r = fma(mf, c_exp10[9], r);
+    double p = c_exp10[6];
 #pragma unroll
-    for (int k = 12; k >= 0; --k) p = fma(p, r, c_exp10[k]);
-    return __hiloint2double(__double2hiint(p) + (__double2loint(t) << 20), __double2loint(p));
+    for (int k = 5; k >= 1; --k) p = fma(p, r, c_exp10[k]);
+    const double sr = __dmul_rn(p, r);
+    const int m = __double2loint(t);
+    const double T = tab[m & 31];
+    const double v = fma(T, sr, T);
+    return __hiloint2double(__double2hiint(v) + ((m >> 5) << 20), __double2loint(v));
 }
 
 // pydub: frame * db_to_float(-attenuation), db_to_float(db) = 10 ** (db / 20).  The quotient att / 20 is
@@ -1196,11 +1219,11 @@ __device__ __forceinline__ double exp10_gain(double x)
 // multiplies only `if attenuation != 0.0`; 10^-0 is exactly 1.0 here (the polynomial at r = 0 is its
 // constant term) and floor(v * 1.0) == v, so the test needs no branch.
 template <bool FAR>
-__device__ __forceinline__ double gain_of_att(double a)
+__device__ __forceinline__ double gain_of_att(double a, const double *__restrict__ tab)
 {
     const double q = __dmul_rn(a, 0.05);
     const double r = fma(-q, 20.0, a);
-    return exp10_gain<FAR>(-fma(r, 0.05, q));
+    return exp10_gain<FAR>(-fma(r, 0.05, q), tab);
 }
 
 // one frame (packed: CH == 2: L | R << 16, CH == 1: the low 16 bits) through audioop.mul
@@ -1270,6 +1293,7 @@ k_comp(const StreamDesc *__restrict__ streams, const PlanDev *__restrict__ plans
     double *bend_b = nullptr;
     double a = 0.0;
     W.base_curve[lane] = 0ull;
+    W.etab[lane] = g_exp10_tab[lane];
     bool okfast = true;
     if (live) {
         const StreamDesc sd = streams[s];
@@ -1317,6 +1341,10 @@ k_comp(const StreamDesc *__restrict__ streams, const PlanDev *__restrict__ plans
     // work and the ragged last block of a stream are written by their owner: zeros (r = 0 gives
     // M = 0, a hold, i.e. an identity step, so partial rows need no branches later) plus whatever
     // valid elements there are.  Returns whether this lane's block can change its state.
+    bool warming = P.mode == 0;                 // where RMS rows are staged (see RecurWarpSmem)
+    auto rms_row = [&](int q) -> uint16_t * {
+        return warming ? reinterpret_cast<uint16_t *>(W.smp[q]) : reinterpret_cast<uint16_t *>(&W.m[q][16]);
+    };
     auto issue_rms = [&](int cbn, bool valid) -> bool {
         const bool on_n = valid && cbn < eb;
         const int i0n = cbn << 5;
@@ -1326,7 +1354,7 @@ k_comp(const StreamDesc *__restrict__ streams, const PlanDev *__restrict__ plans
         const bool rms16 = (reinterpret_cast<unsigned long long>(rms_b) & 15ull) == 0;    // chunk starts at odd rates may not be
         const uint16_t *srcp = (work_n && cntn == 32 && rms16) ? rms_b + i0n : nullptr;
         if (srcp == nullptr) {
-            uint16_t *row = &W.rms[lane][0];
+            uint16_t *row = rms_row(lane);
 #pragma unroll
             for (int j = 0; j < 4; ++j) reinterpret_cast<uint4 *>(row)[j] = make_uint4(0u, 0u, 0u, 0u);
             if (work_n) {
@@ -1339,7 +1367,7 @@ k_comp(const StreamDesc *__restrict__ streams, const PlanDev *__restrict__ plans
         for (int q0 = 0; q0 < 32; q0 += 8) {
             const unsigned long long p = __shfl_sync(FULL, (unsigned long long)srcp, q0 + sub);
             if (p != 0ull) {
-                const unsigned sa = (unsigned)__cvta_generic_to_shared(&W.rms[q0 + sub][piece * 8]);
+                const unsigned sa = (unsigned)__cvta_generic_to_shared(rms_row(q0 + sub) + piece * 8);
                 asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(p + 16ull * piece) : "memory");
             }
         }
@@ -1389,8 +1417,8 @@ k_comp(const StreamDesc *__restrict__ streams, const PlanDev *__restrict__ plans
             for (int j = 0; j < B200M_RECUR_GB; ++j) {
                 const ulonglong2 cp2 = *reinterpret_cast<const ulonglong2 *>(&W.base_curve[(q0 + j) & ~1]);   // one load serves two rows
                 const double *curve = reinterpret_cast<const double *>((j & 1) ? cp2.y : cp2.x);
-                const unsigned r = W.rms[q0 + j][lane];
-                v[j] = (curve != nullptr && r != 0u) ? __ldg(curve + r) : 0.0;
+                const unsigned r = rms_row(q0 + j)[lane];
+                v[j] = r != 0u ? __ldg(curve + r) : 0.0;    // a row without a curve (a lane without work) is all zeros
             }
 #pragma unroll
             for (int j = 0; j < B200M_RECUR_GB; ++j) W.m[q0 + j][lane] = v[j];
@@ -1467,6 +1495,7 @@ k_comp(const StreamDesc *__restrict__ streams, const PlanDev *__restrict__ plans
         asm volatile("cp.async.wait_group 0;" ::: "memory");
         __syncwarp();
     }
+    warming = false;
     const double a_start = a;
 
     // ---- the tile itself: the CTA's bands in lockstep over its 32-frame blocks ---------------------------------
@@ -1496,7 +1525,6 @@ k_comp(const StreamDesc *__restrict__ streams, const PlanDev *__restrict__ plans
         const bool quiet = !__any_sync(FULL, on && (work || __double_as_longlong(a) != 0ll));
         if (any_work) phase_b();
         __syncwarp();
-        work = issue_rms(cb + 1, on);                               // the RMS rows of the next block start moving now
         {
             uint4 *crow = reinterpret_cast<uint4 *>(W.m[lane]);      // compressed frames: word w overwrites M[2w], M[2w+1] (consumed)
             const double2 *mrow = reinterpret_cast<const double2 *>(W.m[lane]);
@@ -1525,7 +1553,7 @@ k_comp(const StreamDesc *__restrict__ streams, const PlanDev *__restrict__ plans
                                 for (int i = 0; i < 4; ++i) {
                                     a = recur_step_pos(a, Mv[i], div_const(Mv[i], A, rA, true), div_const(Mv[i], R, rR, true));
                                     if (DBG && att_dbg != nullptr && 4 * w + i < cnt) att_dbg[fdbg + 4 * w + i] = a;
-                                    v[i] = mul_frame<2>(sv[i], gain_of_att<false>(a));
+                                    v[i] = mul_frame<2>(sv[i], gain_of_att<false>(a, W.etab));
                                 }
                             } else {                                 // mono: two frames per 32-bit word
 #pragma unroll
@@ -1533,10 +1561,10 @@ k_comp(const StreamDesc *__restrict__ streams, const PlanDev *__restrict__ plans
                                     const double2 M = mrow[4 * w + i];
                                     a = recur_step_pos(a, M.x, div_const(M.x, A, rA, true), div_const(M.x, R, rR, true));
                                     if (DBG && att_dbg != nullptr && 8 * w + 2 * i < cnt) att_dbg[fdbg + 8 * w + 2 * i] = a;
-                                    const unsigned lo = mul_frame<1>(sv[i] & 0xffffu, gain_of_att<false>(a));
+                                    const unsigned lo = mul_frame<1>(sv[i] & 0xffffu, gain_of_att<false>(a, W.etab));
                                     a = recur_step_pos(a, M.y, div_const(M.y, A, rA, true), div_const(M.y, R, rR, true));
                                     if (DBG && att_dbg != nullptr && 8 * w + 2 * i + 1 < cnt) att_dbg[fdbg + 8 * w + 2 * i + 1] = a;
-                                    const unsigned hi = mul_frame<1>(sv[i] >> 16, gain_of_att<false>(a));
+                                    const unsigned hi = mul_frame<1>(sv[i] >> 16, gain_of_att<false>(a, W.etab));
                                     v[i] = lo | (hi << 16);
                                 }
                             }
@@ -1555,7 +1583,7 @@ k_comp(const StreamDesc *__restrict__ streams, const PlanDev *__restrict__ plans
                                 for (int i = 0; i < 4; ++i) {
                                     a = recur_step(a, Mv[i], div_const(Mv[i], A, rA, ex), div_const(Mv[i], R, rR, ex));
                                     if (DBG && att_dbg != nullptr && 4 * w + i < cnt) att_dbg[fdbg + 4 * w + i] = a;
-                                    v[i] = mul_frame<2>(sv[i], gain_of_att<true>(a));
+                                    v[i] = mul_frame<2>(sv[i], gain_of_att<true>(a, W.etab));
                                 }
                             } else {
 #pragma unroll 1
@@ -1563,10 +1591,10 @@ k_comp(const StreamDesc *__restrict__ streams, const PlanDev *__restrict__ plans
                                     const double2 M = mrow[4 * w + i];
                                     a = recur_step(a, M.x, div_const(M.x, A, rA, ex), div_const(M.x, R, rR, ex));
                                     if (DBG && att_dbg != nullptr && 8 * w + 2 * i < cnt) att_dbg[fdbg + 8 * w + 2 * i] = a;
-                                    const unsigned lo = mul_frame<1>(sv[i] & 0xffffu, gain_of_att<true>(a));
+                                    const unsigned lo = mul_frame<1>(sv[i] & 0xffffu, gain_of_att<true>(a, W.etab));
                                     a = recur_step(a, M.y, div_const(M.y, A, rA, ex), div_const(M.y, R, rR, ex));
                                     if (DBG && att_dbg != nullptr && 8 * w + 2 * i + 1 < cnt) att_dbg[fdbg + 8 * w + 2 * i + 1] = a;
-                                    const unsigned hi = mul_frame<1>(sv[i] >> 16, gain_of_att<true>(a));
+                                    const unsigned hi = mul_frame<1>(sv[i] >> 16, gain_of_att<true>(a, W.etab));
                                     v[i] = lo | (hi << 16);
                                 }
                             }
@@ -1581,7 +1609,8 @@ k_comp(const StreamDesc *__restrict__ streams, const PlanDev *__restrict__ plans
             }
         }
         __syncwarp();
-        issue_smp(cb + 1, on);                                      // the samples of the next block (W.smp is consumed)
+        work = issue_rms(cb + 1, on);                               // the next block's RMS rows (into the consumed halves of the M rows)
+        issue_smp(cb + 1, on);                                      // ... and samples (W.smp is consumed)
         if (NB > 1) __syncthreads();                                // every band's compressed rows are in place
         // ---- overlay + store, row-wise: one lane per frame, rows dealt round-robin to the CTA's warps ------------
 #pragma unroll 2
@@ -1722,7 +1751,7 @@ k_comp_fix(const StreamDesc *__restrict__ streams, const PlanDev *__restrict__ p
                 for (int b = 0; b < NB; ++b) {
                     const double at = s_att[wid][b][lane];
                     const int bb = NB == 3 ? b : P.band_base;
-                    const unsigned v = mul_frame<CH>(load_frame<CH>(bp.band[bb], f), gain_of_att<true>(at));
+                    const unsigned v = mul_frame<CH>(load_frame<CH>(bp.band[bb], f), gain_of_att<true>(at, g_exp10_tab));
                     if (bp.att[bb] != nullptr) bp.att[bb][f] = at;
                     acc = b == 0 ? v : add_frame_sat<CH>(acc, v);
                 }
@@ -1871,6 +1900,136 @@ k_kweight(const IN *__restrict__ src_all, const TrackDesc *__restrict__ tracks, 
 constexpr size_t kweight_smem_bytes()
 {
     return 2 * sizeof(SecTab) + (size_t)(KTILE_PAD + (KTILE_PAD & 1)) * 4 + 4 * 8 + 2 * 8 * 2 * 8 + (size_t)KTILE * 4 /* raw tile */;
+}
+
+// =====================================================================================
+// k_kweightw: the same K-weighting for a large batch, one WARP per segment of a track
+// (the shape of k_chainw: one warp per CTA, provably uniform control flow, no CTA barrier
+// in the loop).  A warp tile is 512 frames -- lane j owns frames 16 j .. 16 j + 15 of the
+// mono mean -- the processed PCM of the next tile arrives with cp.async while this one
+// is filtered, the filter tables sit in the constant bank (every plan of a batch has the
+// same K-weighting: it depends on the rate alone) and each lane stores its 16 results
+// as four 16-byte words.  k_kweight (eight warps, a CTA-wide scan and three barriers per
+// 4096 frames) ran at 46 % of the fp64 pipe and half the DRAM rate; small batches, which
+// cannot give 148 x 16 warps a run of four warm-ups each, stay with it.
+// =====================================================================================
+template <int CH> struct KwW {
+    static constexpr int WT = 32 * SEG;                     // frames per warp tile
+    static constexpr int RSTRIDE = CH == 2 ? 20 : 12;       // 32-bit words per lane's 16 raw frames (16 / 8 used): conflict-free LDS.128
+    static constexpr int RAW_WORDS = 32 * RSTRIDE;
+    static constexpr int DEPTH = 3;                         // raw tiles in flight or in use
+    static constexpr size_t SMEM = 2 * 32 * 4 * 8 /* Q[lane] of the two sections */ + (size_t)DEPTH * RAW_WORDS * 4 + 4 * 8 /* carry */;
+};
+#ifndef B200M_KWW_OCC
+#define B200M_KWW_OCC 12           // 168 registers: the two sections' tables live in registers across the loop
+#endif
+template <int CH>
+__global__ void __launch_bounds__(32, B200M_KWW_OCC)
+k_kweightw(const int16_t *__restrict__ src_all, const TrackDesc *__restrict__ tracks, const SegDesc *__restrict__ segs,
+           const PlanDev *__restrict__ plans, float *__restrict__ kw, const __grid_constant__ KwTabsC kt)
+{
+    using W = KwW<CH>;
+    constexpr int WT = W::WT;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double (*sQ)[32][4] = reinterpret_cast<double (*)[32][4]>(smem_raw);
+    unsigned *raw_all = reinterpret_cast<unsigned *>(smem_raw + 2 * 32 * 4 * 8);         // [DEPTH][RAW_WORDS]
+    double *carry = reinterpret_cast<double *>(smem_raw + 2 * 32 * 4 * 8 + (size_t)W::DEPTH * W::RAW_WORDS * 4);
+    const int lane = threadIdx.x;
+    const SegDesc sg = segs[blockIdx.x];
+    const TrackDesc td = tracks[sg.owner];
+    const PlanDev *__restrict__ pl = plans + td.plan;
+    if (!pl->has_lufs || sg.begin >= sg.end) return;                 // CTA-uniform
+    for (int i = lane; i < 2 * 128; i += 32) reinterpret_cast<double *>(sQ)[i] = reinterpret_cast<const double *>(pl->kw[i >> 7].Q)[i & 127];
+    if (lane < 4) carry[lane] = 0.0;
+    __syncwarp();
+    const int16_t *__restrict__ src = src_all + td.off * CH;
+    float *__restrict__ dst = kw + td.off;
+    const bool in16 = (reinterpret_cast<unsigned long long>(src) & 15ull) == 0;
+    const int64_t frames = td.frames;
+
+    // processed PCM of tile t0 -> raw[]: 16-byte pieces (4 stereo / 8 mono frames each), zeros past the end of the track
+    auto fetch = [&](int64_t t0, int slot) {
+        unsigned *raw = raw_all + slot * W::RAW_WORDS;
+        constexpr int FPP = 8 / CH, PPL = 16 / FPP;                   // frames per piece, pieces per lane's 16 frames
+#pragma unroll
+        for (int h = 0; h < PPL; ++h) {
+            const int p = lane + 32 * h;
+            const int64_t gf = t0 + (int64_t)FPP * p;
+            unsigned *d = raw + W::RSTRIDE * (p / PPL) + 4 * (p % PPL);
+            if (in16 && gf + FPP <= frames) {
+                const unsigned sa = (unsigned)__cvta_generic_to_shared(d);
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(src + gf * CH) : "memory");
+            } else {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    if (CH == 2) {
+                        d[k] = gf + k < frames ? reinterpret_cast<const unsigned *>(src)[gf + k] : 0u;
+                    } else {
+                        const unsigned lo = gf + 2 * k < frames ? (unsigned)(unsigned short)src[gf + 2 * k] : 0u;
+                        const unsigned hi = gf + 2 * k + 1 < frames ? (unsigned)(unsigned short)src[gf + 2 * k + 1] : 0u;
+                        d[k] = lo | (hi << 16);
+                    }
+                }
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+
+    const int64_t t_first = max((int64_t)0, sg.begin - sg.warm);
+    // two tiles ahead: with 12 warps per SM one tile in flight per warp leaves the DRAM pipe half empty
+    fetch(t_first, 0);
+    fetch(t_first + WT, 1);
+    int slot = 0;
+    for (int64_t t0 = t_first; t0 < sg.end; t0 += WT) {
+        const bool store = t0 >= sg.begin;                           // warm-up tiles only advance the filter states
+        const int nvalid = store ? (int)min((int64_t)WT, sg.end - t0) : 0;
+        asm volatile("cp.async.wait_group 1;" ::: "memory");
+        __syncwarp();
+        double x[SEG];
+        {
+            const uint4 *rp = reinterpret_cast<const uint4 *>(raw_all + slot * W::RAW_WORDS + W::RSTRIDE * lane);
+            if (CH == 2) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const uint4 w = rp[i];
+                    const unsigned ww[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll      // float32 (vL + vR) / 2 with vL, vR multiples of 2^-15: exact (ENG:214)
+                    for (int k = 0; k < 4; ++k) x[4 * i + k] = (double)((float)(prmt_sx(ww[k], 0x9910u) + prmt_sx(ww[k], 0xbb32u)) * (1.0f / 65536.0f));
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < 2; ++i) {
+                    const uint4 w = rp[i];
+                    const unsigned ww[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        x[8 * i + 2 * k] = (double)((float)prmt_sx(ww[k], 0x9910u) * (1.0f / 32768.0f));
+                        x[8 * i + 2 * k + 1] = (double)((float)prmt_sx(ww[k], 0xbb32u) * (1.0f / 32768.0f));
+                    }
+                }
+            }
+        }
+        // the tile two ahead goes into the third slot (a group is committed every round, so wait_group 1 always
+        // means "the next tile to be read has landed"; past the track's end a fetch is a zero fill)
+        fetch(t0 + 2 * WT, slot == 0 ? 2 : slot - 1);
+        slot = slot == 2 ? 0 : slot + 1;
+        section_round_w<32>(x, kt.sec[0], sQ[0], carry + 0, lane);
+#pragma unroll
+        for (int n = 0; n < SEG; ++n) x[n] = (double)(float)x[n];    // input_data[:, ch] = ... (float32 store between the stages)
+        section_round_w<32>(x, kt.sec[1], sQ[1], carry + 2, lane);
+        if (store) {
+            float *o = dst + t0 + SEG * lane;
+            const int f0 = SEG * lane;
+            if ((reinterpret_cast<unsigned long long>(o) & 15ull) == 0 && f0 + SEG <= nvalid) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                    reinterpret_cast<float4 *>(o)[i] = make_float4((float)x[4 * i], (float)x[4 * i + 1], (float)x[4 * i + 2], (float)x[4 * i + 3]);
+            } else {
+#pragma unroll
+                for (int n = 0; n < SEG; ++n) if (f0 + n < nvalid) o[n] = (float)x[n];
+            }
+        }
+    }
 }
 
 // =====================================================================================
