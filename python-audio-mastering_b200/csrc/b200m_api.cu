@@ -45,6 +45,7 @@ struct b200m_handle {
     std::map<int, std::pair<int32_t *, int>> pw_trees;      // block length -> (device table, smem floats)
     int blocks_smem_floats = 0;                              // max over the current plans
     int hops_smem_floats = 0;                                // the same for the hop trees (0: no plan shares hops)
+    int hops_stage_floats = 0;                               // the longest hop of the current plans (k_hops stages a hop in shared memory), 0 when it would not fit
     // pinned staging for descriptors / small results
     char *pin = nullptr;
     size_t pin_cap = 0;
@@ -336,6 +337,12 @@ static double settle_frames(const b200m_biquad &q)
 
 // Warm-up (frames) that makes a k_chain / k_kweight segment independent of what came before it:
 // the sections of a cascade settle one after the other, parallel branches (LP / HP) together.
+constexpr size_t HOPS_SMEM_MAX = 100 * 1024;                // k_hops: tree values + one staged hop (19 KB at 48 kHz, 77 KB at 192 kHz)
+static size_t hops_smem_bytes(const b200m_handle *h)
+{
+    return (size_t)(h->hops_smem_floats + 4 + h->hops_stage_floats) * 4 + 16;
+}
+
 static double chain_warm_frames(const b200m_plan &p)
 {
     double w = 0;
@@ -649,7 +656,7 @@ static int ensure_plans(b200m_handle *h, const b200m_plan *plans, int n)
     h->plans_key.clear();
     ++h->tab_tick;
     std::vector<PlanDev> host(n);
-    int blocks_smem = 0, hops_smem = 0;
+    int blocks_smem = 0, hops_smem = 0, hops_stage = 0;
     for (int i = 0; i < n; ++i) {
         const b200m_plan &p = plans[i];
         PlanDev &d = host[i];
@@ -677,7 +684,7 @@ static int ensure_plans(b200m_handle *h, const b200m_plan *plans, int n)
                 int hf = 0;
                 rc = get_pw_tree(h, nblk / 4, &d.htree, &hf);
                 if (rc) return rc;
-                if (d.htree) { d.hop = nblk / 4; hops_smem = std::max(hops_smem, hf); }
+                if (d.htree) { d.hop = nblk / 4; hops_smem = std::max(hops_smem, hf); hops_stage = std::max(hops_stage, d.hop); }
             }
         }
         if (p.multiband) {
@@ -721,6 +728,7 @@ static int ensure_plans(b200m_handle *h, const b200m_plan *plans, int n)
     h->plans_host.swap(host);
     h->blocks_smem_floats = blocks_smem;
     h->hops_smem_floats = hops_smem;
+    h->hops_stage_floats = ((size_t)(hops_smem + 4 + hops_stage) * 4 + 16 <= HOPS_SMEM_MAX) ? hops_stage : 0;
     h->plans_key.assign(plans, plans + n);
     return B200M_OK;
 }
@@ -782,12 +790,17 @@ extern "C" int b200m_create(int device, b200m_handle **out)
     if (e == cudaSuccess) e = allow_smem(k_chainw<1, false, false, CW_SLUT, true>, ChainW<1>::SMEM_SLUT_MP);
     if (e == cudaSuccess) e = allow_smem(k_chainw<2, true, false, CW_SLUT, true>, ChainW<2>::SMEM_SLUT_MP);
     if (e == cudaSuccess) e = allow_smem(k_chainw<2, false, false, CW_SLUT, true>, ChainW<2>::SMEM_SLUT_MP);
+    if (e == cudaSuccess) e = allow_smem(k_hops, HOPS_SMEM_MAX);
     if (e == cudaSuccess) e = allow_smem(k_detect<1>, detect_smem_bytes(8192));
     if (e == cudaSuccess) e = allow_smem(k_detect<2>, detect_smem_bytes(8192));
     if (e == cudaSuccess) e = allow_smem(k_comp<1, 1, true>, recur_smem_bytes(1));
     if (e == cudaSuccess) e = allow_smem(k_comp<2, 1, true>, recur_smem_bytes(1));
     if (e == cudaSuccess) e = allow_smem(k_comp<1, 3, false>, recur_smem_bytes(3));
     if (e == cudaSuccess) e = allow_smem(k_comp<2, 3, false>, recur_smem_bytes(3));
+    if (const char *ck = std::getenv("B200M_COMP_CARVEOUT")) {          // experiment: shared-memory carve-out (percent) of the compressor kernel
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_comp<2, 3, false>, cudaFuncAttributePreferredSharedMemoryCarveout, std::atoi(ck));
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_comp<1, 3, false>, cudaFuncAttributePreferredSharedMemoryCarveout, std::atoi(ck));
+    }
     if (e == cudaSuccess) e = allow_smem(k_kweight<1, int16_t, true>, kweight_smem_bytes());
     if (e == cudaSuccess) e = allow_smem(k_kweight<2, int16_t, true>, kweight_smem_bytes());
     if (e == cudaSuccess) e = allow_smem(k_kweight<1, float, true>, kweight_smem_bytes());
@@ -1128,7 +1141,7 @@ static int launch_loudness(b200m_handle *h, const Group &g, const int16_t *d_pro
         // hop sums go to d_zsel (k_gate's scratch, free until then): nblocks + 3 floats in nblocks doubles per track
         const bool hops = h->hops_smem_floats > 0 && g.max_blocks >= 3;
         const dim3 gh(g.max_blocks + 3, g.n_tracks);
-        if (hops) LAUNCH("k_hops", k_hops<<<gh, BNT, (size_t)h->hops_smem_floats * 4 + 16, h->stream>>>(d_kw, g.d_tracks, h->d_plans, d_zsel));
+        if (hops) LAUNCH("k_hops", k_hops<<<gh, BNT, hops_smem_bytes(h), h->stream>>>(d_kw, g.d_tracks, h->d_plans, d_zsel, h->hops_stage_floats));
         if (g.max_blocks > 0) LAUNCH("k_blocks", k_blocks<<<gb, BNT, (size_t)h->blocks_smem_floats * 4 + 16, h->stream>>>(d_kw, g.d_tracks, h->d_plans, hops ? d_zsel : nullptr, d_z));
     }
     LAUNCH("k_gate", k_gate<<<g.n_tracks, GNT, 0, h->stream>>>(g.d_tracks, h->d_plans, d_z, d_zsel, d_loud));
@@ -1894,7 +1907,7 @@ extern "C" int b200m_slice_energies(b200m_handle *h, const int16_t *proc_ext_dev
     else         LAUNCH("k_kweight", k_kweight<1, int16_t, true><<<g.n_ksegs, KNT, kweight_smem_bytes(), h->stream>>>(proc_ext_dev, d_tracks, d_segs, h->d_plans, d_kw, kt));
     const dim3 gb((unsigned)(j1 - j0), 1);
     const bool hops = h->hops_smem_floats > 0 && j1 - j0 >= 3;
-    if (hops) LAUNCH("k_hops", k_hops<<<dim3((unsigned)(j1 - j0 + 3), 1), BNT, (size_t)h->hops_smem_floats * 4 + 16, h->stream>>>(d_kw, d_tracks, h->d_plans, d_hops));
+    if (hops) LAUNCH("k_hops", k_hops<<<dim3((unsigned)(j1 - j0 + 3), 1), BNT, hops_smem_bytes(h), h->stream>>>(d_kw, d_tracks, h->d_plans, d_hops, h->hops_stage_floats));
     LAUNCH("k_blocks", k_blocks<<<gb, BNT, (size_t)h->blocks_smem_floats * 4 + 16, h->stream>>>(d_kw, d_tracks, h->d_plans, hops ? d_hops : nullptr, z_dev));
     CK(cudaGetLastError());
     return B200M_OK;

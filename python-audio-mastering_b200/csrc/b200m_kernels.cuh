@@ -1612,18 +1612,38 @@ k_comp(const StreamDesc *__restrict__ streams, const PlanDev *__restrict__ plans
         work = issue_rms(cb + 1, on);                               // the next block's RMS rows (into the consumed halves of the M rows)
         issue_smp(cb + 1, on);                                      // ... and samples (W.smp is consumed)
         if (NB > 1) __syncthreads();                                // every band's compressed rows are in place
-        // ---- overlay + store, row-wise: one lane per frame, rows dealt round-robin to the CTA's warps ------------
-#pragma unroll 2
-        for (int q = wid; q < 32; q += NB) {
-            const ulonglong2 d = W.row[q];
-            if (lane < (int)d.y) {
-                const int64_t f = (int64_t)d.x + lane;
-                if (CH == 2) {
-                    unsigned v = reinterpret_cast<const unsigned *>(WS[0].m[q])[lane];
+        // ---- overlay + store, row-wise, rows dealt round-robin to the CTA's warps -----------------------------------
+        if (CH == 2) {
+            // stereo: four frames (one 128-bit word) per lane, eight lanes per row, four rows per instruction
 #pragma unroll
-                    for (int b = 1; b < NB; ++b) v = add_frame_sat<2>(v, reinterpret_cast<const unsigned *>(WS[b].m[q])[lane]);
-                    reinterpret_cast<unsigned *>(proc)[f] = v;
-                } else {
+            for (int it = wid; it < 8; it += NB) {
+                const int q = 4 * it + (lane >> 3), part = lane & 7;
+                const ulonglong2 d = W.row[q];
+                const int left = (int)d.y - 4 * part;                    // frames of the row from this lane's first one on
+                if (left > 0) {
+                    uint4 v = reinterpret_cast<const uint4 *>(WS[0].m[q])[part];
+#pragma unroll
+                    for (int b = 1; b < NB; ++b) {
+                        const uint4 o = reinterpret_cast<const uint4 *>(WS[b].m[q])[part];
+                        v.x = add_frame_sat<2>(v.x, o.x); v.y = add_frame_sat<2>(v.y, o.y);
+                        v.z = add_frame_sat<2>(v.z, o.z); v.w = add_frame_sat<2>(v.w, o.w);
+                    }
+                    unsigned *g = reinterpret_cast<unsigned *>(proc) + ((int64_t)d.x + 4 * part);
+                    if (left >= 4 && (reinterpret_cast<unsigned long long>(g) & 15ull) == 0) *reinterpret_cast<uint4 *>(g) = v;
+                    else {
+                        g[0] = v.x;
+                        if (left > 1) g[1] = v.y;
+                        if (left > 2) g[2] = v.z;
+                        if (left > 3) g[3] = v.w;
+                    }
+                }
+            }
+        } else {
+#pragma unroll 2
+            for (int q = wid; q < 32; q += NB) {
+                const ulonglong2 d = W.row[q];
+                if (lane < (int)d.y) {
+                    const int64_t f = (int64_t)d.x + lane;
                     unsigned v = reinterpret_cast<const uint16_t *>(WS[0].m[q])[lane];
 #pragma unroll
                     for (int b = 1; b < NB; ++b) v = add_frame_sat<1>(v, reinterpret_cast<const uint16_t *>(WS[b].m[q])[lane]);
@@ -2158,7 +2178,7 @@ __device__ __forceinline__ float pw_tree_eval(const float *__restrict__ y, const
 // hop multiples (checked per block), and walks the block itself otherwise.
 __global__ void __launch_bounds__(BNT)
 k_hops(const float *__restrict__ kw, const TrackDesc *__restrict__ tracks, const PlanDev *__restrict__ plans,
-       double *__restrict__ hops)
+       double *__restrict__ hops, int stage_floats)
 {
     extern __shared__ float bval[];
     const TrackDesc td = tracks[blockIdx.y];
@@ -2167,7 +2187,24 @@ k_hops(const float *__restrict__ kw, const TrackDesc *__restrict__ tracks, const
     if (!pl->has_lufs || pl->hop <= 0 || td.nblocks < 3 || hs >= td.nblocks + 3) return;
     const int64_t b = (int64_t)(td.j0 + hs) * pl->hop, e = b + pl->hop;
     if (b < td.abs0 || e > td.total_frames || e - td.abs0 > td.frames) return;     // not (entirely) in this buffer: no block will ask for it
-    const float v = pw_tree_eval(kw + td.off + (b - td.abs0), pl->htree, bval, threadIdx.x);
+    // The hop's samples come into shared memory as 16-byte cp.async pieces (all of them in flight at once), and the
+    // leaves read them there: leaves walk with a stride of eight floats, which from global memory meant 32-byte
+    // requests and a dependent load every iteration (56 % of the DRAM rate; staged: the kernel streams).
+    const float *src = kw + td.off + (b - td.abs0);
+    const int32_t *T = pl->htree;
+    float *stage = bval + ((T[1] + T[2] + 3) & ~3);
+    const int n = pl->hop;
+    if (stage_floats >= n && (reinterpret_cast<unsigned long long>(src) & 15ull) == 0 && (n & 3) == 0) {
+        for (int i = threadIdx.x; i < n / 4; i += BNT) {
+            const unsigned sa = (unsigned)__cvta_generic_to_shared(stage + 4 * i);
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(src + 4 * i) : "memory");
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncthreads();
+        src = stage;
+    }
+    const float v = pw_tree_eval(src, T, bval, threadIdx.x);
     if (threadIdx.x == 0) reinterpret_cast<float *>(hops + td.zoff)[hs] = v;
 }
 
