@@ -1022,9 +1022,11 @@ k_detectw(const StreamDesc *__restrict__ streams, const PlanDev *__restrict__ pl
         // ---- integer RMS, stores, hold bits ---------------------------------------------------------------------
         unsigned r[8];
         bool act = false;
-        if (i0 >= H) {                                              // the whole look-back lies inside the stream: n = CH * look (warp-uniform)
+        if (i0 >= H && nH != 0u) {                                  // the whole look-back lies inside the stream: n = CH * look (warp-uniform)
+            // no test inside the loop: the eight roots are independent chains (conversion, MUFU, multiply, compare) that
+            // must interleave; a per-element "nH ?" compiles to a branch around each of them
 #pragma unroll
-            for (int k = 0; k < 8; ++k) r[k] = nH ? window_rms_rn((unsigned long long)(mine + p[k]), nH, rnH) : 0u;
+            for (int k = 0; k < 8; ++k) r[k] = window_rms_rn((unsigned long long)(mine + p[k]), nH, rnH);
         } else {
 #pragma unroll
             for (int k = 0; k < 8; ++k) r[k] = f + k >= H ? (nH ? window_rms_rn((unsigned long long)(mine + p[k]), nH, rnH) : 0u)
