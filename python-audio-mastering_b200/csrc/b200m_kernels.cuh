@@ -1943,7 +1943,7 @@ template <int CH> struct KwW {
     static constexpr size_t SMEM = 2 * 32 * 4 * 8 /* Q[lane] of the two sections */ + (size_t)DEPTH * RAW_WORDS * 4 + 4 * 8 /* carry */;
 };
 #ifndef B200M_KWW_OCC
-#define B200M_KWW_OCC 12           // 168 registers: the two sections' tables live in registers across the loop
+#define B200M_KWW_OCC 16           // resident warps per SM the kernel is built for (<= 128 registers)
 #endif
 template <int CH>
 __global__ void __launch_bounds__(32, B200M_KWW_OCC)
@@ -1973,7 +1973,18 @@ k_kweightw(const int16_t *__restrict__ src_all, const TrackDesc *__restrict__ tr
     auto fetch = [&](int64_t t0, int slot) {
         unsigned *raw = raw_all + slot * W::RAW_WORDS;
         constexpr int FPP = 8 / CH, PPL = 16 / FPP;                   // frames per piece, pieces per lane's 16 frames
+        if (in16 && t0 + WT <= frames) {
+            // the whole tile lies inside the track (warp-uniform; all but a track's last tile): piece lane + 32 h sits
+            // 512 h bytes behind piece `lane` in global memory and 8 h / PPL ... rows further in raw[] -- constant offsets
+            const char *gp = reinterpret_cast<const char *>(src + t0 * CH) + 16 * lane;
+            const unsigned sa = (unsigned)__cvta_generic_to_shared(raw + W::RSTRIDE * (lane / PPL) + 4 * (lane % PPL));
 #pragma unroll
+            for (int h = 0; h < PPL; ++h)
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa + h * (W::RSTRIDE * (32 / PPL) * 4)), "l"(gp + 512 * h) : "memory");
+            asm volatile("cp.async.commit_group;" ::: "memory");
+            return;
+        }
+#pragma unroll 1
         for (int h = 0; h < PPL; ++h) {
             const int p = lane + 32 * h;
             const int64_t gf = t0 + (int64_t)FPP * p;
@@ -2455,6 +2466,20 @@ __device__ __forceinline__ int final_sample(int q, bool has, double gain)
     return quant16((double)limiter32((float)q * (1.0f / 32768.0f), 0.98f));
 }
 
+// eight samples through final_sample: the path of a vector in which some sample meets the limiter (one copy of the code)
+__device__ __noinline__ uint4 final_vector(uint4 w, bool has, double gain)
+{
+    const unsigned in[4] = {w.x, w.y, w.z, w.w};
+    unsigned o[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int r0 = final_sample(prmt_sx(in[k], 0x9910u), has, gain);
+        const int r1 = final_sample(prmt_sx(in[k], 0xbb32u), has, gain);
+        o[k] = (unsigned)(r0 & 0xffff) | ((unsigned)r1 << 16);
+    }
+    return make_uint4(o[0], o[1], o[2], o[3]);
+}
+
 template <int CH>
 __global__ void __launch_bounds__(256)
 k_final(const int16_t *__restrict__ proc, const TrackDesc *__restrict__ tracks,
@@ -2485,13 +2510,26 @@ k_final(const int16_t *__restrict__ proc, const TrackDesc *__restrict__ tracks,
             if (v == 1 && !second) break;
             const unsigned in[4] = {w[v].x, w[v].y, w[v].z, w[v].w};
             unsigned o[4];
+            // the eight samples of a vector take the common case without a branch (one multiply, one truncation: see
+            // final_sample; without a loudness target the sample itself), the "needs the limiter" tests accumulate
+            // in one predicate, and only a vector with such a sample (or a NaN) goes back through final_sample.  A branch
+            // per sample kept the eight conversion / multiply chains from overlapping.
+            bool slow = false;
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-                const int r0 = final_sample((int)(short)(in[k] & 0xffffu), has, gain);
-                const int r1 = final_sample((int)in[k] >> 16, has, gain);
-                o[k] = (unsigned)(r0 & 0xffff) | ((unsigned)r1 << 16);
+                const int q0 = prmt_sx(in[k], 0x9910u), q1 = prmt_sx(in[k], 0xbb32u);
+                if (has) {
+                    const double p0 = __dmul_rn((double)q0, gain), p1 = __dmul_rn((double)q1, gain);
+                    slow = slow || !(fabs(p0) <= 0.98 * 32768.0) || !(fabs(p1) <= 0.98 * 32768.0);
+                    o[k] = __byte_perm((unsigned)__double2int_rz(p0), (unsigned)__double2int_rz(p1), 0x5410);
+                } else {
+                    slow = slow || abs(q0) > 32112 || abs(q1) > 32112;
+                    o[k] = in[k];
+                }
             }
-            reinterpret_cast<uint4 *>(dst)[v ? g2 : g] = make_uint4(o[0], o[1], o[2], o[3]);
+            uint4 ov = make_uint4(o[0], o[1], o[2], o[3]);
+            if (slow) ov = final_vector(w[v], has, gain);
+            reinterpret_cast<uint4 *>(dst)[v ? g2 : g] = ov;
         }
     }
     for (int64_t i = nvec * 8 + (int64_t)blockIdx.x * 256 + threadIdx.x; i < nsamp; i += (int64_t)gridDim.x * 256)
