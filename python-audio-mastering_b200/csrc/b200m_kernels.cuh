@@ -1150,7 +1150,7 @@ __device__ __forceinline__ double recur_step(double a, double M, double inc, dou
 __device__ __forceinline__ double recur_step_pos(double a, double M, double inc, double dec)
 {
     const long long ab = __double_as_longlong(a), Mb = __double_as_longlong(M);
-    const bool p = ab <= Mb;
+    const bool p = ab <= Mb;                                 // (as fp64 compares -- one instruction each, on the fp64 pipe -- the kernel gains 1 %)
     const double u = __dadd_rn(a, inc), d = __dsub_rn(a, dec);
     const bool q1 = __double_as_longlong(u) >= Mb;
     const bool q2 = __double2hiint(d) < 0;                   // a - dec < 0 (a - dec == -0 cannot occur: a, dec >= +0 and RN)
@@ -1212,7 +1212,8 @@ __device__ __forceinline__ double exp10_gain(double x, const double *__restrict_
     const int m = __double2loint(t);
     const double T = tab[m & 31];
     const double v = fma(T, sr, T);
-    return __hiloint2double(__double2hiint(v) + ((m >> 5) << 20), __double2loint(v));
+    // n << 20 with n = m >> 5, written as (m & ~31) * 2^15 so that mask, shift and add are two instructions (|m| < 2^15: no overflow)
+    return __hiloint2double(__double2hiint(v) + (m & ~31) * 32768, __double2loint(v));
 }
 
 // pydub: frame * db_to_float(-attenuation), db_to_float(db) = 10 ** (db / 20).  The quotient att / 20 is
