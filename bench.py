@@ -327,12 +327,17 @@ def run_b200_arm(args):
         e1.record()
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1)
+        rank_ms.clear()
+        rank_ms.append(ms)
         if world > 1:
-            t = torch.tensor([ms], device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
+            every = [torch.zeros(1, device=dev) for _ in range(world)]
+            dist.all_gather(every, torch.tensor([ms], device=dev))
+            rank_ms[:] = [float(x.item()) for x in every]       # every rank's own time (reported beside the max)
+            ms = max(rank_ms)
         barrier()
         return ms
+
+    rank_ms = []
 
     # ---- device-resident: `value` ------------------------------------------------------------------
     def step_dev():
@@ -349,8 +354,14 @@ def run_b200_arm(args):
     eng.reset_profile()
     l0 = eng.launch_count()
     ms_dev = timed(step_dev, args.steps)
+    rank_ms_dev = [m / args.steps for m in rank_ms]
     launches = eng.launch_count() - l0
     ktimes = {k: eng.kernel_time_ms(k) for k in KERNELS}
+    rank_kernel_ms = [sum(v[0] for v in ktimes.values()) / args.steps]
+    if world > 1:
+        every = [torch.zeros(1, device=dev) for _ in range(world)]
+        dist.all_gather(every, torch.tensor([rank_kernel_ms[0]], device=dev))
+        rank_kernel_ms = [float(x.item()) for x in every]
     eng.set_profiling(False)
     track0 = d_in[0].cpu().numpy() if rank == 0 else None        # the CPU legs master these very bytes
 
@@ -434,6 +445,7 @@ def run_b200_arm(args):
                     "copy_only_ms": ms_copy / args.steps, "frac_of_copy_roof": ms_copy / ms_e2e,
                     "copy_only_note": "the same pinned buffers, H2D and D2H of every rank at once, no kernels: the host-fabric roof of this step"},
             "gpu_launches": int(launches),
+            "rank_ms_per_step": rank_ms_dev, "rank_kernel_ms_per_step": rank_kernel_ms,
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": alg_bytes,

@@ -15,7 +15,8 @@ if os.environ.get("WARM") or os.environ.get("TILE"):
 st = dict(bass_boost=4.0, mid_cut=3.0, presence_boost=1.0, treble_boost=3.0, saturation=sat, width=1.2, multiband=True, lufs=-14.0)
 t0 = time.time()
 hat = synth.HAT_DENSE if os.environ.get("HAT", "dense") == "dense" else synth.HAT_SPARSE
-d_in = torch.cat([synth.make_tracks_torch(k, min(32, ntracks - k), seconds, rate, "cuda", hat_cfg=hat) for k in range(0, ntracks, 32)])
+track0 = int(os.environ.get("TRACK0", 0))       # first track of the synthetic programme (bench.py's rank r starts at r * tracks_per_gpu)
+d_in = torch.cat([synth.make_tracks_torch(track0 + k, min(32, ntracks - k), seconds, rate, "cuda", hat_cfg=hat) for k in range(0, ntracks, 32)])
 torch.cuda.synchronize(); print("synth", time.time() - t0)
 n = d_in.shape[1]
 d_out = torch.empty_like(d_in)
