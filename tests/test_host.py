@@ -172,3 +172,37 @@ def test_wav_header_is_the_wave_modules():
         assert bytes(out) == f.getvalue()[:44]
     assert lib.b200m_wav_header(44100, 3, 10, (C.c_ubyte * 44)()) != 0
     assert lib.b200m_wav_header(44100, 2, 1 << 31, (C.c_ubyte * 44)()) != 0      # does not fit a RIFF file
+
+
+def test_gain_routine_constants_and_accuracy():
+    """k_comp's 10^x (exp10_gain, csrc/b200m_kernels.cuh): the constants in the header are the correctly rounded
+    ones (Taylor coefficients of 10^r, 32 log2 10, the two pieces of -log10(2)/32, the table 2^(j/32)), and the
+    operation sequence -- simulated with exact FMA semantics by scripts/exp10_check.py -- stays within 1.05 ulp of
+    60-digit arithmetic over the exponents a compressor produces (the class of libm's exp10, which pydub's
+    db_to_float goes through)."""
+    mpmath = pytest.importorskip("mpmath")
+    import importlib.util, random
+    spec = importlib.util.spec_from_file_location("exp10_check", os.path.join(ROOT, "scripts", "exp10_check.py"))
+    chk = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(chk)
+    src = open(os.path.join(ROOT, "python-audio-mastering_b200", "csrc", "b200m_kernels.cuh")).read()
+    body = re.search(r"__constant__ double c_exp10\[11\] = \{(.*?)\};", src, re.S).group(1)
+    consts = [float.fromhex(t) if "0x" in t else float(t) for t in re.findall(r"-?0x[0-9a-fA-F.]+p[+-]?\d+|\d+\.\d+", re.sub(r"//.*", "", body))]
+    assert len(consts) == 11
+    assert consts[:7] == chk.TAYLOR[:7]
+    assert consts[7] == 32.0 * chk.LOG2_10 and consts[8] == chk.NEG_LOG10_2_HI / 32.0 and consts[9] == chk.NEG_LOG10_2_LO / 32.0
+    assert consts[10] == chk.MAGIC
+    tab = re.search(r"g_exp10_tab\[32\] = \{(.*?)\};", src, re.S).group(1)
+    tab = [float.fromhex(t) for t in re.findall(r"0x[0-9a-fA-F.]+p[+-]?\d+", tab)]
+    assert tab == [float(mpmath.mpf(2) ** (mpmath.mpf(j) / 32)) for j in range(32)]
+    rnd = random.Random(11)
+    worst = 0.0
+    for i in range(3000):
+        att = rnd.random() * (60.0 if i % 4 else 5000.0)
+        q = att * 0.05
+        x = -chk.fma(chk.fma(-q, 20.0, att), 0.05, q)          # att / 20 rounded like CPython's true division
+        assert x == -(att / 20.0)
+        if x > -300.0:
+            worst = max(worst, chk.ulp_err(chk.exp10_tf(x, 32, 6), x))
+    assert chk.exp10_tf(-0.0, 32, 6) == 1.0                      # pydub multiplies only when att != 0: 10^-0 must be exactly 1
+    assert worst <= 1.05, worst
