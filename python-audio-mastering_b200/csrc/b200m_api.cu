@@ -209,6 +209,9 @@ static void build_sectab(const b200m_biquad &q, SecTab &T)
         mm(Pk, Pk, Pk);
     }
     for (int i = 0; i < 4; ++i) T.PW[i] = (double)Pk[i];
+    ld AH[4] = {1, 0, 0, 1};
+    for (int n = 0; n < SEG / 2; ++n) mm(AH, A, AH);
+    for (int i = 0; i < 4; ++i) T.AH[i] = (double)AH[i];
     ld Qj[4] = {1, 0, 0, 1};
     for (int j = 0; j < 32; ++j) {
         for (int i = 0; i < 4; ++i) T.Q[j][i] = (double)Qj[i];
@@ -972,6 +975,7 @@ static void fill_tabc(SecTabC &d, const SecTab &s)
     std::memcpy(d.g, s.g, sizeof d.g);
     std::memcpy(d.P, s.P, sizeof d.P);
     std::memcpy(d.PW, s.PW, sizeof d.PW);
+    std::memcpy(d.AH, s.AH, sizeof d.AH);
 }
 
 // ------------------------------------------------------------------------------------

@@ -33,9 +33,11 @@ struct SecTab {
     double g[SEG][2];   // g[n] = A^(SEG-1-n) B : end state of a segment from zero state
     double P[5][4];     // A^(SEG * 2^k), k = 0..4 : warp-shuffle scan steps (row major 2x2)
     double PW[4];       // A^(SEG * 32)            : warp-to-warp carry
+    double AH[4];       // A^(SEG / 2)             : state in the middle of a lane's segment (section_round_w)
+    double pad2_[4];
     double Q[32][4];    // A^(SEG * lane)          : carry-in to each lane's segment start
 };
-static_assert(sizeof(SecTab) == 192 * 8, "SecTab layout");
+static_assert(sizeof(SecTab) == 200 * 8, "SecTab layout");
 
 struct BandDev {
     double thresh_rms, attack_frames, release_frames, slope;
@@ -118,6 +120,7 @@ struct SecTabC {
     double g[SEG][2];
     double P[5][4];
     double PW[4];
+    double AH[4];
 };
 
 // U: the lane-independent tables (a SecTab in shared memory or a SecTabC in the constant bank), Q: A^(SEG lane).

@@ -306,9 +306,9 @@ template <int CH> struct ChainW {
 };
 
 // The lane-independent tables of the launch's single plan (SecTabC, b200m_device.cuh), by value.
-struct ChainTabsC { SecTabC sec[8]; };       // eq[4] lp[2] hp[2]: 3904 bytes
+struct ChainTabsC { SecTabC sec[8]; };       // eq[4] lp[2] hp[2]: 4160 bytes (kernel parameters may take 32 KB since CUDA 12.1)
 struct KwTabsC { SecTabC sec[2]; };          // K-weighting shelf and high-pass (a function of the rate alone)
-static_assert(sizeof(ChainTabsC) <= 3936, "ChainTabsC must fit the 4 KB kernel parameter space next to the other arguments");
+static_assert(sizeof(ChainTabsC) <= 4224, "ChainTabsC grew: check the constant-bank budget of the chain kernels");
 
 // One biquad over the warp's tile.  j = lane within the channel group of NL lanes; carry (shared
 // memory, 2 doubles per section and channel) = the section state at the tile start, replaced by the
@@ -318,18 +318,19 @@ template <int NL, typename TU>
 __device__ __forceinline__ void section_round_w(double (&x)[SEG], const TU &U, const double (*__restrict__ Q)[4], double *carry, int j)
 {
     const TU *T = &U;
-    // zero-state end state of the segment: even and odd samples accumulate separately (two chains
-    // per component instead of one: half the dependent latency)
-    double s0 = 0.0, s1 = 0.0, r0 = 0.0, r1 = 0.0;
+    constexpr int H = SEG / 2;
+    // zero-state end states of the two HALVES of the lane's segment (g[n + H] = A^(H-1-n) B weighs sample n of a half):
+    // f = state after samples 0 .. H-1, s = what samples H .. SEG-1 add; the segment's own is A^H f + s.
+    double f0 = 0.0, f1 = 0.0, s0 = 0.0, s1 = 0.0;
 #pragma unroll
-    for (int n = 0; n < SEG; n += 2) {
-        s0 = fma(T->g[n][0], x[n], s0);
-        s1 = fma(T->g[n][1], x[n], s1);
-        r0 = fma(T->g[n + 1][0], x[n + 1], r0);
-        r1 = fma(T->g[n + 1][1], x[n + 1], r1);
+    for (int n = 0; n < H; ++n) {
+        f0 = fma(T->g[n + H][0], x[n], f0);
+        f1 = fma(T->g[n + H][1], x[n], f1);
+        s0 = fma(T->g[n + H][0], x[n + H], s0);
+        s1 = fma(T->g[n + H][1], x[n + H], s1);
     }
-    s0 = __dadd_rn(s0, r0);
-    s1 = __dadd_rn(s1, r1);
+    s0 = fma(T->AH[0], f0, fma(T->AH[1], f1, s0));
+    s1 = fma(T->AH[2], f0, fma(T->AH[3], f1, s1));
 #pragma unroll
     for (int k = 0; (1 << k) < NL; ++k) {
         const double t0 = __shfl_up_sync(FULL, s0, 1 << k, NL);
@@ -345,18 +346,26 @@ __device__ __forceinline__ void section_round_w(double (&x)[SEG], const TU &U, c
     const double c0 = carry[0], c1 = carry[1];
     double z0 = fma(Q[j][0], c0, fma(Q[j][1], c1, e0));
     double z1 = fma(Q[j][2], c0, fma(Q[j][3], c1, e1));
+    // the state in the middle of the segment, so that the two halves run as two independent recurrences (the
+    // dependent chain of the DF2T step is two FMAs per sample: one chain leaves the fp64 pipe waiting)
+    double y0 = fma(T->AH[0], z0, fma(T->AH[1], z1, f0));
+    double y1 = fma(T->AH[2], z0, fma(T->AH[3], z1, f1));
     const double b0 = T->b0, b1 = T->b1, b2 = T->b2, na1 = -T->a1, na2 = -T->a2;
 #pragma unroll
-    for (int n = 0; n < SEG; ++n) {
-        const double xn = x[n];
-        const double t0 = fma(b1, xn, z1), t1 = b2 * xn;
-        const double y = fma(b0, xn, z0);
-        z0 = fma(na1, y, t0);
-        z1 = fma(na2, y, t1);
-        x[n] = y;
+    for (int n = 0; n < H; ++n) {
+        const double xa = x[n], xb = x[n + H];
+        const double ta0 = fma(b1, xa, z1), ta1 = b2 * xa;
+        const double tb0 = fma(b1, xb, y1), tb1 = b2 * xb;
+        const double ya = fma(b0, xa, z0), yb = fma(b0, xb, y0);
+        z0 = fma(na1, ya, ta0);
+        y0 = fma(na1, yb, tb0);
+        z1 = fma(na2, ya, ta1);
+        y1 = fma(na2, yb, tb1);
+        x[n] = ya;
+        x[n + H] = yb;
     }
     __syncwarp();                                   // every lane has read the carry
-    if (j == NL - 1) { carry[0] = z0; carry[1] = z1; }
+    if (j == NL - 1) { carry[0] = y0; carry[1] = y1; }
 }
 
 // Two INDEPENDENT biquads over the same tile side by side (the low-pass and the high-pass branch of
