@@ -40,7 +40,7 @@ SETTINGS = dict(bass_boost=4.0, mid_cut=3.0, presence_boost=1.0, treble_boost=3.
 RATE = 48000
 METRIC = "audio-sec mastered/sec (RTF)"
 UNIT = "audio-s/s"
-KERNELS = ["k_chain", "k_detect", "k_comp", "k_comp_repair", "k_comp_fix", "k_kweight", "k_hops", "k_blocks", "k_gate", "k_final"]
+KERNELS = ["k_chain", "k_detect", "k_comp", "k_comp_sprint", "k_comp_repair", "k_comp_fix", "k_kweight", "k_hops", "k_blocks", "k_gate", "k_final"]
 GEN_BATCH = 32          # tracks synthesised per call (bounds the generator's temporaries)
 
 

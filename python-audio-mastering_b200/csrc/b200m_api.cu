@@ -49,6 +49,13 @@ struct b200m_handle {
     // pinned staging for descriptors / small results
     char *pin = nullptr;
     size_t pin_cap = 0;
+    // b200m_master_batch alternates between `pin` and `pinB` for its descriptors and results, and waits only for the call
+    // that used a buffer last (two calls ago): the host side of call i + 1 (cutting groups and segments, ~1.5 ms for one
+    // track) then runs while the kernels of call i do.  Every other entry point synchronises the stream before it touches `pin`.
+    char *pinB = nullptr;
+    size_t pinB_cap = 0;
+    int pin_turn = 0;
+    cudaEvent_t pin_ev[2] = {nullptr, nullptr};
     // profiling
     bool profiling = false;
     std::vector<std::string> prof_names;
@@ -58,6 +65,7 @@ struct b200m_handle {
     int64_t launches = 0;
     // recurrence tiling (0 = automatic) and its verification counters
     int recur_tile = 0, recur_warm = 0, recur_rounds = -1;
+    bool comp_sprint = true;         // automatic repair = k_comp_sprint + one round (B200M_COMP_SPRINT=0: Jacobi rounds, as when a round count is set)
     // time segmentation of k_chain / k_kweight: 0 = automatic, < 0 = off, > 0 = tiles per segment
     int seg_chain = 0, seg_kweight = 0;
     int chain_kernel = 0;            // 0 = automatic, 1 = k_chain (a CTA per segment), 2 = k_chainw (a warp per segment)
@@ -769,6 +777,7 @@ extern "C" int b200m_create(int device, b200m_handle **out)
     h->device = device;
     if (const char *ck = std::getenv("B200M_CHAIN_KERNEL")) h->chain_kernel = std::max(0, std::min(2, std::atoi(ck)));   // test / experiment override
     if (const char *ck = std::getenv("B200M_KWEIGHT_KERNEL")) h->kweight_kernel = std::max(0, std::min(2, std::atoi(ck)));
+    if (const char *ck = std::getenv("B200M_COMP_SPRINT")) h->comp_sprint = std::atoi(ck) != 0;
     if (const char *ck = std::getenv("B200M_CHAIN_SLUT")) h->chain_slut_ok = std::atoi(ck) != 0;
     if (const char *ck = std::getenv("B200M_DETECT_KERNEL")) h->detect_kernel = std::atoi(ck);
     if (const char *ck = std::getenv("B200M_CHAIN_WAVES")) h->chain_waves = std::max(1, std::min(16, std::atoi(ck)));
@@ -835,6 +844,8 @@ extern "C" void b200m_destroy(b200m_handle *h)
     if (h->ws) cudaFree(h->ws);
     if (h->d_plans) cudaFree(h->d_plans);
     if (h->pin) cudaFreeHost(h->pin);
+    if (h->pinB) cudaFreeHost(h->pinB);
+    for (cudaEvent_t e : h->pin_ev) if (e) cudaEventDestroy(e);
     if (h->d_counters) cudaFree(h->d_counters);
     for (auto &kv : h->curves) cudaFree(kv.second.ptr);
     for (auto &kv : h->sat_luts) cudaFree(kv.second.ptr);
@@ -1031,7 +1042,9 @@ static size_t recur_spec_doubles(const b200m_handle *h, const Group &g, int nban
 {
     const RecurParams P = recur_params(h, g, nbands, 0);
     const size_t lanes = (size_t)g.n_streams * P.tiles;
-    return 4 * lanes * nbands /* ss / se ping-pong */ + (lanes + 1) / 2 /* dirty list (uint32) */ + MAX_REPAIR_ROUNDS / 2 + 2 /* one counter per round */;
+    const size_t pieces = (size_t)g.n_streams * (size_t)((g.max_stream_frames + 1023) / 1024);      // k_comp_sprint's 1024-frame pieces
+    return 4 * lanes * nbands /* ss / se ping-pong */ + (lanes + 1) / 2 /* dirty list (uint32) */ + MAX_REPAIR_ROUNDS / 2 + 2 /* one counter per round */ +
+           (pieces + 1) / 2 /* list of pieces (uint32) */ + (pieces + 63) / 64 + 2 /* their bitmap */;
 }
 
 // debug_att: the per-frame attenuation trajectory is materialised too (b200m_compress_dynamic_range's att_out)
@@ -1091,6 +1104,29 @@ static int launch_compressor(b200m_handle *h, const Group &g, const BandPtrs &bp
         const int rounds = std::min(h->recur_rounds >= 0 ? h->recur_rounds : auto_rounds, MAX_REPAIR_ROUNDS);
         CK(cudaMemsetAsync(d_counts, 0, MAX_REPAIR_ROUNDS * sizeof(unsigned), h->stream));
         const unsigned gdirty = (unsigned)((lanes + 255) / 256);
+        if (h->recur_rounds < 0 && h->comp_sprint) {
+            // The true state first, the samples after: k_comp_sprint walks the stretches whose guess was wrong with the
+            // recurrence alone (sequential per stream and band, tiles whose guess was right are skipped), leaves the
+            // true state at the end of every 32-frame block and lists the 1024-frame pieces whose samples change;
+            // k_comp (mode 2) then recomputes those pieces, all at once, each from its own true state.
+            const int fine_tiles = (g.max_stream_frames + 1023) / 1024;
+            const size_t pieces = (size_t)g.n_streams * fine_tiles;
+            unsigned *d_pieces = d_counts + MAX_REPAIR_ROUNDS + 2;
+            unsigned *d_bitmap = d_pieces + ((pieces + 1) / 2) * 2;
+            CK(cudaMemsetAsync(d_bitmap, 0, ((pieces + 63) / 64) * 8, h->stream));
+            const unsigned gs = (unsigned)(((size_t)g.n_streams * nbands + 3) / 4);
+            if (nbands == 3) LAUNCH("k_comp_sprint", k_comp_sprint<3><<<gs, 128, 0, h->stream>>>(g.d_streams, h->d_plans, P1, bp, ss[0], se[0], ss[1], se[1], d_pieces, d_counts, d_bitmap, fine_tiles, h->d_counters));
+            else             LAUNCH("k_comp_sprint", k_comp_sprint<1><<<gs, 128, 0, h->stream>>>(g.d_streams, h->d_plans, P1, bp, ss[0], se[0], ss[1], se[1], d_pieces, d_counts, d_bitmap, fine_tiles, h->d_counters));
+            RecurParams P2 = P;
+            P2.mode = 2; P2.tile_len = 1024; P2.tiles = fine_tiles;
+            {
+                const unsigned gr_keep = gr;
+                const unsigned gr = (unsigned)((pieces + 31) / 32);      // upper bound: CTAs beyond the list leave at once
+                (void)gr_keep;
+                LAUNCH_COMP("k_comp_repair", P2, nullptr, nullptr, nullptr, nullptr, d_pieces, d_counts);
+            }
+            cur = 1;                                                     // the joints are consistent by construction: (ss[1], se[1])
+        } else
         for (int round = 0; round < rounds; ++round) {               // parallel repair rounds (Jacobi), dirty tiles only
             if (nbands == 3) LAUNCH("k_comp_dirty", k_comp_dirty<3><<<gdirty, 256, 0, h->stream>>>(g.d_streams, h->d_plans, P1, ss[cur], se[cur], ss[cur ^ 1], se[cur ^ 1], d_list, d_counts + round, h->d_counters));
             else             LAUNCH("k_comp_dirty", k_comp_dirty<1><<<gdirty, 256, 0, h->stream>>>(g.d_streams, h->d_plans, P1, ss[cur], se[cur], ss[cur ^ 1], se[cur ^ 1], d_list, d_counts + round, h->d_counters));
@@ -1660,9 +1696,20 @@ static int master_batch_impl(b200m_handle *h, const void *pcm_in, int in_on_devi
     for (auto &gp : gps) { max_need = std::max(max_need, gp.need); pin_total += gp.pin_bytes; }
     rc = ws_reserve(h, max_need * slots);
     if (rc) return rc;
-    rc = pin_reserve(h, pin_total);
-    if (rc) return rc;
-    CK(cudaStreamSynchronize(h->stream));       // pinned staging of an earlier call may still be in flight
+    const int pb = (h->pin_turn ^= 1);
+    if (!h->pin_ev[pb]) CK(cudaEventCreateWithFlags(&h->pin_ev[pb], cudaEventDisableTiming));
+    CK(cudaEventSynchronize(h->pin_ev[pb]));    // pinned staging: the call that used this buffer last (two calls ago) is through
+    if (pb == 0) {
+        rc = pin_reserve(h, pin_total);
+        if (rc) return rc;
+    } else if (pin_total > h->pinB_cap) {
+        CK(cudaStreamSynchronize(h->stream));
+        if (h->pinB) cudaFreeHost(h->pinB);
+        h->pinB = nullptr; h->pinB_cap = 0;
+        CK(cudaMallocHost(&h->pinB, pin_total + 4096));
+        h->pinB_cap = pin_total + 4096;
+    }
+    char *const pbuf = pb ? h->pinB : h->pin;
     if (pipelined && !h->s_in) {
         CK(cudaStreamCreateWithFlags(&h->s_in, cudaStreamNonBlocking));
         CK(cudaStreamCreateWithFlags(&h->s_out, cudaStreamNonBlocking));
@@ -1695,7 +1742,7 @@ static int master_batch_impl(b200m_handle *h, const void *pcm_in, int in_on_devi
             X.in = X.comp = X.out = h->stream;
             X.slot_free = X.h2d_done = X.comp_done = X.d2h_done = nullptr;
         }
-        rc = exec_group(h, gp, h->ws + (i % slots) * max_need, h->pin + pin_off, X, (const int16_t *)pcm_in, in_dev, in_offsets,
+        rc = exec_group(h, gp, h->ws + (i % slots) * max_need, pbuf + pin_off, X, (const int16_t *)pcm_in, in_dev, in_offsets,
                         in_frames, (int16_t *)pcm_out, out_dev, nullptr, targets, out_total);
         h->stream = own;
         if (rc) break;
@@ -1712,12 +1759,13 @@ static int master_batch_impl(b200m_handle *h, const void *pcm_in, int in_on_devi
         cudaEventRecord(done_c2, h->s_comp2);
         cudaStreamWaitEvent(h->stream, done_c2, 0);
     }
+    cudaEventRecord(h->pin_ev[pb], h->stream);
     if (rc) { cudaStreamSynchronize(h->stream); return rc; }
     if (loudness_out || gain_out || !out_dev) {
         CK(cudaStreamSynchronize(h->stream));
         for (size_t i = 0; i < gps.size(); ++i) {
             const GroupPlan &gp = gps[i];
-            const double2 *hl = reinterpret_cast<const double2 *>(h->pin + pin_offs[i] + gp.res_off);
+            const double2 *hl = reinterpret_cast<const double2 *>(pbuf + pin_offs[i] + gp.res_off);
             for (int t = gp.t_begin; t < gp.t_end; ++t) {
                 const bool has = gp.F > 0;
                 if (loudness_out) loudness_out[t] = has ? hl[t - gp.t_begin].x : NAN;

@@ -1285,7 +1285,7 @@ k_comp(const StreamDesc *__restrict__ streams, const PlanDev *__restrict__ plans
     const int wid = NB == 1 ? 0 : (int)(threadIdx.x >> 5), lane = threadIdx.x & 31;
     // mode 1 (repair round): the lanes take the (stream, tile) pairs k_comp_dirty listed, densely packed
     unsigned n_dirty = 0u;
-    if (P.mode == 1) {
+    if (P.mode >= 1) {
         n_dirty = *dirty_count;
         if (blockIdx.x * 32u >= n_dirty) return;                         // CTA-uniform
     }
@@ -1294,7 +1294,7 @@ k_comp(const StreamDesc *__restrict__ streams, const PlanDev *__restrict__ plans
     unsigned char (*s_same)[32] = reinterpret_cast<unsigned char (*)[32]>(recur_smem + NB * sizeof(RecurWarpSmem));   // [NB][32]
     const int band = NB == 3 ? wid : P.band_base;
     const unsigned li = blockIdx.x * 32u + lane;
-    const int gl = P.mode == 1 ? (li < n_dirty ? (int)dirty_list[li] : P.n_streams * P.tiles) : (int)li;
+    const int gl = P.mode >= 1 ? (li < n_dirty ? (int)dirty_list[li] : P.n_streams * P.tiles) : (int)li;
     const int s = gl / P.tiles, tile = gl % P.tiles;
     bool live = s < P.n_streams;
     int start = 0, end = 0;
@@ -1332,6 +1332,9 @@ k_comp(const StreamDesc *__restrict__ streams, const PlanDev *__restrict__ plans
         a = tile == 0 ? 0.0 : se_in[slot - 1];
         a_in = a;
     }
+    // mode 2: recompute a piece whose true start state k_comp_sprint left in the block-end states (no speculation,
+    // no merging: the whole piece, from the state at the end of the block before it)
+    if (P.mode == 2 && live && start > 0) a = bend_b[(start >> 5) - 1];
     // warp-uniform: this band passed the plan-time checks in every plan of the warp (exact constant division, curve
     // finite and >= +0, attenuation bounded): the branch-free step and gain
     const bool fast = __all_sync(FULL, okfast || !live);
@@ -1617,7 +1620,7 @@ k_comp(const StreamDesc *__restrict__ streams, const PlanDev *__restrict__ plans
                 if (DBG && quiet && att_dbg != nullptr)
                     for (int k = 0; k < cnt; ++k) att_dbg[out_off + i0 + k] = a;
                 s_same[wid][lane] = (unsigned char)(__double_as_longlong(a) == __double_as_longlong(old_end));
-                bend_b[cb] = a;
+                if (P.mode != 2) bend_b[cb] = a;                    // (mode 2 would store what is there already)
             }
         }
         __syncwarp();
@@ -1678,7 +1681,7 @@ k_comp(const StreamDesc *__restrict__ streams, const PlanDev *__restrict__ plans
         if (P.mode == 0) {
             ss_out[slot] = a_start;
             se_out[slot] = a;
-        } else {
+        } else if (P.mode == 1) {
             ss_out[slot] = a_in;
             se_out[slot] = merged ? se_in[slot] : a;
         }
@@ -1716,6 +1719,105 @@ k_comp_dirty(const StreamDesc *__restrict__ streams, const PlanDev *__restrict__
             const size_t sl = slot0 + (size_t)b * P.tiles;
             ss_out[sl] = ss_in[sl]; se_out[sl] = se_in[sl];
         }
+    }
+}
+
+// k_comp_sprint: the TRUE state at every tile joint, ahead of the (single) repair round.  A Jacobi round carries
+// the truth one tile further and costs a launch whose length is its slowest lane's -- with gains, samples and overlay,
+// ~40 ns per frame; where trajectories from different pasts stay apart for long (pydub releases at a rate
+// proportional to the CURRENT maximum attenuation: after a loud passage a quiet one just above the threshold lets the
+// state drift for seconds without touching a clamp) that was one round per tile of the stretch.  The state alone
+// is much cheaper to carry: one warp per (stream, band) walks the stream's tiles in order; a tile whose assumed start
+// is the truth is skipped (its stored end is the truth), any other is walked -- recurrence only, 32 frames per
+// step of the warp: every lane loads one frame's RMS, gathers its curve value and divides, the values go round by
+// shuffle, the loads of the next block are in flight meanwhile -- until the state meets the stored block-end state of
+// the speculative pass (then the stored end holds) or the tile ends.  `se_true` receives the end state of every
+// tile; k_comp_dirty / k_comp (mode 1) with se_in = se_true then re-run exactly the tiles whose guess was wrong, each
+// from its true state, all in ONE round.
+template <int NB>
+__global__ void __launch_bounds__(128)
+k_comp_sprint(const StreamDesc *__restrict__ streams, const PlanDev *__restrict__ plans, RecurParams P, BandPtrs bp,
+              const double *__restrict__ ss, const double *__restrict__ se, double *__restrict__ ss_true, double *__restrict__ se_true,
+              unsigned *__restrict__ fine_list, unsigned *__restrict__ fine_count, unsigned *__restrict__ fine_bitmap, int fine_tiles,
+              unsigned long long *__restrict__ counters)
+{
+    const int gw = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    const int s = gw / NB, b = gw % NB;
+    if (s >= P.n_streams) return;
+    const StreamDesc sd = streams[s];
+    const PlanDev *__restrict__ pl = plans + sd.plan;
+    if (!pl->multiband || sd.out_frames <= 0) return;
+    const int band = NB == 3 ? b : P.band_base;
+    const int ntiles = (sd.out_frames + P.tile_len - 1) / P.tile_len;
+    const size_t base = ((size_t)s * NB + b) * P.tiles;
+    ss += base; se += base; ss_true += base; se_true += base;
+    bool broken = false;
+    for (int t = lane; t < ntiles; t += 32) {
+        ss_true[t] = ss[t];
+        se_true[t] = se[t];
+        broken |= t > 0 && __double_as_longlong(ss[t]) != __double_as_longlong(se[t - 1]);
+    }
+    if (!__any_sync(FULL, broken)) return;
+    __syncwarp();
+    const uint16_t *__restrict__ rms = bp.rms[band] + sd.out_off;
+    const uint32_t *__restrict__ hold = bp.hold[band] + sd.blk_off;
+    double *bend = bp.bend[band] + (size_t)sd.blk_off * 32;
+    const double *__restrict__ curve = pl->curve[band];
+    const BandDev bd = pl->band[band];
+    const bool exact = bd.div_trick != 0;
+    const double A = bd.attack_frames, R = bd.release_frames, rA = bd.r_attack, rR = bd.r_release;
+    // one frame per lane of block `blk` of a tile ending at frame i1: its curve value and the two quotients, and
+    // (every lane the same) the stored state at the end of the block
+    auto fetch = [&](int blk, int i1, double &M, double &inc, double &dec, double &old_end) {
+        const int f = (blk << 5) + lane;
+        const bool held = (hold[blk >> 5] >> (blk & 31)) & 1u;
+        const unsigned r = (!held && f < i1) ? rms[f] : 0u;
+        old_end = bend[blk];
+        M = r ? __ldg(curve + r) : 0.0;
+        inc = div_const(M, A, rA, exact);
+        dec = div_const(M, R, rR, exact);
+    };
+    __shared__ double s_step[4][3][32];           // the block's M, M / A, M / R, read back as broadcasts by the serial steps
+    double (*sw)[32] = s_step[threadIdx.x >> 5];
+    double truth = se[0];                         // tile 0 starts from att = 0 exactly
+    for (int t = 1; t < ntiles; ++t) {
+        if (__double_as_longlong(ss[t]) == __double_as_longlong(truth)) { truth = se[t]; continue; }   // warp-uniform
+        const int i0 = t * P.tile_len, i1 = min(i0 + P.tile_len, sd.out_frames);
+        const int b0 = i0 >> 5, b1 = (i1 + 31) >> 5;
+        double a = truth;
+        bool merged = false;
+        double M, inc, dec, old_end;
+        fetch(b0, i1, M, inc, dec, old_end);
+        int last = b0;                                // the last block whose trajectory differs from the stored one
+        for (int blk = b0; blk < b1; ++blk) {
+            last = blk;
+            const bool any = __any_sync(FULL, __double_as_longlong(M) != 0ll);      // an all-zero block (held) is 32 identity steps
+            if (any) { sw[0][lane] = M; sw[1][lane] = inc; sw[2][lane] = dec; }
+            const double cmp = old_end;
+            __syncwarp();
+            if (blk + 1 < b1) fetch(blk + 1, i1, M, inc, dec, old_end);             // in flight during the steps
+            if (any) {
+                if (exact) {
+#pragma unroll 8
+                    for (int k = 0; k < 32; ++k) a = recur_step_pos(a, sw[0][k], sw[1][k], sw[2][k]);
+                } else {
+#pragma unroll 4
+                    for (int k = 0; k < 32; ++k) a = recur_step(a, sw[0][k], sw[1][k], sw[2][k]);
+                }
+            }
+            __syncwarp();                                                           // the steps have read the block's values
+            if (__double_as_longlong(a) == __double_as_longlong(cmp)) { merged = true; break; }
+            if (lane == 0) bend[blk] = a;                                           // the stored trajectory becomes the true one
+        }
+        // the samples of blocks b0 .. last are to be recomputed: mark the 1024-frame pieces that cover them
+        // (once each: the three bands of a stream mark the same pieces)
+        for (int ft = (b0 >> 5) + lane; ft <= (last >> 5); ft += 32) {
+            const unsigned gidx = (unsigned)s * (unsigned)fine_tiles + (unsigned)ft, bit = 1u << (gidx & 31u);
+            if (!(atomicOr(&fine_bitmap[gidx >> 5], bit) & bit)) fine_list[atomicAdd(fine_count, 1u)] = gidx;
+        }
+        if (lane == 0) { ss_true[t] = truth; atomicAdd(&counters[2], 1ull); }
+        truth = merged ? se[t] : a;
+        if (lane == 0) se_true[t] = truth;
     }
 }
 

@@ -13,6 +13,8 @@ eng = get_engine(0)
 if os.environ.get("WARM") or os.environ.get("TILE"):
     eng.set_recur_tiling(int(os.environ.get("TILE", 0)), int(os.environ.get("WARM", 0)), int(os.environ.get("ROUNDS", -1)))
 st = dict(bass_boost=4.0, mid_cut=3.0, presence_boost=1.0, treble_boost=3.0, saturation=sat, width=1.2, multiband=True, lufs=-14.0)
+if os.environ.get("PRESET") == "pop":           # bench.py's cfg2
+    st.update(bass_boost=2.0, mid_cut=0.0, presence_boost=3.5, treble_boost=2.5)
 t0 = time.time()
 hat = synth.HAT_DENSE if os.environ.get("HAT", "dense") == "dense" else synth.HAT_SPARSE
 track0 = int(os.environ.get("TRACK0", 0))       # first track of the synthetic programme (bench.py's rank r starts at r * tracks_per_gpu)
@@ -32,7 +34,7 @@ t0 = time.time()
 for _ in range(K): step()
 eng.synchronize(); dt = (time.time() - t0) / K
 tot = 0
-for k in ["k_chain", "k_detect", "k_comp", "k_comp_repair", "k_comp_fix", "k_kweight", "k_hops", "k_blocks", "k_gate", "k_final"]:
+for k in ["k_chain", "k_detect", "k_comp", "k_comp_sprint", "k_comp_repair", "k_comp_fix", "k_kweight", "k_hops", "k_blocks", "k_gate", "k_final"]:
     ms, cnt = eng.kernel_time_ms(k); tot += ms / K
     print(f"{k:10s} {ms / K:9.3f} ms/step  ({cnt} launches)")
 print(f"sum {tot:.3f} ms ; wall {dt * 1e3:.3f} ms/step ; RTF {ntracks * seconds / dt:.0f} ; frames {ntracks * n} ; "

@@ -147,7 +147,10 @@ def test_recurrence_tiling_is_exact_for_any_tile_length(eng):
     q1 = port.process_chunk(synth.make_track(41, 6.0, rate), rate, dict(bass_boost=4.0, treble_boost=3.0))
     bands = port.split_bands(q1, rate)
     try:
-        for tile, warm, rounds in [(32, 32, 0), (32, 32, 3), (256, 64, 2), (4096, 1024, 4), (8192, 32768, 1), (0, 0, -1)]:
+        # rounds >= 0: Jacobi repair rounds (+ the sequential backstop); rounds < 0 (automatic): k_comp_sprint carries the
+        # true state through the wrong stretches and the pieces it lists are recomputed in one pass
+        for tile, warm, rounds in [(32, 32, 0), (32, 32, 3), (256, 64, 2), (4096, 1024, 4), (8192, 32768, 1), (0, 0, -1),
+                                   (32, 32, -1), (96, 64, -1), (1056, 256, -1), (4096, 1024, -1)]:
             eng.set_recur_tiling(tile, warm, rounds)
             eng.recur_stats(reset=True)
             for b, (thr, ratio), (att, rel) in zip(bands, port.band_params({"high_thresh": -30.0}), port.BAND_TIMES):
