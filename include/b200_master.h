@@ -127,12 +127,13 @@ int b200m_set_profiling(b200m_handle *h, int on);
 int b200m_kernel_time_ms(b200m_handle *h, const char *kernel, double *total_ms, int64_t *launches);
 int b200m_reset_profile(b200m_handle *h);
 /* Compressor recurrence tiling: each (chunk, band) attenuation chain is cut into time tiles that
- * run in parallel after a warm-up over the preceding `warm_frames` (k_recur_tiles), wrong guesses
- * are repaired in `rounds` parallel passes and finally by an exact sequential pass (k_recur_fix).
+ * run in parallel after a warm-up over the preceding `warm_frames` (k_comp), wrong guesses are
+ * repaired, and an exact sequential pass (k_comp_fix) is the backstop.
  * tile_frames = 0: automatic tile length; warm_frames = 0: automatic: 16384 or 1.75 release times of the band, whichever is more (counted in frames of
- * 32-frame blocks with any activity; silent stretches carry the state unchanged); rounds < 0: automatic, 6 .. 24 by tile length (each round is a
- * list-building launch plus a repair launch over the dirty tiles only: a round with nothing to repair costs microseconds).
- * Results never depend on any of the three. */
+ * 32-frame blocks with any activity; silent stretches carry the state unchanged); rounds < 0: automatic repair -- the true state is carried
+ * through the wrong stretches by the recurrence alone (k_comp_sprint) and the 1024-frame pieces whose samples change are recomputed in one pass;
+ * rounds >= 0: that many Jacobi rounds instead (each a list-building launch plus a re-run of the tiles whose start state was wrong: a round carries
+ * the truth one tile further).  Results never depend on any of the three. */
 int b200m_set_recur_tiling(b200m_handle *h, int tile_frames, int warm_frames, int rounds);
 /* Time segmentation of the filter kernels: k_chain (2048-frame tiles) and k_kweight (4096-sample
  * tiles) cut every stream / track into segments of this many tiles, one CTA each, joined by
