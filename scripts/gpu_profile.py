@@ -10,6 +10,8 @@ seconds = float(sys.argv[2]) if len(sys.argv) > 2 else 180.0
 rate = int(sys.argv[3]) if len(sys.argv) > 3 else 48000
 sat = float(sys.argv[4]) if len(sys.argv) > 4 else 25
 eng = get_engine(0)
+if os.environ.get("WS_GB"):                     # bench.py hands the library what the GPU has free (up to 112 GB): 256-track groups
+    eng.set_workspace_limit(int(float(os.environ["WS_GB"]) * (1 << 30)))
 if os.environ.get("WARM") or os.environ.get("TILE"):
     eng.set_recur_tiling(int(os.environ.get("TILE", 0)), int(os.environ.get("WARM", 0)), int(os.environ.get("ROUNDS", -1)))
 st = dict(bass_boost=4.0, mid_cut=3.0, presence_boost=1.0, treble_boost=3.0, saturation=sat, width=1.2, multiband=True, lufs=-14.0)
